@@ -1,0 +1,135 @@
+/*
+ * w2s.h -- C ABI of the B200-native masked-coalition evaluation path ("wave-to-scores").
+ *
+ * Drop-in boundary for ONE path of HagenMarin/SHAP-Transformer-ASR: the model-evaluation
+ * callback an explainer invokes on masked audio coalitions.  Every entry point names the
+ * reference interface it replaces (paths relative to the reference repo; HF = the
+ * third-party `transformers` package the reference imports).
+ *
+ * Conventions: extern "C", plain pointers and sizes, `int` status (0 = ok, non-zero =
+ * error; text via w2s_last_error) -- no C++ exceptions and no torch types cross this
+ * boundary.  The caller owns every buffer it passes; the handle owns weights, workspace
+ * and plans.  Calls are asynchronous on the given CUDA stream (cudaStream_t passed as
+ * void*), with no hidden device synchronisation unless stated.  One handle per
+ * (device, stream); a handle is not re-entrant.  There is no CPU fallback: every entry
+ * point fails with an error when no sm_100 device is present.
+ */
+#ifndef W2S_H_
+#define W2S_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct w2s_handle w2s_handle;
+
+#define W2S_MAX_CONV_LAYERS 8
+
+/* Output reductions (w2s_set_targets `mode`). */
+enum {
+  W2S_OUT_MAX     = 0, /* max logit per frame           -> [n, T']  shap_calculation.py:50            */
+  W2S_OUT_LOGIT   = 1, /* logits[:, t_d, tok_d]          -> [n, D]   feasability_tests/w2v2conformer.py:40-42 */
+  W2S_OUT_LOGPROB = 2, /* log_softmax(logits)[t_d,tok_d] -> [n, D]   north-star per-character CTC output      */
+  W2S_OUT_MEAN    = 3, /* mean over vocab and time       -> [n, 1]   lime_shap_wav2vec2_comparison.py:68-70   */
+  W2S_OUT_LOGITS  = 4  /* raw logits                     -> [n, T', V]  (target selection, parity tests)      */
+};
+
+/* w2s_config.flags */
+enum {
+  W2S_FLAG_VALIDATE_GEMM = 1, /* run every contraction on the CUDA-core validation kernels (same bf16 data) */
+  W2S_FLAG_VALIDATE_ATTN = 2  /* run attention on the CUDA-core validation kernel                            */
+};
+
+/* Mirrors transformers.Wav2Vec2Config / Wav2Vec2ConformerConfig (the objects the reference
+ * obtains from from_pretrained at shap_calculation.py:218-219, w2v2conformer.py:58-59). */
+typedef struct {
+  int32_t kind;                 /* 0 = Wav2Vec2ForCTC, 1 = Wav2Vec2ConformerForCTC */
+  int32_t num_conv_layers;
+  int32_t conv_dim[W2S_MAX_CONV_LAYERS];
+  int32_t conv_kernel[W2S_MAX_CONV_LAYERS];
+  int32_t conv_stride[W2S_MAX_CONV_LAYERS];
+  int32_t conv_bias;            /* 0 / 1 */
+  int32_t feat_extract_norm;    /* 0 = "group", 1 = "layer" */
+  int32_t hidden_size;
+  int32_t num_hidden_layers;
+  int32_t num_attention_heads;
+  int32_t intermediate_size;
+  int32_t num_conv_pos_embeddings;
+  int32_t num_conv_pos_embedding_groups;
+  int32_t vocab_size;
+  float   layer_norm_eps;
+  int32_t do_stable_layer_norm; /* 0 / 1 */
+  int32_t position_embeddings_type; /* conformer: 0 none, 1 "relative", 2 "rotary" */
+  int32_t conv_depthwise_kernel_size;
+  int32_t hidden_act;           /* 0 = "gelu" (erf form), 1 = "swish" */
+  int32_t rotary_embedding_base;
+  int32_t max_batch;            /* coalitions evaluated per internal batch tile (0 = choose) */
+  int32_t flags;                /* W2S_FLAG_* */
+} w2s_config;
+
+/* Replaces model construction + .to(device) (shap_calculation.py:218-219,258).
+ * `names[i]` are HF state_dict keys ("wav2vec2.feature_extractor.conv_layers.0.conv.weight", ...,
+ * "lm_head.bias"; the weight-normed pos-conv must be passed folded as
+ * "<prefix>encoder.pos_conv_embed.conv.weight"), `ptrs[i]` fp32 DEVICE pointers in the HF layout with
+ * `numels[i]` elements.  Weights are converted/re-laid-out into handle-owned storage; the caller may
+ * free its copies after the call returns (the call synchronises the device once). */
+int w2s_create(const w2s_config* cfg, const char* const* names, const float* const* ptrs,
+               const int64_t* numels, int n_weights, int device, w2s_handle** out);
+
+void w2s_destroy(w2s_handle* h);
+
+/* NULL handle -> message of the last failed w2s_create on this thread. */
+const char* w2s_last_error(const w2s_handle* h);
+
+/* L -> T' (HF wav2vec2/modeling_wav2vec2.py:1005-1024). */
+int64_t w2s_num_frames(const w2s_handle* h, int64_t num_samples);
+
+/* Replaces the masker's captured state (feasability_tests/conformer_test.ipynb:138-141): the already
+ * normalised clip x[L] (fp32, device; copied), the segment partition seg_bounds[M+1] (host, ascending,
+ * seg_bounds[0]=0, seg_bounds[M]=L) and the baseline fill value (0.0 in the reference). */
+int w2s_set_clip(w2s_handle* h, const float* x_dev, int64_t L, const int32_t* seg_bounds_host, int M,
+                 float baseline, void* stream);
+
+/* Replaces timestep_to_explain / token_id_to_explain (w2v2conformer.py:93-110) and the character-frame
+ * list of visualization.py:319-327: D (frame, token) pairs (host arrays; ignored for MAX/MEAN/LOGITS). */
+int w2s_set_targets(w2s_handle* h, const int32_t* frame_idx_host, const int32_t* token_idx_host, int D,
+                    int mode);
+
+/* Number of fp32 values one evaluated row produces under the current mode for clips of L samples. */
+int64_t w2s_out_width(const w2s_handle* h, int64_t num_samples);
+
+/* The fused masker + model callable: coalition bit matrix z_bits[K, ceil(M/32)] (device; bit m of row k
+ * set = segment m KEPT, clear = replaced by the baseline) -> out[K, width] fp32 (device). */
+int w2s_eval(w2s_handle* h, const uint32_t* z_bits_dev, int64_t K, float* out_dev, void* stream);
+
+/* Replaces ModelWrapper.forward (shap_calculation.py:31-50), predict_function
+ * (w2v2conformer.py:116-131) and lime_predict_fn (lime_shap_wav2vec2_comparison.py:60-71) for explicit
+ * waveform rows x[n, L] (fp32, device, row stride `ld` elements) -> out[n, width] fp32 (device). */
+int w2s_eval_waveforms(w2s_handle* h, const float* x_dev, int64_t n, int64_t L, int64_t ld, float* out_dev,
+                       void* stream);
+
+/* Standalone masker (conformer_test.ipynb:138-141 semantics with keep-bits): materialise
+ * out[K, L] = keep ? x : baseline for the clip set by w2s_set_clip. */
+int w2s_mask(w2s_handle* h, const uint32_t* z_bits_dev, int64_t K, float* out_dev, void* stream);
+
+/* KernelSHAP constrained weighted least squares (shap KernelExplainer.solve with l1_reg=False; SURVEY.md
+ * Appendix A step 6): z_bits[K, ceil(M/32)], kernel weights w[K] (fp64), y[K, D] fp32, fx[D], fnull[D]
+ * (fp64) -> phi[M, D] fp64, all device pointers.  `status_dev` (int32, device, may be NULL) receives 0,
+ * or 1 when the normal matrix is not positive definite. */
+int w2s_wls(w2s_handle* h, const uint32_t* z_bits_dev, const double* w_dev, const float* y_dev, int64_t K,
+            int M, int D, const double* fx_dev, const double* fnull_dev, double* phi_dev, int32_t* status_dev,
+            void* stream);
+
+/* Test / profiling hooks for the individual kernels (used by tests/ and bench.py only). */
+int w2s_debug_gemm(int use_tcgen05, const void* a_bf16, const void* w_bf16, const float* bias, void* out,
+                   int M, int N, int K, int act, int out_fp32, void* stream);
+int w2s_kernel_count(const w2s_handle* h, int64_t* launches_per_batch, int64_t* batch_tile);
+/* algorithmic FLOPs (2*MAC) of one coalition forward for clips of L samples */
+double w2s_flops_per_forward(const w2s_handle* h, int64_t num_samples);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* W2S_H_ */

@@ -1,0 +1,778 @@
+// C ABI (include/w2s.h): handle, weight re-layout, workspace, per-batch launch plans and the
+// orchestration of one masked-coalition forward.  Everything below the boundary is CUDA for sm_100a;
+// there is no CPU path.
+#include "../../include/w2s.h"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+using namespace w2s;
+typedef __nv_bfloat16 bf16;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct LayerW {
+  // wav2vec2 encoder layer (post-LN / stable-LN)
+  bf16 *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+  float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+  // conformer extras
+  bf16 *f2w1 = nullptr, *f2w2 = nullptr, *wpos = nullptr, *pw1 = nullptr, *pw2 = nullptr;
+  float *f2b1 = nullptr, *f2b2 = nullptr, *bias_u = nullptr, *bias_v = nullptr;
+  float *lnf1_g = nullptr, *lnf1_b = nullptr, *lnf2_g = nullptr, *lnf2_b = nullptr;
+  float *lnc_g = nullptr, *lnc_b = nullptr, *lnfin_g = nullptr, *lnfin_b = nullptr;
+  float *dw_w = nullptr, *dw_scale = nullptr, *dw_shift = nullptr;  // depthwise taps [H][k], folded BatchNorm
+  bf16* pos_proj = nullptr;  // [2T-1, H], built per clip length
+};
+
+struct Step {
+  std::string name;
+  std::function<std::string(cudaStream_t)> run;
+};
+
+struct Plan {
+  int n = 0;
+  std::vector<Step> steps;
+  std::vector<GemmLaunch*> gemms;
+  std::vector<AttnTcPlan*> attn;
+  ~Plan() {
+    for (auto* g : gemms) delete g;
+    for (auto* a : attn) attention_tc_free(a);
+  }
+};
+
+}  // namespace
+
+struct w2s_handle {
+  w2s_config cfg{};
+  int device = 0;
+  int num_sms = 148;
+  std::string err;
+  std::vector<void*> allocs;      // weights: live until destroy
+  std::vector<void*> ws_allocs;   // workspace: re-made when the clip length changes
+
+  // weights
+  float *conv0_w = nullptr, *conv0_b = nullptr, *norm0_g = nullptr, *norm0_b = nullptr;
+  float *ln0_wbar = nullptr, *ln0_gram = nullptr, *ln0_wb = nullptr;
+  float ln0_bmean = 0.f, ln0_b2mean = 0.f;
+  bf16* conv_w[W2S_MAX_CONV_LAYERS] = {};
+  float* conv_b[W2S_MAX_CONV_LAYERS] = {};
+  float* conv_ln_g[W2S_MAX_CONV_LAYERS] = {};
+  float* conv_ln_b[W2S_MAX_CONV_LAYERS] = {};
+  float *fp_ln_g = nullptr, *fp_ln_b = nullptr, *fp_b = nullptr;
+  bf16* fp_w = nullptr;
+  bf16* pos_w = nullptr;
+  float* pos_b = nullptr;
+  float *enc_ln_g = nullptr, *enc_ln_b = nullptr;
+  std::vector<LayerW> layers;
+  bf16* head_w = nullptr;
+  float* head_b = nullptr;
+
+  // clip state
+  long long L = 0;
+  int M = 0, zwords = 0;
+  float baseline = 0.f;
+  float* clip = nullptr;
+  uint16_t* seg_id = nullptr;
+  long long clip_cap = 0;
+
+  // targets
+  int mode = W2S_OUT_MAX, D = 0, max_frame = 0;
+  int *frames = nullptr, *tokens = nullptr;
+  int targets_cap = 0;
+
+  // workspace (sized for max_batch rows of the current clip length)
+  long long ws_L = -1;
+  int T = 0, Tp = 0;
+  std::vector<int> Tl;  // conv output lengths
+  float* xm = nullptr;
+  long long xm_ld = 0;
+  float *gn_a = nullptr, *gn_b = nullptr;
+  bf16 *bufA = nullptr, *bufB = nullptr;
+  bf16 *fpn = nullptr, *h0 = nullptr, *hp = nullptr, *hb = nullptr, *h1 = nullptr, *qkv = nullptr, *vt = nullptr,
+       *ctx = nullptr, *ffn = nullptr;
+  float* pre = nullptr;
+  double* wls_work = nullptr;
+  long long wls_cap = 0;
+  std::map<int, std::unique_ptr<Plan>> plans;
+
+  // per-call dynamic arguments read by the plan steps at launch time
+  const float* cur_x = nullptr;
+  long long cur_ld = 0;
+  float* cur_out = nullptr;
+
+  ~w2s_handle() {
+    plans.clear();
+    for (void* p : ws_allocs) cudaFree(p);
+    for (void* p : allocs) cudaFree(p);
+  }
+};
+
+namespace {
+
+template <typename T>
+std::string dalloc(std::vector<void*>& pool, T** out, size_t count, bool zero = false) {
+  void* p = nullptr;
+  const size_t bytes = count * sizeof(T) + 65536;  // slack: strided-conv views may touch a few rows past the end
+  W2S_CUDA_OK(cudaMalloc(&p, bytes));
+  if (zero) W2S_CUDA_OK(cudaMemset(p, 0, bytes));
+  pool.push_back(p);
+  *out = reinterpret_cast<T*>(p);
+  return "";
+}
+
+struct WeightTable {
+  std::map<std::string, std::pair<const float*, int64_t>> t;
+  std::string prefix;
+  std::string get(const std::string& name, int64_t expect, const float** out) const {
+    auto it = t.find(name);
+    if (it == t.end()) return "missing weight '" + name + "'";
+    if (expect >= 0 && it->second.second != expect)
+      return "weight '" + name + "' has " + std::to_string(it->second.second) + " elements, expected " +
+             std::to_string(expect);
+    *out = it->second.first;
+    return "";
+  }
+  bool has(const std::string& name) const { return t.count(name) != 0; }
+};
+
+std::string copy_f32(w2s_handle* h, const WeightTable& wt, const std::string& name, int64_t n, float** dst) {
+  const float* src = nullptr;
+  W2S_TRY(wt.get(name, n, &src));
+  W2S_TRY(dalloc(h->allocs, dst, (size_t)n));
+  W2S_CUDA_OK(cudaMemcpy(*dst, src, sizeof(float) * n, cudaMemcpyDeviceToDevice));
+  return "";
+}
+std::string copy_bf16(w2s_handle* h, const WeightTable& wt, const std::string& name, int64_t n, bf16* dst) {
+  const float* src = nullptr;
+  W2S_TRY(wt.get(name, n, &src));
+  return launch_cast_bf16(src, dst, n, 0);
+}
+
+std::string load_weights(w2s_handle* h, const WeightTable& wt) {
+  const w2s_config& c = h->cfg;
+  const std::string P = wt.prefix;
+  const int H = c.hidden_size, I = c.intermediate_size, V = c.vocab_size;
+  const bool layer = c.feat_extract_norm == 1;
+  // ---- feature encoder ----
+  for (int l = 0; l < c.num_conv_layers; ++l) {
+    const std::string cp = P + "feature_extractor.conv_layers." + std::to_string(l) + ".";
+    const int Cin = l == 0 ? 1 : c.conv_dim[l - 1], Cout = c.conv_dim[l], kw = c.conv_kernel[l];
+    if (l == 0) {
+      W2S_TRY(copy_f32(h, wt, cp + "conv.weight", (int64_t)Cout * kw, &h->conv0_w));
+      if (c.conv_bias) W2S_TRY(copy_f32(h, wt, cp + "conv.bias", Cout, &h->conv0_b));
+      W2S_TRY(copy_f32(h, wt, cp + "layer_norm.weight", Cout, &h->norm0_g));
+      W2S_TRY(copy_f32(h, wt, cp + "layer_norm.bias", Cout, &h->norm0_b));
+      if (layer) {
+        W2S_TRY(dalloc(h->allocs, &h->ln0_wbar, 16));
+        W2S_TRY(dalloc(h->allocs, &h->ln0_gram, 256));
+        W2S_TRY(dalloc(h->allocs, &h->ln0_wb, 16));
+        float* sc = nullptr;
+        W2S_TRY(dalloc(h->allocs, &sc, 2));
+        W2S_TRY(launch_conv0_ln_prep(h->conv0_w, h->conv0_b, Cout, kw, h->ln0_wbar, h->ln0_gram, h->ln0_wb, sc, 0));
+        float hs[2];
+        W2S_CUDA_OK(cudaMemcpy(hs, sc, sizeof(hs), cudaMemcpyDeviceToHost));
+        h->ln0_bmean = hs[0];
+        h->ln0_b2mean = hs[1];
+      }
+    } else {
+      const float* src = nullptr;
+      W2S_TRY(wt.get(cp + "conv.weight", (int64_t)Cout * Cin * kw, &src));
+      W2S_TRY(dalloc(h->allocs, &h->conv_w[l], (size_t)Cout * Cin * kw));
+      W2S_TRY(launch_repack_conv(src, h->conv_w[l], Cout, Cin, kw, 0));
+      if (c.conv_bias) W2S_TRY(copy_f32(h, wt, cp + "conv.bias", Cout, &h->conv_b[l]));
+      if (layer) {
+        W2S_TRY(copy_f32(h, wt, cp + "layer_norm.weight", Cout, &h->conv_ln_g[l]));
+        W2S_TRY(copy_f32(h, wt, cp + "layer_norm.bias", Cout, &h->conv_ln_b[l]));
+      }
+    }
+  }
+  // ---- feature projection ----
+  const int Cl = c.conv_dim[c.num_conv_layers - 1];
+  W2S_TRY(copy_f32(h, wt, P + "feature_projection.layer_norm.weight", Cl, &h->fp_ln_g));
+  W2S_TRY(copy_f32(h, wt, P + "feature_projection.layer_norm.bias", Cl, &h->fp_ln_b));
+  W2S_TRY(dalloc(h->allocs, &h->fp_w, (size_t)H * Cl));
+  W2S_TRY(copy_bf16(h, wt, P + "feature_projection.projection.weight", (int64_t)H * Cl, h->fp_w));
+  W2S_TRY(copy_f32(h, wt, P + "feature_projection.projection.bias", H, &h->fp_b));
+  // ---- encoder ----
+  W2S_TRY(copy_f32(h, wt, P + "encoder.layer_norm.weight", H, &h->enc_ln_g));
+  W2S_TRY(copy_f32(h, wt, P + "encoder.layer_norm.bias", H, &h->enc_ln_b));
+  h->layers.resize(c.num_hidden_layers);
+  if (c.kind == 0) {
+    const int G = c.num_conv_pos_embedding_groups, kp = c.num_conv_pos_embeddings, cpg = H / G;
+    const float* src = nullptr;
+    W2S_TRY(wt.get(P + "encoder.pos_conv_embed.conv.weight", (int64_t)H * cpg * kp, &src));
+    W2S_TRY(dalloc(h->allocs, &h->pos_w, (size_t)H * kp * 64));
+    W2S_TRY(launch_repack_posconv(src, h->pos_w, H, G, kp, 0));
+    W2S_TRY(copy_f32(h, wt, P + "encoder.pos_conv_embed.conv.bias", H, &h->pos_b));
+    for (int l = 0; l < c.num_hidden_layers; ++l) {
+      LayerW& w = h->layers[l];
+      const std::string lp = P + "encoder.layers." + std::to_string(l) + ".";
+      W2S_TRY(dalloc(h->allocs, &w.wqkv, (size_t)3 * H * H));
+      W2S_TRY(copy_bf16(h, wt, lp + "attention.q_proj.weight", (int64_t)H * H, w.wqkv));
+      W2S_TRY(copy_bf16(h, wt, lp + "attention.k_proj.weight", (int64_t)H * H, w.wqkv + (size_t)H * H));
+      W2S_TRY(copy_bf16(h, wt, lp + "attention.v_proj.weight", (int64_t)H * H, w.wqkv + (size_t)2 * H * H));
+      W2S_TRY(dalloc(h->allocs, &w.bqkv, (size_t)3 * H));
+      const float* b = nullptr;
+      const char* nm[3] = {"attention.q_proj.bias", "attention.k_proj.bias", "attention.v_proj.bias"};
+      for (int j = 0; j < 3; ++j) {
+        W2S_TRY(wt.get(lp + nm[j], H, &b));
+        W2S_CUDA_OK(cudaMemcpy(w.bqkv + (size_t)j * H, b, sizeof(float) * H, cudaMemcpyDeviceToDevice));
+      }
+      W2S_TRY(dalloc(h->allocs, &w.wo, (size_t)H * H));
+      W2S_TRY(copy_bf16(h, wt, lp + "attention.out_proj.weight", (int64_t)H * H, w.wo));
+      W2S_TRY(copy_f32(h, wt, lp + "attention.out_proj.bias", H, &w.bo));
+      W2S_TRY(copy_f32(h, wt, lp + "layer_norm.weight", H, &w.ln1_g));
+      W2S_TRY(copy_f32(h, wt, lp + "layer_norm.bias", H, &w.ln1_b));
+      W2S_TRY(dalloc(h->allocs, &w.w1, (size_t)I * H));
+      W2S_TRY(copy_bf16(h, wt, lp + "feed_forward.intermediate_dense.weight", (int64_t)I * H, w.w1));
+      W2S_TRY(copy_f32(h, wt, lp + "feed_forward.intermediate_dense.bias", I, &w.b1));
+      W2S_TRY(dalloc(h->allocs, &w.w2, (size_t)H * I));
+      W2S_TRY(copy_bf16(h, wt, lp + "feed_forward.output_dense.weight", (int64_t)H * I, w.w2));
+      W2S_TRY(copy_f32(h, wt, lp + "feed_forward.output_dense.bias", H, &w.b2));
+      W2S_TRY(copy_f32(h, wt, lp + "final_layer_norm.weight", H, &w.ln2_g));
+      W2S_TRY(copy_f32(h, wt, lp + "final_layer_norm.bias", H, &w.ln2_b));
+    }
+  } else {
+    return "Wav2Vec2ConformerForCTC weights: conformer encoder is not built into this library yet";
+  }
+  W2S_TRY(dalloc(h->allocs, &h->head_w, (size_t)V * H));
+  W2S_TRY(copy_bf16(h, wt, "lm_head.weight", (int64_t)V * H, h->head_w));
+  W2S_TRY(copy_f32(h, wt, "lm_head.bias", V, &h->head_b));
+  W2S_CUDA_OK(cudaDeviceSynchronize());
+  return "";
+}
+
+int64_t num_frames(const w2s_config& c, int64_t L, std::vector<int>* lens) {
+  int64_t n = L;
+  for (int l = 0; l < c.num_conv_layers; ++l) {
+    if (n < c.conv_kernel[l]) return 0;
+    n = (n - c.conv_kernel[l]) / c.conv_stride[l] + 1;
+    if (lens) lens->push_back((int)n);
+  }
+  return n;
+}
+
+void free_workspace(w2s_handle* h) {
+  h->plans.clear();
+  for (void* p : h->ws_allocs) cudaFree(p);
+  h->ws_allocs.clear();
+  h->ws_L = -1;
+}
+
+std::string ensure_workspace(w2s_handle* h, long long L) {
+  if (h->ws_L == L) return "";
+  cudaDeviceSynchronize();
+  free_workspace(h);
+  const w2s_config& c = h->cfg;
+  h->Tl.clear();
+  const int64_t T = num_frames(c, L, &h->Tl);
+  if (T <= 0) return "clip of " + std::to_string(L) + " samples is shorter than the conv receptive field";
+  h->T = (int)T;
+  h->Tp = (int)((T + 63) / 64 * 64);
+  const size_t nb = (size_t)c.max_batch;
+  const int H = c.hidden_size, I = c.intermediate_size;
+  const int Cl = c.conv_dim[c.num_conv_layers - 1];
+  auto& pool = h->ws_allocs;
+  h->xm_ld = (L + 3) / 4 * 4;
+  W2S_TRY(dalloc(pool, &h->xm, nb * h->xm_ld));
+  W2S_TRY(dalloc(pool, &h->gn_a, nb * c.conv_dim[0]));
+  W2S_TRY(dalloc(pool, &h->gn_b, nb * c.conv_dim[0]));
+  size_t szA = 0, szB = 0;
+  for (int l = 0; l < c.num_conv_layers; ++l) {
+    const size_t s = nb * (size_t)h->Tl[l] * c.conv_dim[l];
+    if (l % 2 == 0) szA = s > szA ? s : szA;
+    else szB = s > szB ? s : szB;
+  }
+  W2S_TRY(dalloc(pool, &h->bufA, szA));
+  W2S_TRY(dalloc(pool, &h->bufB, szB ? szB : 1));
+  const size_t rows = nb * (size_t)T;
+  W2S_TRY(dalloc(pool, &h->fpn, rows * Cl));
+  W2S_TRY(dalloc(pool, &h->h0, rows * H));
+  W2S_TRY(dalloc(pool, &h->hb, rows * H));
+  W2S_TRY(dalloc(pool, &h->h1, rows * H));
+  W2S_TRY(dalloc(pool, &h->pre, rows * H));
+  W2S_TRY(dalloc(pool, &h->qkv, rows * 3 * H));
+  W2S_TRY(dalloc(pool, &h->ctx, rows * H));
+  W2S_TRY(dalloc(pool, &h->ffn, rows * I));
+  W2S_TRY(dalloc(pool, &h->vt, nb * (size_t)H * h->Tp, /*zero=*/true));
+  if (c.kind == 0) {
+    W2S_TRY(dalloc(pool, &h->hp,
+                   nb * (size_t)(T + c.num_conv_pos_embeddings) * c.num_conv_pos_embedding_groups * 64));
+  }
+  h->ws_L = L;
+  return "";
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan construction: every launch of one batch-tile forward, with tensor maps encoded once
+// ------------------------------------------------------------------------------------------------
+struct PlanBuilder {
+  w2s_handle* h;
+  Plan* plan;
+  int n;
+  bool simt_gemm, simt_attn;
+
+  std::string add_gemm(const std::string& name, const GemmProblem& p) {
+    GemmLaunch* gl = new GemmLaunch();
+    plan->gemms.push_back(gl);
+    W2S_TRY(gemm_prepare(p, h->num_sms, gl));
+    const bool simt = simt_gemm;
+    plan->steps.push_back({name, [gl, simt](cudaStream_t s) { return simt ? gemm_launch_simt(*gl, s) : gemm_launch_tc(*gl, s); }});
+    return "";
+  }
+  void add(const std::string& name, std::function<std::string(cudaStream_t)> f) {
+    plan->steps.push_back({name, std::move(f)});
+  }
+  std::string add_ln(const std::string& name, const void* in, int in_fp32, long long rows, int H, const float* g,
+                     const float* b, float eps, int act, bf16* out, float* out_f32) {
+    add(name, [=](cudaStream_t s) { return launch_layernorm(in, in_fp32, rows, H, g, b, eps, act, out, out_f32, s); });
+    return "";
+  }
+  static GemmProblem plain(const bf16* a, long long rows, int K, const bf16* w, int N) {
+    GemmProblem p;
+    p.a = a; p.a_cols = K; p.a_rows = rows; p.a_batches = 1; p.a_row_stride = K; p.a_batch_stride = rows * (long long)K;
+    p.a_kb_per_row = K / 64; p.a_g_col = 0;
+    p.w = w; p.M = (int)rows; p.N = N; p.K = K; p.Bz = 1; p.G = 1;
+    p.epi.ldg = 0; p.epi.ldb = 0; p.epi.ldm = N;
+    return p;
+  }
+
+  std::string build() {
+    const w2s_config& c = h->cfg;
+    const int T = h->T, H = c.hidden_size, I = c.intermediate_size;
+    const bool layer = c.feat_extract_norm == 1;
+    const long long rows = (long long)n * T;
+    w2s_handle* hh = h;
+    const int nn = n;
+
+    // ---- K1: conv0 + norm + GELU -------------------------------------------------------------------
+    {
+      Conv0Params cp{};
+      cp.n = n; cp.L = (int)h->ws_L; cp.T0 = h->Tl[0]; cp.C = c.conv_dim[0]; cp.kw = c.conv_kernel[0];
+      cp.stride = c.conv_stride[0];
+      cp.w = h->conv0_w; cp.bias = h->conv0_b; cp.gamma = h->norm0_g; cp.beta = h->norm0_b;
+      cp.gn_a = h->gn_a; cp.gn_b = h->gn_b;
+      cp.ln_wbar = h->ln0_wbar; cp.ln_gram = h->ln0_gram; cp.ln_wb = h->ln0_wb;
+      cp.ln_bmean = h->ln0_bmean; cp.ln_b2mean = h->ln0_b2mean;
+      cp.out = h->bufA;
+      if (!layer)
+        add("conv0_stats", [=](cudaStream_t s) {
+          Conv0Params q = cp;
+          q.x = hh->cur_x; q.ld = hh->cur_ld;
+          return launch_conv0_stats(q, s);
+        });
+      add("conv0", [=](cudaStream_t s) {
+        Conv0Params q = cp;
+        q.x = hh->cur_x; q.ld = hh->cur_ld;
+        return launch_conv0(q, layer, s);
+      });
+    }
+    // ---- K2: conv1..6 as implicit GEMM over the stride-row view of the previous layer ---------------------
+    bf16* cur = h->bufA;
+    for (int l = 1; l < c.num_conv_layers; ++l) {
+      bf16* nxt = (l % 2 == 1) ? h->bufB : h->bufA;
+      const int Cin = c.conv_dim[l - 1], Cout = c.conv_dim[l], kw = c.conv_kernel[l], st = c.conv_stride[l];
+      const int Tin = h->Tl[l - 1], Tout = h->Tl[l];
+      if ((st * Cin) % 64) return "conv layer " + std::to_string(l) + ": stride * in_channels must be a multiple of 64";
+      GemmProblem p;
+      p.a = cur; p.a_cols = (long long)st * Cin; p.a_rows = (Tin + st - 1) / st; p.a_batches = n;
+      p.a_row_stride = (long long)st * Cin; p.a_batch_stride = (long long)Tin * Cin;
+      p.a_kb_per_row = st * Cin / 64; p.a_g_col = 0;
+      p.w = h->conv_w[l]; p.M = Tout; p.N = Cout; p.K = kw * Cin; p.Bz = n; p.G = 1;
+      p.epi.bias = h->conv_b[l];
+      p.epi.act = layer ? ACT_NONE : ACT_GELU;
+      p.epi.out = nxt; p.epi.ldb = (long long)Tout * Cout; p.epi.ldm = Cout;
+      W2S_TRY(add_gemm("conv" + std::to_string(l), p));
+      if (layer)
+        add_ln("conv" + std::to_string(l) + "_ln_gelu", nxt, 0, (long long)n * Tout, Cout, h->conv_ln_g[l],
+               h->conv_ln_b[l], 1e-5f, ACT_GELU, nxt, nullptr);
+      cur = nxt;
+    }
+    // ---- K3: feature projection ---------------------------------------------------------------------------
+    const int Cl = c.conv_dim[c.num_conv_layers - 1];
+    add_ln("featproj_ln", cur, 0, rows, Cl, h->fp_ln_g, h->fp_ln_b, c.layer_norm_eps, ACT_NONE, h->fpn, nullptr);
+    {
+      GemmProblem p = plain(h->fpn, rows, Cl, h->fp_w, H);
+      p.epi.bias = h->fp_b;
+      p.epi.out = h->h0;
+      W2S_TRY(add_gemm("featproj", p));
+    }
+    if (c.kind != 0) return "conformer encoder not built yet";
+    const bool stable = c.do_stable_layer_norm != 0;
+    // ---- K4: positional conv (grouped, k=128) + GELU + residual (+ LayerNorm) ----------------------------
+    {
+      const int G = c.num_conv_pos_embedding_groups, kp = c.num_conv_pos_embeddings, cpg = H / G;
+      add("pos_pad", [=](cudaStream_t s) { return launch_pos_pad(hh->h0, nn, T, H, G, kp, hh->hp, s); });
+      GemmProblem p;
+      p.a = h->hp; p.a_cols = (long long)G * 64; p.a_rows = T + kp; p.a_batches = n;
+      p.a_row_stride = (long long)G * 64; p.a_batch_stride = (long long)(T + kp) * G * 64;
+      p.a_kb_per_row = 1; p.a_g_col = 64;
+      p.w = h->pos_w; p.M = T; p.N = cpg; p.K = kp * 64; p.Bz = n; p.G = G;
+      p.epi.bias = h->pos_b; p.epi.act = ACT_GELU;
+      p.epi.residual = h->h0; p.epi.res_fp32 = 0;
+      p.epi.out = h->pre; p.epi.out_fp32 = 1;
+      p.epi.ldg = cpg; p.epi.ldb = (long long)T * H; p.epi.ldm = H;
+      W2S_TRY(add_gemm("pos_conv", p));
+      if (!stable)
+        add_ln("encoder_ln", h->pre, 1, rows, H, h->enc_ln_g, h->enc_ln_b, c.layer_norm_eps, ACT_NONE, h->hb, nullptr);
+    }
+    // ---- K5-K8: transformer layers ------------------------------------------------------------------------
+    AttnParams ap{};
+    ap.qkv = h->qkv; ap.vt = h->vt; ap.ctx = h->ctx; ap.B = n; ap.T = T; ap.Tp = h->Tp; ap.H = H;
+    ap.heads = c.num_attention_heads; ap.hd = H / c.num_attention_heads;
+    ap.scale = 1.0f / sqrtf((float)ap.hd);
+    const bool tc_attn = !simt_attn && attention_tc_supported(ap);
+    AttnTcPlan* apl = nullptr;
+    if (tc_attn) {
+      W2S_TRY(attention_tc_prepare(ap, &apl));
+      plan->attn.push_back(apl);
+    }
+    const int act = c.hidden_act == 1 ? ACT_SWISH : ACT_GELU;
+    for (int l = 0; l < c.num_hidden_layers; ++l) {
+      const LayerW& w = h->layers[l];
+      const std::string ls = "L" + std::to_string(l) + ".";
+      if (stable) add_ln(ls + "ln1", h->pre, 1, rows, H, w.ln1_g, w.ln1_b, c.layer_norm_eps, ACT_NONE, h->hb, nullptr);
+      {
+        GemmProblem p = plain(h->hb, rows, H, w.wqkv, 3 * H);
+        p.epi.bias = w.bqkv;
+        p.epi.out = h->qkv;
+        if (tc_attn) {
+          p.epi.vt = h->vt; p.epi.vt_n0 = 2 * H; p.epi.vt_T = T; p.epi.vt_Tp = h->Tp;
+          p.epi.vt_heads = ap.heads; p.epi.vt_hd = ap.hd;
+        }
+        W2S_TRY(add_gemm(ls + "qkv", p));
+      }
+      if (tc_attn) add(ls + "attention", [=](cudaStream_t s) { return attention_tc_launch(apl, s); });
+      else add(ls + "attention", [=](cudaStream_t s) { return launch_attention_simt(ap, s); });
+      {
+        GemmProblem p = plain(h->ctx, rows, H, w.wo, H);
+        p.epi.bias = w.bo;
+        p.epi.residual = stable ? (const void*)h->pre : (const void*)h->hb;
+        p.epi.res_fp32 = stable ? 1 : 0;
+        p.epi.out = h->pre; p.epi.out_fp32 = 1;
+        W2S_TRY(add_gemm(ls + "out_proj", p));
+      }
+      if (stable) add_ln(ls + "ln2", h->pre, 1, rows, H, w.ln2_g, w.ln2_b, c.layer_norm_eps, ACT_NONE, h->h1, nullptr);
+      else add_ln(ls + "ln1", h->pre, 1, rows, H, w.ln1_g, w.ln1_b, c.layer_norm_eps, ACT_NONE, h->h1, nullptr);
+      {
+        GemmProblem p = plain(h->h1, rows, H, w.w1, I);
+        p.epi.bias = w.b1; p.epi.act = act;
+        p.epi.out = h->ffn;
+        W2S_TRY(add_gemm(ls + "ffn1", p));
+      }
+      {
+        GemmProblem p = plain(h->ffn, rows, I, w.w2, H);
+        p.epi.bias = w.b2;
+        p.epi.residual = stable ? (const void*)h->pre : (const void*)h->h1;
+        p.epi.res_fp32 = stable ? 1 : 0;
+        p.epi.out = h->pre; p.epi.out_fp32 = 1;
+        W2S_TRY(add_gemm(ls + "ffn2", p));
+      }
+      if (!stable) add_ln(ls + "ln2", h->pre, 1, rows, H, w.ln2_g, w.ln2_b, c.layer_norm_eps, ACT_NONE, h->hb, nullptr);
+    }
+    if (stable)
+      add_ln("encoder_ln", h->pre, 1, rows, H, h->enc_ln_g, h->enc_ln_b, c.layer_norm_eps, ACT_NONE, h->hb, nullptr);
+    // ---- K9: lm_head + reduction ---------------------------------------------------------------------------
+    add("head", [=](cudaStream_t s) {
+      HeadParams hp{};
+      hp.h = hh->hb; hp.w = hh->head_w; hp.bias = hh->head_b;
+      hp.n = nn; hp.T = T; hp.H = H; hp.V = hh->cfg.vocab_size; hp.mode = hh->mode; hp.D = hh->D;
+      hp.frames = hh->frames; hp.tokens = hh->tokens; hp.out = hh->cur_out;
+      return launch_head(hp, s);
+    });
+    return "";
+  }
+};
+
+std::string get_plan(w2s_handle* h, int n, Plan** out) {
+  auto it = h->plans.find(n);
+  if (it != h->plans.end()) {
+    *out = it->second.get();
+    return "";
+  }
+  std::unique_ptr<Plan> pl(new Plan());
+  pl->n = n;
+  PlanBuilder b{h, pl.get(), n, (h->cfg.flags & W2S_FLAG_VALIDATE_GEMM) != 0, (h->cfg.flags & W2S_FLAG_VALIDATE_ATTN) != 0};
+  W2S_TRY(b.build());
+  *out = pl.get();
+  h->plans[n] = std::move(pl);
+  return "";
+}
+
+int64_t out_width(const w2s_handle* h, int64_t L) {
+  const int64_t T = num_frames(h->cfg, L, nullptr);
+  switch (h->mode) {
+    case W2S_OUT_MAX: return T;
+    case W2S_OUT_MEAN: return 1;
+    case W2S_OUT_LOGITS: return T * h->cfg.vocab_size;
+    default: return h->D;
+  }
+}
+
+std::string run_batches(w2s_handle* h, const uint32_t* zbits, const float* x, long long ld, int64_t K, float* out,
+                        cudaStream_t s) {
+  const int64_t width = out_width(h, h->ws_L);
+  if (width <= 0) return "no outputs selected (w2s_set_targets)";
+  for (int64_t k0 = 0; k0 < K; k0 += h->cfg.max_batch) {
+    const int n = (int)((K - k0) < h->cfg.max_batch ? (K - k0) : h->cfg.max_batch);
+    Plan* pl = nullptr;
+    W2S_TRY(get_plan(h, n, &pl));
+    if (zbits) {
+      W2S_TRY(launch_mask(h->clip, h->seg_id, zbits + k0 * h->zwords, h->zwords, n, h->L, h->baseline, h->xm,
+                          h->xm_ld, s));
+      h->cur_x = h->xm;
+      h->cur_ld = h->xm_ld;
+    } else {
+      h->cur_x = x + k0 * ld;
+      h->cur_ld = ld;
+    }
+    h->cur_out = out + k0 * width;
+    for (const Step& st : pl->steps) {
+      std::string e = st.run(s);
+      if (!e.empty()) return st.name + ": " + e;
+    }
+  }
+  return "";
+}
+
+int fail(w2s_handle* h, const std::string& e) {
+  h->err = e;
+  return 1;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int w2s_create(const w2s_config* cfg, const char* const* names, const float* const* ptrs, const int64_t* numels,
+               int n_weights, int device, w2s_handle** out) {
+  g_create_error.clear();
+  if (!cfg || !out) {
+    g_create_error = "null argument";
+    return 1;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    g_create_error = "no CUDA device: this library has no CPU path";
+    return 1;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) {
+    g_create_error = "cudaSetDevice failed";
+    return 1;
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) {
+    g_create_error = std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                     std::to_string(prop.minor) + "; this library is built for sm_100a only";
+    return 1;
+  }
+  std::unique_ptr<w2s_handle> h(new w2s_handle());
+  h->cfg = *cfg;
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  if (h->cfg.max_batch <= 0) h->cfg.max_batch = 64;
+  if (cfg->num_conv_layers < 1 || cfg->num_conv_layers > W2S_MAX_CONV_LAYERS) {
+    g_create_error = "num_conv_layers out of range";
+    return 1;
+  }
+  if (cfg->hidden_size % cfg->num_attention_heads) {
+    g_create_error = "hidden_size must be divisible by num_attention_heads";
+    return 1;
+  }
+  std::string e = gemm_init();
+  if (e.empty()) e = attention_tc_init();
+  if (e.empty()) {
+    WeightTable wt;
+    wt.prefix = cfg->kind == 1 ? "wav2vec2_conformer." : "wav2vec2.";
+    for (int i = 0; i < n_weights; ++i) wt.t[names[i]] = {ptrs[i], numels[i]};
+    e = load_weights(h.get(), wt);
+  }
+  if (!e.empty()) {
+    g_create_error = e;
+    return 1;
+  }
+  *out = h.release();
+  return 0;
+}
+
+void w2s_destroy(w2s_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  delete h;
+}
+
+const char* w2s_last_error(const w2s_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int64_t w2s_num_frames(const w2s_handle* h, int64_t num_samples) { return num_frames(h->cfg, num_samples, nullptr); }
+
+int w2s_set_clip(w2s_handle* h, const float* x_dev, int64_t L, const int32_t* seg_bounds_host, int M, float baseline,
+                 void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (L <= 0 || M <= 0 || M > 2048) return fail(h, "set_clip: need L > 0 and 1 <= M <= 2048");
+  if (seg_bounds_host[0] != 0 || seg_bounds_host[M] != L) return fail(h, "set_clip: seg_bounds must span [0, L]");
+  std::vector<uint16_t> seg((size_t)L);
+  for (int m = 0; m < M; ++m) {
+    if (seg_bounds_host[m + 1] < seg_bounds_host[m]) return fail(h, "set_clip: seg_bounds must be ascending");
+    for (int64_t i = seg_bounds_host[m]; i < seg_bounds_host[m + 1]; ++i) seg[(size_t)i] = (uint16_t)m;
+  }
+  std::string e = ensure_workspace(h, L);
+  if (!e.empty()) return fail(h, e);
+  if (h->clip_cap < L) {
+    if (h->clip) cudaFree(h->clip);
+    if (h->seg_id) cudaFree(h->seg_id);
+    if (cudaMalloc((void**)&h->clip, sizeof(float) * (L + 16)) != cudaSuccess ||
+        cudaMalloc((void**)&h->seg_id, sizeof(uint16_t) * (L + 16)) != cudaSuccess)
+      return fail(h, "set_clip: out of device memory");
+    h->clip_cap = L;
+  }
+  if (cudaMemcpyAsync(h->clip, x_dev, sizeof(float) * L, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
+      cudaMemcpyAsync(h->seg_id, seg.data(), sizeof(uint16_t) * L, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+      cudaStreamSynchronize(s) != cudaSuccess)
+    return fail(h, std::string("set_clip: copy failed: ") + cudaGetErrorString(cudaGetLastError()));
+  h->L = L;
+  h->M = M;
+  h->zwords = (M + 31) / 32;
+  h->baseline = baseline;
+  return 0;
+}
+
+int w2s_set_targets(w2s_handle* h, const int32_t* frame_idx_host, const int32_t* token_idx_host, int D, int mode) {
+  if (mode < W2S_OUT_MAX || mode > W2S_OUT_LOGITS) return fail(h, "set_targets: unknown mode");
+  h->mode = mode;
+  if (mode == W2S_OUT_LOGIT || mode == W2S_OUT_LOGPROB) {
+    if (D <= 0 || !frame_idx_host || !token_idx_host) return fail(h, "set_targets: need D > 0 (frame, token) pairs");
+    for (int d = 0; d < D; ++d)
+      if (token_idx_host[d] < 0 || token_idx_host[d] >= h->cfg.vocab_size || frame_idx_host[d] < 0)
+        return fail(h, "set_targets: target out of range");
+    if (h->targets_cap < D) {
+      if (h->frames) cudaFree(h->frames);
+      if (h->tokens) cudaFree(h->tokens);
+      if (cudaMalloc((void**)&h->frames, sizeof(int) * D) != cudaSuccess ||
+          cudaMalloc((void**)&h->tokens, sizeof(int) * D) != cudaSuccess)
+        return fail(h, "set_targets: out of device memory");
+      h->targets_cap = D;
+    }
+    if (cudaMemcpy(h->frames, frame_idx_host, sizeof(int) * D, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(h->tokens, token_idx_host, sizeof(int) * D, cudaMemcpyHostToDevice) != cudaSuccess)
+      return fail(h, "set_targets: copy failed");
+    h->D = D;
+    h->max_frame = 0;
+    for (int d = 0; d < D; ++d) h->max_frame = frame_idx_host[d] > h->max_frame ? frame_idx_host[d] : h->max_frame;
+  } else {
+    h->D = 0;
+  }
+  return 0;
+}
+
+int64_t w2s_out_width(const w2s_handle* h, int64_t num_samples) { return out_width(h, num_samples); }
+
+int w2s_eval(w2s_handle* h, const uint32_t* z_bits_dev, int64_t K, float* out_dev, void* stream) {
+  if (h->L <= 0) return fail(h, "eval: no clip set (w2s_set_clip)");
+  if (!z_bits_dev || !out_dev) return fail(h, "eval: null buffer");
+  if ((h->mode == W2S_OUT_LOGIT || h->mode == W2S_OUT_LOGPROB) && h->max_frame >= h->T)
+    return fail(h, "eval: target frame beyond the clip's " + std::to_string(h->T) + " frames");
+  std::string e = ensure_workspace(h, h->L);
+  if (e.empty()) e = run_batches(h, z_bits_dev, nullptr, 0, K, out_dev, (cudaStream_t)stream);
+  return e.empty() ? 0 : fail(h, e);
+}
+
+int w2s_eval_waveforms(w2s_handle* h, const float* x_dev, int64_t n, int64_t L, int64_t ld, float* out_dev,
+                       void* stream) {
+  if (!x_dev || !out_dev) return fail(h, "eval_waveforms: null buffer");
+  if (ld < L) return fail(h, "eval_waveforms: row stride smaller than the row length");
+  std::string e = ensure_workspace(h, L);
+  if (e.empty() && (h->mode == W2S_OUT_LOGIT || h->mode == W2S_OUT_LOGPROB) && h->max_frame >= h->T)
+    e = "target frame beyond the clip's " + std::to_string(h->T) + " frames";
+  if (e.empty()) e = run_batches(h, nullptr, x_dev, ld, n, out_dev, (cudaStream_t)stream);
+  return e.empty() ? 0 : fail(h, e);
+}
+
+int w2s_mask(w2s_handle* h, const uint32_t* z_bits_dev, int64_t K, float* out_dev, void* stream) {
+  if (h->L <= 0) return fail(h, "mask: no clip set (w2s_set_clip)");
+  std::string e = launch_mask(h->clip, h->seg_id, z_bits_dev, h->zwords, K, h->L, h->baseline, out_dev, h->L,
+                              (cudaStream_t)stream);
+  return e.empty() ? 0 : fail(h, e);
+}
+
+int w2s_wls(w2s_handle* h, const uint32_t* z_bits_dev, const double* w_dev, const float* y_dev, int64_t K, int M,
+            int D, const double* fx_dev, const double* fnull_dev, double* phi_dev, int32_t* status_dev, void* stream) {
+  const long long need = (long long)(M - 1) * (M - 1) + (long long)(M - 1) * D;
+  if (h->wls_cap < need) {
+    cudaStreamSynchronize((cudaStream_t)stream);
+    if (h->wls_work) cudaFree(h->wls_work);
+    if (cudaMalloc((void**)&h->wls_work, sizeof(double) * need) != cudaSuccess) return fail(h, "wls: out of device memory");
+    h->wls_cap = need;
+  }
+  std::string e = launch_wls(z_bits_dev, (M + 31) / 32, w_dev, y_dev, K, M, D, fx_dev, fnull_dev, phi_dev, status_dev,
+                             h->wls_work, (cudaStream_t)stream);
+  return e.empty() ? 0 : fail(h, e);
+}
+
+int w2s_debug_gemm(int use_tcgen05, const void* a_bf16, const void* w_bf16, const float* bias, void* out, int M, int N,
+                   int K, int act, int out_fp32, void* stream) {
+  g_create_error.clear();
+  std::string e = gemm_init();
+  if (e.empty()) {
+    GemmProblem p = PlanBuilder::plain((const bf16*)a_bf16, M, K, (const bf16*)w_bf16, N);
+    p.epi.bias = bias; p.epi.act = act; p.epi.out = out; p.epi.out_fp32 = out_fp32;
+    GemmLaunch gl;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, dev);
+    e = gemm_prepare(p, prop.multiProcessorCount, &gl);
+    if (e.empty()) e = use_tcgen05 ? gemm_launch_tc(gl, (cudaStream_t)stream) : gemm_launch_simt(gl, (cudaStream_t)stream);
+  }
+  if (!e.empty()) {
+    g_create_error = e;
+    return 1;
+  }
+  return 0;
+}
+
+int w2s_kernel_count(const w2s_handle* h, int64_t* launches_per_batch, int64_t* batch_tile) {
+  if (batch_tile) *batch_tile = h->cfg.max_batch;
+  int64_t n = 0;
+  for (auto& kv : h->plans)
+    if ((int64_t)kv.second->steps.size() > n) n = (int64_t)kv.second->steps.size();
+  if (launches_per_batch) *launches_per_batch = n + 1;  // + mask kernel
+  return 0;
+}
+
+double w2s_flops_per_forward(const w2s_handle* h, int64_t L) {
+  const w2s_config& c = h->cfg;
+  std::vector<int> Tl;
+  const double T = (double)num_frames(c, L, &Tl);
+  if (T <= 0) return 0.0;
+  double f = 0.0;
+  for (int l = 0; l < c.num_conv_layers; ++l)
+    f += 2.0 * Tl[l] * c.conv_dim[l] * (l == 0 ? 1 : c.conv_dim[l - 1]) * c.conv_kernel[l];
+  const double H = c.hidden_size, I = c.intermediate_size;
+  f += 2.0 * T * c.conv_dim[c.num_conv_layers - 1] * H;
+  if (c.kind == 0) f += 2.0 * T * H * (H / c.num_conv_pos_embedding_groups) * c.num_conv_pos_embeddings;
+  double per_layer = 2.0 * T * H * 3 * H + 4.0 * T * T * H + 2.0 * T * H * H + 4.0 * T * H * I;
+  if (c.kind == 1) {
+    per_layer += 4.0 * T * H * I;                                   // second macaron FFN
+    per_layer += 2.0 * T * H * 2 * H + 2.0 * T * H * c.conv_depthwise_kernel_size + 2.0 * T * H * H;  // conv module
+    if (c.position_embeddings_type == 1) per_layer += 2.0 * (2 * T - 1) * H * H + 2.0 * T * (2 * T - 1) * H;
+  }
+  f += per_layer * c.num_hidden_layers;
+  f += 2.0 * T * H * c.vocab_size;
+  return f;
+}
+
+}  // extern "C"

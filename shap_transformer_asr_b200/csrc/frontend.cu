@@ -1,0 +1,428 @@
+// HBM-bound front of the path: coalition materialisation (K0), conv0 + norm + GELU (K1), LayerNorm,
+// positional-conv staging and the one-off weight re-layout kernels.
+#include "kernels.cuh"
+
+namespace w2s {
+
+// =================================================================================================
+// K0  mask + baseline fill.  One thread = 4 consecutive samples (float4 store, 128 B per 8 lanes).
+// Follows feasability_tests/conformer_test.ipynb:138-141 (fill value) with keep-bit convention.
+// =================================================================================================
+__global__ void __launch_bounds__(256) mask_kernel(const float* __restrict__ x, const uint16_t* __restrict__ seg_id,
+                                                    const uint32_t* __restrict__ zbits, int zwords, long long L,
+                                                    float baseline, float* __restrict__ out, long long ld) {
+  __shared__ uint32_t z[64];
+  const long long k = blockIdx.y;
+  if (threadIdx.x < zwords) z[threadIdx.x] = zbits[k * zwords + threadIdx.x];
+  __syncthreads();
+  const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i0 >= L) return;
+  float* o = out + k * ld + i0;
+  if (i0 + 4 <= L && ((ld & 3) == 0)) {
+    const float4 xv = *reinterpret_cast<const float4*>(x + i0);
+    const ushort4 sv = *reinterpret_cast<const ushort4*>(seg_id + i0);
+    float4 r;
+    r.x = (z[sv.x >> 5] >> (sv.x & 31)) & 1u ? xv.x : baseline;
+    r.y = (z[sv.y >> 5] >> (sv.y & 31)) & 1u ? xv.y : baseline;
+    r.z = (z[sv.z >> 5] >> (sv.z & 31)) & 1u ? xv.z : baseline;
+    r.w = (z[sv.w >> 5] >> (sv.w & 31)) & 1u ? xv.w : baseline;
+    *reinterpret_cast<float4*>(o) = r;
+  } else {
+    for (int j = 0; j < 4 && i0 + j < L; ++j) {
+      const uint32_t sgm = seg_id[i0 + j];
+      o[j] = (z[sgm >> 5] >> (sgm & 31)) & 1u ? x[i0 + j] : baseline;
+    }
+  }
+}
+
+std::string launch_mask(const float* x, const uint16_t* seg_id, const uint32_t* zbits, int zwords, long long K,
+                        long long L, float baseline, float* out, long long ld, cudaStream_t s) {
+  if (zwords > 64) return "mask: more than 2048 segments are not supported";
+  if (K == 0) return "";
+  dim3 grid((unsigned)((L + 1023) / 1024), (unsigned)K);
+  mask_kernel<<<grid, 256, 0, s>>>(x, seg_id, zbits, zwords, L, baseline, out, ld);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+// =================================================================================================
+// K1a  GroupNorm statistics of conv0 output without materialising it.
+// conv0 is linear and bias-free under GroupNorm (a conv bias cancels in y - mean), so per waveform row
+//   sum_t y[t,c]   = sum_j w[c,j] S[j],        S[j]    = sum_t x[s t + j]
+//   sum_t y[t,c]^2 = sum_jj' w[c,j] w[c,j'] R[j,j'],  R[j,j'] = sum_t x[s t + j] x[s t + j']
+// (HF wav2vec2/modeling_wav2vec2.py:302-323: GroupNorm(num_groups=C) normalises each channel over time).
+// One CTA per waveform row: 65 fp32 accumulators per thread, fp64 from the block reduction onwards.
+// =================================================================================================
+template <int KW>
+__global__ void __launch_bounds__(256) conv0_stats_kernel(const Conv0Params p) {
+  constexpr int NR = KW * (KW + 1) / 2;
+  constexpr int NACC = KW + NR;
+  __shared__ double red[8][NACC];
+  __shared__ double tot[NACC];
+  const int row = blockIdx.x;
+  const float* x = p.x + (long long)row * p.ld;
+  float acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+  for (int t = threadIdx.x; t < p.T0; t += blockDim.x) {
+    float xv[KW];
+    const float* xp = x + (long long)t * p.stride;
+#pragma unroll
+    for (int j = 0; j < KW; ++j) xv[j] = __ldg(xp + j);
+    int r = KW;
+#pragma unroll
+    for (int j = 0; j < KW; ++j) {
+      acc[j] += xv[j];
+#pragma unroll
+      for (int jj = j; jj < KW; ++jj) {
+        acc[r] = fmaf(xv[j], xv[jj], acc[r]);
+        ++r;
+      }
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) {
+    float v = warp_sum(acc[i]);
+    if (lane == 0) red[warp][i] = (double)v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NACC) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    tot[threadIdx.x] = s;
+  }
+  __syncthreads();
+  const double invT = 1.0 / (double)p.T0;
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    double wj[KW];
+#pragma unroll
+    for (int j = 0; j < KW; ++j) wj[j] = (double)p.w[c * KW + j];
+    double sum = 0.0, sq = 0.0;
+    int r = KW;
+#pragma unroll
+    for (int j = 0; j < KW; ++j) {
+      sum += wj[j] * tot[j];
+#pragma unroll
+      for (int jj = j; jj < KW; ++jj) {
+        const double term = wj[j] * wj[jj] * tot[r++];
+        sq += (jj == j) ? term : 2.0 * term;
+      }
+    }
+    const double mean = sum * invT;
+    double var = sq * invT - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double rstd = rsqrt(var + 1e-5);
+    const double a = rstd * (double)p.gamma[c];
+    p.gn_a[(long long)row * p.C + c] = (float)a;
+    p.gn_b[(long long)row * p.C + c] = (float)((double)p.beta[c] - mean * a);
+  }
+}
+
+std::string launch_conv0_stats(const Conv0Params& p, cudaStream_t s) {
+  if (p.kw != 10) return "conv0: only kernel width 10 is implemented for layer 0";
+  if (p.n == 0) return "";
+  conv0_stats_kernel<10><<<p.n, 256, 0, s>>>(p);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+// =================================================================================================
+// K1b  conv0 + norm + GELU, channels-last bf16 output [n, T0, C].
+// CTA = (frame tile of FT frames, waveform row).  The waveform window is staged in shared memory once;
+// each thread owns 8 consecutive channels (one 16-byte store per frame) and keeps their 10-tap filters and
+// affine constants in registers; all lanes of a warp work on the same frame, so window reads broadcast.
+// HF wav2vec2/modeling_wav2vec2.py:302-323 (group) / :275-299 (layer).
+// =================================================================================================
+template <int KW, bool LAYER>
+__global__ void __launch_bounds__(256, 2) conv0_kernel(const Conv0Params p, int FT) {
+  extern __shared__ float sm[];
+  float* xs = sm;                      // FT*stride + KW window
+  float* fmean = xs + FT * p.stride + KW;  // [FT] (layer variant)
+  float* frstd = fmean + FT;
+  const int row = blockIdx.y;
+  const int f0 = blockIdx.x * FT;
+  const int nf = min(FT, p.T0 - f0);
+  const float* x = p.x + (long long)row * p.ld + (long long)f0 * p.stride;
+  const int nwin = (nf - 1) * p.stride + KW;
+  for (int i = threadIdx.x; i < nwin; i += blockDim.x) xs[i] = __ldg(x + i);
+  __syncthreads();
+
+  if constexpr (LAYER) {
+    // per-frame statistics over channels from the 10-sample window (quadratic form with the filter Gram matrix)
+    for (int f = threadIdx.x; f < nf; f += blockDim.x) {
+      float xv[KW];
+#pragma unroll
+      for (int j = 0; j < KW; ++j) xv[j] = xs[f * p.stride + j];
+      float mean = p.ln_bmean, ex2 = p.ln_b2mean;
+#pragma unroll
+      for (int j = 0; j < KW; ++j) {
+        mean = fmaf(p.ln_wbar[j], xv[j], mean);
+        ex2 = fmaf(2.0f * p.ln_wb[j], xv[j], ex2);
+        float gj = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < KW; ++jj) gj = fmaf(p.ln_gram[j * KW + jj], xv[jj], gj);
+        ex2 = fmaf(gj, xv[j], ex2);
+      }
+      const float var = fmaxf(ex2 - mean * mean, 0.f);
+      fmean[f] = mean;
+      frstd[f] = rsqrtf(var + 1e-5f);
+    }
+    __syncthreads();
+  }
+
+  const int tpf = p.C >> 3;            // threads per frame
+  const int fpar = blockDim.x / tpf;   // frames in flight per CTA
+  const int c0 = (threadIdx.x % tpf) * 8;
+  const int fslot = threadIdx.x / tpf;
+  float w[8][KW], ca[8], cb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int j = 0; j < KW; ++j) w[i][j] = __ldg(p.w + (c0 + i) * KW + j);
+    if constexpr (LAYER) {
+      ca[i] = __ldg(p.gamma + c0 + i);
+      cb[i] = __ldg(p.beta + c0 + i);
+    } else {
+      ca[i] = p.gn_a[(long long)row * p.C + c0 + i];
+      cb[i] = p.gn_b[(long long)row * p.C + c0 + i];
+    }
+  }
+  float bias[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bias[i] = (LAYER && p.bias) ? __ldg(p.bias + c0 + i) : 0.f;
+
+  __nv_bfloat16* out = p.out + ((long long)row * p.T0 + f0) * p.C + c0;
+  for (int f = fslot; f < nf; f += fpar) {
+    float xv[KW];
+#pragma unroll
+    for (int j = 0; j < KW; ++j) xv[j] = xs[f * p.stride + j];
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float a = bias[i];
+#pragma unroll
+      for (int j = 0; j < KW; ++j) a = fmaf(w[i][j], xv[j], a);
+      if constexpr (LAYER) a = (a - fmean[f]) * frstd[f];
+      y[i] = gelu_erf(fmaf(a, ca[i], cb[i]));
+    }
+    uint4 u;
+    u.x = pack_bf16x2(y[0], y[1]);
+    u.y = pack_bf16x2(y[2], y[3]);
+    u.z = pack_bf16x2(y[4], y[5]);
+    u.w = pack_bf16x2(y[6], y[7]);
+    *reinterpret_cast<uint4*>(out + (long long)f * p.C) = u;
+  }
+}
+
+std::string launch_conv0(const Conv0Params& p, bool layer_norm, cudaStream_t s) {
+  if (p.kw != 10) return "conv0: only kernel width 10 is implemented for layer 0";
+  const int tpf = p.C / 8;
+  if (p.C % 8 || tpf > 256 || (256 % tpf)) return "conv0: channel count must be 8 * (a divisor of 256)";
+  if (p.n == 0) return "";
+  const int FT = 128;
+  dim3 grid((p.T0 + FT - 1) / FT, p.n);
+  const size_t smem = (size_t)(FT * p.stride + p.kw + 2 * FT) * sizeof(float);
+  if (layer_norm) conv0_kernel<10, true><<<grid, 256, smem, s>>>(p, FT);
+  else conv0_kernel<10, false><<<grid, 256, smem, s>>>(p, FT);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+// filter-bank statistics for the layer-norm variant: one CTA, trivially small
+__global__ void conv0_ln_prep_kernel(const float* w, const float* bias, int C, int kw, float* wbar, float* gram,
+                                     float* wb, float* scalars) {
+  const int t = threadIdx.x;
+  if (t < kw * kw) {
+    const int j = t / kw, jj = t % kw;
+    double s = 0.0;
+    for (int c = 0; c < C; ++c) s += (double)w[c * kw + j] * (double)w[c * kw + jj];
+    gram[t] = (float)(s / C);
+  }
+  if (t < kw) {
+    double s = 0.0, sb = 0.0;
+    for (int c = 0; c < C; ++c) {
+      s += (double)w[c * kw + t];
+      if (bias) sb += (double)w[c * kw + t] * (double)bias[c];
+    }
+    wbar[t] = (float)(s / C);
+    wb[t] = (float)(sb / C);
+  }
+  if (t == 0) {
+    double s = 0.0, s2 = 0.0;
+    if (bias)
+      for (int c = 0; c < C; ++c) {
+        s += (double)bias[c];
+        s2 += (double)bias[c] * (double)bias[c];
+      }
+    scalars[0] = (float)(s / C);
+    scalars[1] = (float)(s2 / C);
+  }
+}
+std::string launch_conv0_ln_prep(const float* w, const float* bias, int C, int kw, float* wbar, float* gram,
+                                 float* wb, float* scalars, cudaStream_t s) {
+  if (kw * kw > 256) return "conv0 prep: kernel too wide";
+  conv0_ln_prep_kernel<<<1, 256, 0, s>>>(w, bias, C, kw, wbar, gram, wb, scalars);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+// =================================================================================================
+// LayerNorm over the last dimension, one warp per row, values held in registers (H <= 1024),
+// fp32 statistics (two-pass), optional activation, bf16 (and optional fp32) output.
+// =================================================================================================
+template <bool IN_F32>
+__global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ in, long long rows, int H,
+                                                         const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float eps, int act,
+                                                         __nv_bfloat16* __restrict__ out, float* __restrict__ out_f32) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  constexpr int MAXV = 32;
+  float v[MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    float t = 0.f;
+    if (idx < H) {
+      if constexpr (IN_F32) t = reinterpret_cast<const float*>(in)[row * H + idx];
+      else t = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(in)[row * H + idx]);
+    }
+    v[i] = t;
+    sum += t;
+  }
+  const float mean = warp_sum(sum) / (float)H;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    const float d = v[i] - mean;
+    if (idx < H) sq = fmaf(d, d, sq);
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)H + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < H) {
+      float y = fmaf((v[i] - mean) * rstd, __ldg(gamma + idx), __ldg(beta + idx));
+      y = apply_act(y, act);
+      if (out) out[row * H + idx] = __float2bfloat16_rn(y);
+      if (out_f32) out_f32[row * H + idx] = y;
+    }
+  }
+}
+
+std::string launch_layernorm(const void* in, int in_fp32, long long rows, int H, const float* gamma,
+                             const float* beta, float eps, int act, __nv_bfloat16* out, float* out_f32,
+                             cudaStream_t s) {
+  if (H > 1024) return "layernorm: H > 1024 not supported";
+  if (rows == 0) return "";
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (in_fp32) layernorm_kernel<true><<<grid, 256, 0, s>>>(in, rows, H, gamma, beta, eps, act, out, out_f32);
+  else layernorm_kernel<false><<<grid, 256, 0, s>>>(in, rows, H, gamma, beta, eps, act, out, out_f32);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+// =================================================================================================
+// positional-conv staging: zero-padded, 64-channel-per-group layout so that each tap of each group is one
+// 128-byte-wide TMA box (HF wav2vec2/modeling_wav2vec2.py:326-379: padding = k/2 on both sides).
+// =================================================================================================
+__global__ void __launch_bounds__(256) pos_pad_kernel(const __nv_bfloat16* __restrict__ h, int T, int H, int G,
+                                                       int kpos, __nv_bfloat16* __restrict__ out) {
+  const int cpg = H / G;
+  const int Tp = T + kpos;
+  const int W = G * 64;
+  const long long total = (long long)gridDim.y * Tp * W;
+  (void)total;
+  const int b = blockIdx.y;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)Tp * W;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int tp = (int)(i / W);
+    const int col = (int)(i - (long long)tp * W);
+    const int g = col >> 6, c = col & 63;
+    const int t = tp - kpos / 2;
+    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+    if (t >= 0 && t < T && c < cpg) v = h[((long long)b * T + t) * H + g * cpg + c];
+    out[(long long)b * Tp * W + i] = v;
+  }
+}
+std::string launch_pos_pad(const __nv_bfloat16* h, int B, int T, int H, int G, int kpos, __nv_bfloat16* out,
+                           cudaStream_t s) {
+  if (H % G || H / G > 64) return "pos_pad: channels per group must be <= 64";
+  if (B == 0) return "";
+  const long long per = (long long)(T + kpos) * G * 64;
+  dim3 grid((unsigned)((per + 255) / 256 > 1024 ? 1024 : (per + 255) / 256), B);
+  pos_pad_kernel<<<grid, 256, 0, s>>>(h, T, H, G, kpos, out);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+// =================================================================================================
+// one-off weight re-layout
+// =================================================================================================
+__global__ void cast_bf16_kernel(const float* src, __nv_bfloat16* dst, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+std::string launch_cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t s) {
+  if (n == 0) return "";
+  cast_bf16_kernel<<<(unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, s>>>(src, dst, n);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+__global__ void repack_conv_kernel(const float* src, __nv_bfloat16* dst, int O, int C, int kw) {
+  const long long n = (long long)O * C * kw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int j = (int)((i / C) % kw);
+    const int o = (int)(i / ((long long)C * kw));
+    dst[i] = __float2bfloat16_rn(src[((long long)o * C + c) * kw + j]);
+  }
+}
+std::string launch_repack_conv(const float* src, __nv_bfloat16* dst, int O, int C, int kw, cudaStream_t s) {
+  const long long n = (long long)O * C * kw;
+  repack_conv_kernel<<<(unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, s>>>(src, dst, O, C, kw);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+__global__ void repack_posconv_kernel(const float* src, __nv_bfloat16* dst, int H, int G, int kw) {
+  const int cpg = H / G;
+  const long long n = (long long)H * kw * 64;  // [G][cpg][kw*64]
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i & 63);
+    const int j = (int)((i >> 6) % kw);
+    const int o = (int)(i / ((long long)kw * 64));  // output channel g*cpg + n
+    float v = 0.f;
+    if (c < cpg) v = src[((long long)o * cpg + c) * kw + j];
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+std::string launch_repack_posconv(const float* src, __nv_bfloat16* dst, int H, int G, int kw, cudaStream_t s) {
+  const long long n = (long long)H * kw * 64;
+  repack_posconv_kernel<<<(unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, s>>>(src, dst, H, G, kw);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+__global__ void repack_glu_kernel(const float* src, __nv_bfloat16* dst, int half, int K) {
+  const long long n = (long long)2 * half * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const int r = (int)(i / K);
+    const int srow = (r & 1) ? (r >> 1) + half : (r >> 1);
+    dst[i] = __float2bfloat16_rn(src[(long long)srow * K + k]);
+  }
+}
+std::string launch_repack_glu(const float* src, __nv_bfloat16* dst, int half, int K, cudaStream_t s) {
+  const long long n = (long long)2 * half * K;
+  repack_glu_kernel<<<(unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, s>>>(src, dst, half, K);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+}  // namespace w2s

@@ -1,0 +1,92 @@
+// Launchers of the non-GEMM kernels of the path (all sm_100a CUDA, no library calls).
+#pragma once
+#include "common.cuh"
+
+namespace w2s {
+
+// ---- K0: coalition materialisation (segment mask + baseline fill) -----------------------------------
+// out[k, i] = bit(z[k], seg_id[i]) ? x[i] : baseline
+std::string launch_mask(const float* x, const uint16_t* seg_id, const uint32_t* zbits, int zwords, long long K,
+                        long long L, float baseline, float* out, long long ld, cudaStream_t s);
+
+// ---- K1: conv0 (Cin = 1) + GroupNorm-over-time / LayerNorm-over-channels + GELU ------------------------
+struct Conv0Params {
+  const float* x;        // [n, ld] waveforms
+  long long ld;
+  int n, L, T0, C, kw, stride;
+  const float* w;        // [C][kw] fp32
+  const float* bias;     // [C] or null
+  const float* gamma;    // [C]
+  const float* beta;     // [C]
+  // group-norm variant: per (row, channel) affine produced by the statistics kernel
+  float* gn_a;           // [n, C]  rstd * gamma
+  float* gn_b;           // [n, C]  beta - mean * rstd * gamma
+  // layer-norm variant: channel statistics of the filter bank (precomputed once)
+  const float* ln_wbar;  // [kw]       mean_c w[c][j]
+  const float* ln_gram;  // [kw][kw]   mean_c w[c][j] w[c][j']
+  const float* ln_wb;    // [kw]       mean_c w[c][j] b[c]
+  float ln_bmean, ln_b2mean;
+  __nv_bfloat16* out;    // [n, T0, C] channels-last
+};
+std::string launch_conv0_stats(const Conv0Params& p, cudaStream_t s);         // group-norm statistics
+std::string launch_conv0(const Conv0Params& p, bool layer_norm, cudaStream_t s);
+// filter-bank statistics for the layer-norm variant (run once at create)
+std::string launch_conv0_ln_prep(const float* w, const float* bias, int C, int kw, float* wbar, float* gram,
+                                 float* wb, float* scalars /*[2]: mean b, mean b^2*/, cudaStream_t s);
+
+// ---- LayerNorm over the last dimension (fp32 or bf16 in, bf16 out), optional activation ---------------
+std::string launch_layernorm(const void* in, int in_fp32, long long rows, int H, const float* gamma,
+                             const float* beta, float eps, int act, __nv_bfloat16* out, float* out_f32,
+                             cudaStream_t s);
+
+// ---- positional-conv input staging: [B, T, H] -> zero-padded [B, T + kpos, G*64] ------------------------
+std::string launch_pos_pad(const __nv_bfloat16* h, int B, int T, int H, int G, int kpos, __nv_bfloat16* out,
+                           cudaStream_t s);
+
+// ---- attention -------------------------------------------------------------------------------------
+struct AttnParams {
+  const __nv_bfloat16* qkv;   // [B*T, 3H]  (q | k | v)
+  const __nv_bfloat16* vt;    // [B, heads, hd, Tp]  V^T (tcgen05 path)
+  __nv_bfloat16* ctx;         // [B*T, H]
+  int B, T, Tp, H, heads, hd;
+  float scale;
+  // conformer relative positions (null when unused)
+  const __nv_bfloat16* pos_proj;  // [2T-1, H] linear_pos(rel_pos_emb), row r <-> relative position T-1-r
+  const float* bias_u;            // [H]
+  const float* bias_v;            // [H]
+};
+std::string launch_attention_simt(const AttnParams& p, cudaStream_t s);
+struct AttnTcPlan;  // opaque: tensor maps + launch geometry
+std::string attention_tc_init();
+std::string attention_tc_prepare(const AttnParams& p, AttnTcPlan** plan);
+std::string attention_tc_launch(const AttnTcPlan* plan, cudaStream_t s);
+void attention_tc_free(AttnTcPlan* plan);
+bool attention_tc_supported(const AttnParams& p);
+
+// ---- K9: lm_head + log-softmax + gather -----------------------------------------------------------------
+struct HeadParams {
+  const __nv_bfloat16* h;     // [n*T, H]
+  const __nv_bfloat16* w;     // [V, H]
+  const float* bias;          // [V]
+  int n, T, H, V, mode, D;
+  const int* frames;          // [D] device
+  const int* tokens;          // [D] device
+  float* out;                 // [n, width]
+};
+std::string launch_head(const HeadParams& p, cudaStream_t s);
+
+// ---- K12: KernelSHAP constrained WLS -----------------------------------------------------------------------
+std::string launch_wls(const uint32_t* zbits, int zwords, const double* w, const float* y, long long K, int M,
+                       int D, const double* fx, const double* fnull, double* phi, int32_t* status,
+                       double* work /* (M-1)*(M-1) + (M-1)*D doubles */, cudaStream_t s);
+
+// ---- weight re-layout (run once at create) -------------------------------------------------------------------
+std::string launch_cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t s);
+// conv weight [O][C][kw] fp32 -> [O][j*C + c] bf16
+std::string launch_repack_conv(const float* src, __nv_bfloat16* dst, int O, int C, int kw, cudaStream_t s);
+// positional conv weight [H][cpg][kw] fp32 -> [G][cpg][kw*64 + c] bf16 (zero for c >= cpg)
+std::string launch_repack_posconv(const float* src, __nv_bfloat16* dst, int H, int G, int kw, cudaStream_t s);
+// rows interleaved for the GLU epilogue: dst[2j] = src[j], dst[2j+1] = src[j + half]
+std::string launch_repack_glu(const float* src, __nv_bfloat16* dst, int half, int K, cudaStream_t s);
+
+}  // namespace w2s

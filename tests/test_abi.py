@@ -1,0 +1,61 @@
+"""CPU: the C-ABI library loads and exports every symbol include/w2s.h declares; no compute without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import __graft_entry__ as entry
+from shap_transformer_asr_b200 import _lib
+from shap_transformer_asr_b200.config import MODELS
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(_lib.LIB_PATH):
+        entry.build()
+    return _lib.load()
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "w2s.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(w2s_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_and_binding_declare_the_same_entry_points():
+    assert header_symbols() == sorted(_lib.SIGNATURES)
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for name in header_symbols():
+        assert hasattr(lib, name), f"libw2s.so does not export {name}"
+
+
+def test_library_has_no_torch_or_cuda_driver_link_dependency():
+    # plain C ABI: only libstdc++/libc style dependencies (cudart is linked statically)
+    out = os.popen(f"ldd {_lib.LIB_PATH}").read()
+    assert "torch" not in out and "libcuda.so" not in out
+
+
+def test_config_struct_matches_header_layout():
+    # 3 ints + 3*8 arrays + ... : keep ctypes mirror in sync with the C struct (all 4-byte fields)
+    text = open(os.path.join(ROOT, "include", "w2s.h")).read()
+    body = text[text.index("typedef struct {"): text.index("} w2s_config;")]
+    n_arrays = len(re.findall(r"\[W2S_MAX_CONV_LAYERS\]", body))
+    n_scalars = len(re.findall(r"^\s*(int32_t|float)\s+\w+;", body, flags=re.M))
+    assert ctypes.sizeof(_lib.W2SConfig) == 4 * (n_scalars + 8 * n_arrays)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_create_fails_loudly_without_a_gpu(lib):
+    cfg = _lib.W2SConfig()
+    handle = ctypes.c_void_p()
+    rc = lib.w2s_create(ctypes.byref(cfg), None, None, None, 0, 0, ctypes.byref(handle))
+    assert rc != 0 and b"no CUDA device" in lib.w2s_last_error(None)
+    from shap_transformer_asr_b200 import Engine
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Engine({}, MODELS["wav2vec2-tiny"])

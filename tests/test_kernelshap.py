@@ -1,0 +1,100 @@
+"""CPU: KernelSHAP restatement (oracle, parity unpinned vs shap itself) -- properties, and the product
+sampler against the oracle sampler bit for bit."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle.kernelshap_ref import KernelExplainerRef, brute_force_shapley
+from shap_transformer_asr_b200.kernelshap import expand_to_samples, sample_coalitions
+
+
+@pytest.mark.parametrize("M,K", [(32, 256), (100, 2048), (200, 8192), (128, 2048), (12, 300), (8, "auto"), (5, 100), (3, 50), (2, 10)])
+def test_product_sampler_is_bit_identical_to_oracle(M, K):
+    np.random.seed(0)
+    Zr, wr = KernelExplainerRef(None, M).sample(K)
+    Z, w, info = sample_coalitions(M, K, seed=0)
+    assert Z.shape == Zr.shape and np.array_equal(Z, Zr.astype(np.uint8))
+    assert np.array_equal(w, wr)
+
+
+def test_sampler_regression_pins(golden_dir):
+    pins = np.load(os.path.join(golden_dir, "sampler_pins.npz"))
+    for key in pins.files:
+        M, K = key[1:].split("_K")
+        K = K if K == "auto" else int(K)
+        Z, w, _ = sample_coalitions(int(M), K, seed=0)
+        p = pins[key]
+        assert Z.shape[0] == int(p[0])
+        assert int(hashlib.sha256(Z.tobytes()).hexdigest()[:12], 16) == int(p[1])
+        assert abs(w.sum() - p[2]) < 1e-12
+
+
+def test_sampler_structure_matches_survey_appendix_a():
+    # only size 1 (+complements) is enumerated at the BASELINE configs,
+    # with normalised weight 0.2563 / 0.1951 / 0.1711 for M = 32 / 100 / 200
+    for M, K, nfixed, w1 in [(32, 256, 64, 0.2563), (100, 2048, 200, 0.1951), (200, 8192, 400, 0.1711)]:
+        Z, w, info = sample_coalitions(M, K, seed=0)
+        assert info["n_fixed"] == nfixed and Z.shape[0] == K
+        assert abs(w[:nfixed].sum() - w1) < 5e-5
+        assert abs(w.sum() - 1.0) < 1e-9
+        sizes = Z[:nfixed].sum(1)
+        assert set(sizes.tolist()) == {1, M - 1}
+        # the fixed rows follow itertools.combinations order, each followed by its complement
+        assert np.array_equal(Z[0], np.eye(M, dtype=np.uint8)[0]) and np.array_equal(Z[1], 1 - Z[0])
+        assert len({r.tobytes() for r in Z}) == K  # de-duplicated
+
+
+def test_seed_determinism_and_sensitivity():
+    a = sample_coalitions(64, 1000, seed=3)[0]
+    b = sample_coalitions(64, 1000, seed=3)[0]
+    c = sample_coalitions(64, 1000, seed=4)[0]
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+
+
+def _game(M, D, seed=0, interactions=True):
+    rng = np.random.default_rng(seed)
+    lin = rng.standard_normal((M, D))
+    pair = rng.standard_normal((M, M, D)) * (0.3 if interactions else 0.0)
+    base = rng.standard_normal(D)
+
+    def f(Z):
+        Z = np.atleast_2d(np.asarray(Z, dtype=np.float64))
+        return base + Z @ lin + np.einsum("ki,kj,ijd->kd", Z, Z, pair)
+
+    return f, lin
+
+
+def test_full_enumeration_equals_brute_force_shapley():
+    M, D = 7, 3
+    f, _ = _game(M, D)
+    phi, fx, fnull = KernelExplainerRef(f, M).shap_values(nsamples=10 ** 6)
+    assert np.abs(phi - brute_force_shapley(f, M)).max() < 1e-9
+    assert np.abs(phi.sum(0) - (fx - fnull)).max() < 1e-9
+
+
+def test_additive_game_is_exact_under_sampling():
+    M, D = 40, 4
+    f, lin = _game(M, D, interactions=False)
+    np.random.seed(1)
+    phi, fx, fnull = KernelExplainerRef(f, M).shap_values(nsamples=600)
+    assert np.abs(phi - lin).max() < 1e-8
+
+
+def test_efficiency_holds_for_sampled_nonadditive_game():
+    M, D = 30, 2
+    f, _ = _game(M, D)
+    np.random.seed(2)
+    phi, fx, fnull = KernelExplainerRef(f, M).shap_values(nsamples=500)
+    assert np.abs(phi.sum(0) - (fx - fnull)).max() < 1e-9
+
+
+def test_expand_to_samples_layout():
+    # reference on-disk layout [1, L, T'] (shap_calculation.py:200-210, evaluation.ipynb:503-504)
+    phi = np.arange(6, dtype=np.float64).reshape(3, 2)
+    b = np.array([0, 2, 3, 6])
+    out = expand_to_samples(phi, b)
+    assert out.shape == (1, 6, 2) and out[0, :, 0].tolist() == [0, 0, 2, 4, 4, 4]
+    per = expand_to_samples(phi, b, per_sample=True)
+    assert np.allclose(per[0].sum(0), phi.sum(0))
