@@ -125,6 +125,12 @@ int w2s_wls(w2s_handle* h, const uint32_t* z_bits_dev, const double* w_dev, cons
 /* Test / profiling hooks for the individual kernels (used by tests/ and bench.py only). */
 int w2s_debug_gemm(int use_tcgen05, const void* a_bf16, const void* w_bf16, const float* bias, void* out,
                    int M, int N, int K, int act, int out_fp32, void* stream);
+/* Per-launch CUDA-event profile on the launching stream (bench.py roofline leg): enable, run evaluations,
+ * then read per launch class (newline-separated names) total milliseconds, algorithmic FLOPs / bytes and
+ * launch counts.  Returns the number of classes, or -1 if `names_cap` is too small. */
+int w2s_profile_enable(w2s_handle* h, int on);
+int64_t w2s_profile_read(w2s_handle* h, char* names, int64_t names_cap, double* ms, double* flops, double* bytes,
+                         int64_t* counts, int64_t max_entries);
 int w2s_kernel_count(const w2s_handle* h, int64_t* launches_per_batch, int64_t* batch_tile);
 /* algorithmic FLOPs (2*MAC) of one coalition forward for clips of L samples */
 double w2s_flops_per_forward(const w2s_handle* h, int64_t num_samples);

@@ -36,6 +36,14 @@ struct LayerW {
 struct Step {
   std::string name;
   std::function<std::string(cudaStream_t)> run;
+  double flops = 0.0;  // algorithmic FLOPs (2*MAC) of this launch, 0 for non-contraction kernels
+  double bytes = 0.0;  // algorithmic HBM bytes of this launch (HBM-bound kernels)
+};
+
+struct ProfRec {
+  std::string name;
+  cudaEvent_t e0, e1;
+  double flops, bytes;
 };
 
 struct Plan {
@@ -104,12 +112,20 @@ struct w2s_handle {
   long long wls_cap = 0;
   std::map<int, std::unique_ptr<Plan>> plans;
 
+  // optional per-launch CUDA-event profile (bench.py roofline leg)
+  bool profiling = false;
+  std::vector<ProfRec> prof;
+
   // per-call dynamic arguments read by the plan steps at launch time
   const float* cur_x = nullptr;
   long long cur_ld = 0;
   float* cur_out = nullptr;
 
   ~w2s_handle() {
+    for (auto& r : prof) {
+      cudaEventDestroy(r.e0);
+      cudaEventDestroy(r.e1);
+    }
     plans.clear();
     for (void* p : ws_allocs) cudaFree(p);
     for (void* p : allocs) cudaFree(p);
@@ -326,11 +342,16 @@ struct PlanBuilder {
     plan->gemms.push_back(gl);
     W2S_TRY(gemm_prepare(p, h->num_sms, gl));
     const bool simt = simt_gemm;
-    plan->steps.push_back({name, [gl, simt](cudaStream_t s) { return simt ? gemm_launch_simt(*gl, s) : gemm_launch_tc(*gl, s); }});
+    Step st{name, [gl, simt](cudaStream_t s) { return simt ? gemm_launch_simt(*gl, s) : gemm_launch_tc(*gl, s); }};
+    st.flops = 2.0 * p.M * (double)p.N * p.K * p.Bz * p.G;
+    plan->steps.push_back(std::move(st));
     return "";
   }
-  void add(const std::string& name, std::function<std::string(cudaStream_t)> f) {
-    plan->steps.push_back({name, std::move(f)});
+  void add(const std::string& name, std::function<std::string(cudaStream_t)> f, double flops = 0.0, double bytes = 0.0) {
+    Step st{name, std::move(f)};
+    st.flops = flops;
+    st.bytes = bytes;
+    plan->steps.push_back(std::move(st));
   }
   std::string add_ln(const std::string& name, const void* in, int in_fp32, long long rows, int H, const float* g,
                      const float* b, float eps, int act, bf16* out, float* out_f32) {
@@ -374,7 +395,7 @@ struct PlanBuilder {
         Conv0Params q = cp;
         q.x = hh->cur_x; q.ld = hh->cur_ld;
         return launch_conv0(q, layer, s);
-      });
+      }, 2.0 * cp.T0 * (double)cp.C * cp.kw * n, ((double)cp.T0 * cp.C * 2.0 + 4.0 * (double)h->ws_L) * n);
     }
     // ---- K2: conv1..6 as implicit GEMM over the stride-row view of the previous layer ---------------------
     bf16* cur = h->bufA;
@@ -527,8 +548,21 @@ std::string run_batches(w2s_handle* h, const uint32_t* zbits, const float* x, lo
     Plan* pl = nullptr;
     W2S_TRY(get_plan(h, n, &pl));
     if (zbits) {
+      ProfRec rec;
+      if (h->profiling) {
+        rec.name = "mask";
+        rec.flops = 0.0;
+        rec.bytes = 4.0 * (double)h->L * n;
+        cudaEventCreate(&rec.e0);
+        cudaEventCreate(&rec.e1);
+        cudaEventRecord(rec.e0, s);
+      }
       W2S_TRY(launch_mask(h->clip, h->seg_id, zbits + k0 * h->zwords, h->zwords, n, h->L, h->baseline, h->xm,
                           h->xm_ld, s));
+      if (h->profiling) {
+        cudaEventRecord(rec.e1, s);
+        h->prof.push_back(rec);
+      }
       h->cur_x = h->xm;
       h->cur_ld = h->xm_ld;
     } else {
@@ -537,7 +571,20 @@ std::string run_batches(w2s_handle* h, const uint32_t* zbits, const float* x, lo
     }
     h->cur_out = out + k0 * width;
     for (const Step& st : pl->steps) {
+      ProfRec rec;
+      if (h->profiling) {
+        rec.name = st.name;
+        rec.flops = st.flops;
+        rec.bytes = st.bytes;
+        cudaEventCreate(&rec.e0);
+        cudaEventCreate(&rec.e1);
+        cudaEventRecord(rec.e0, s);
+      }
       std::string e = st.run(s);
+      if (h->profiling) {
+        cudaEventRecord(rec.e1, s);
+        h->prof.push_back(rec);
+      }
       if (!e.empty()) return st.name + ": " + e;
     }
   }
@@ -742,6 +789,49 @@ int w2s_debug_gemm(int use_tcgen05, const void* a_bf16, const void* w_bf16, cons
     return 1;
   }
   return 0;
+}
+
+int w2s_profile_enable(w2s_handle* h, int on) {
+  cudaDeviceSynchronize();
+  for (auto& r : h->prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  h->prof.clear();
+  h->profiling = on != 0;
+  return 0;
+}
+
+int64_t w2s_profile_read(w2s_handle* h, char* names, int64_t names_cap, double* ms, double* flops, double* bytes,
+                         int64_t* counts, int64_t max_entries) {
+  cudaDeviceSynchronize();
+  // aggregate by launch class: strip the "L<i>." layer prefix
+  std::vector<std::string> keys;
+  std::vector<double> tms, tfl, tby;
+  std::vector<int64_t> cnt;
+  for (auto& r : h->prof) {
+    std::string k = r.name;
+    if (k.size() > 1 && k[0] == 'L' && isdigit((unsigned char)k[1])) k = k.substr(k.find('.') + 1);
+    size_t i = 0;
+    for (; i < keys.size(); ++i)
+      if (keys[i] == k) break;
+    if (i == keys.size()) {
+      keys.push_back(k);
+      tms.push_back(0.0); tfl.push_back(0.0); tby.push_back(0.0); cnt.push_back(0);
+    }
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    tms[i] += t; tfl[i] += r.flops; tby[i] += r.bytes; cnt[i] += 1;
+  }
+  std::string joined;
+  int64_t n = 0;
+  for (size_t i = 0; i < keys.size() && n < max_entries; ++i, ++n) {
+    joined += keys[i] + "\n";
+    ms[n] = tms[i]; flops[n] = tfl[i]; bytes[n] = tby[i]; counts[n] = cnt[i];
+  }
+  if ((int64_t)joined.size() + 1 > names_cap) return -1;
+  memcpy(names, joined.c_str(), joined.size() + 1);
+  return n;
 }
 
 int w2s_kernel_count(const w2s_handle* h, int64_t* launches_per_batch, int64_t* batch_tile) {

@@ -205,6 +205,23 @@ class Engine:
     def flops_per_forward(self, num_samples: Optional[int] = None) -> float:
         return float(self.lib.w2s_flops_per_forward(self._h, int(num_samples or self.num_samples)))
 
+    def profile(self, on: bool):
+        self.lib.w2s_profile_enable(self._h, int(on))
+
+    def profile_read(self):
+        """-> {launch class: dict(ms, flops, bytes, launches)} accumulated since profile(True)."""
+        cap, nmax = 1 << 16, 256
+        names = C.create_string_buffer(cap)
+        ms = (C.c_double * nmax)()
+        fl = (C.c_double * nmax)()
+        by = (C.c_double * nmax)()
+        cn = (C.c_int64 * nmax)()
+        n = self.lib.w2s_profile_read(self._h, names, cap, ms, fl, by, cn, nmax)
+        if n < 0:
+            raise RuntimeError("w2s_profile_read: buffer too small")
+        keys = names.value.decode().split("\n")[:n]
+        return {k: dict(ms=ms[i], flops=fl[i], bytes=by[i], launches=cn[i]) for i, k in enumerate(keys)}
+
     def kernel_count(self):
         a, b = C.c_int64(), C.c_int64()
         self.lib.w2s_kernel_count(self._h, C.byref(a), C.byref(b))

@@ -1,0 +1,158 @@
+"""GPU: the CUDA path through the C ABI against the oracle / golden vectors.
+
+Tolerances (bf16 operands, fp32 accumulation and statistics; stated per north_star):
+  logits      max |gpu - ref| <= LOGIT_TOL * max |ref|
+  attributions max |phi_gpu - phi_ref| <= PHI_TOL * max |phi_ref|, identical argmax transcript on the unmasked clip
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import VARIANTS, build_model, rel_err
+from oracle import callback as CB
+from oracle import w2v2_forward as W
+from oracle.kernelshap_ref import KernelExplainerRef
+from shap_transformer_asr_b200.config import MODELS
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 0.04
+PHI_TOL = 0.10
+
+IMPLEMENTED = ["tiny_group", "tiny_layer_stable"]
+
+
+@pytest.fixture(scope="module")
+def P():
+    import shap_transformer_asr_b200 as pkg
+    assert torch.cuda.is_available()
+    return pkg
+
+
+@pytest.mark.parametrize("name", IMPLEMENTED)
+@pytest.mark.parametrize("mode", ["validate", "tcgen05"])
+def test_tiny_logits_match_golden(P, golden_dir, name, mode):
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    cfg = VARIANTS[name]
+    eng = P.Engine(build_model(cfg), cfg, max_batch=2, validate_gemm=mode == "validate", validate_attn=mode == "validate")
+    eng.set_targets("logits")
+    x = torch.from_numpy(g["x"]).cuda()
+    out = eng.eval_waveforms(x).view(g["logits"].shape).cpu().numpy()   # 3 rows, batch tile 2: ragged last tile
+    err = rel_err(out, g["logits"])
+    print(f"{name} [{mode}] logits rel err {err:.3e}")
+    assert err < LOGIT_TOL
+    eng.close()
+
+
+@pytest.fixture(scope="module")
+def base_engine(P):
+    cfg = MODELS["wav2vec2-base"]
+    model = build_model(cfg)
+    eng = P.Engine(model, cfg, max_batch=32)
+    yield eng, model, cfg
+    eng.close()
+
+
+def test_c1_base_logits_match_golden(P, base_engine, golden_dir):
+    eng, model, cfg = base_engine
+    g = np.load(os.path.join(golden_dir, "c1_base.npz"))
+    clip = P.synthetic_clip(16000)
+    eng.set_clip(clip, num_segments=32)
+    eng.set_targets("logits")
+    out = eng.eval_bits(eng.bits_to_device(g["rows"])).view(g["logits"].shape).cpu().numpy()
+    err = rel_err(out, g["logits"])
+    print(f"C1 base logits rel err {err:.3e}; max abs {np.abs(out - g['logits']).max():.3e}")
+    assert err < LOGIT_TOL
+    # identical argmax transcript on the unmasked clip (row 0), allowing only exact near-ties to differ
+    same = out[0].argmax(-1) == g["logits"][0].argmax(-1)
+    top2 = np.sort(g["logits"][0], -1)
+    near_tie = (top2[:, -1] - top2[:, -2]) < 2 * np.abs(out[0] - g["logits"][0]).max()
+    assert np.all(same | near_tie)
+    f, t = P.char_targets(out[0])
+    assert len(f) > 0
+
+
+def test_callback_shapes_match_reference_interfaces(P, base_engine):
+    eng, model, cfg = base_engine
+    sd, d = W.state_dict_of(model), cfg.to_dict()
+    x = np.random.default_rng(5).standard_normal((3, 16000)).astype(np.float32)
+    ref_logits = W.ctc_logits(sd, d, torch.from_numpy(x)).detach()
+    # B1: ModelWrapper.forward, all three input ranks (shap_calculation.py:33-36)
+    wrap = P.ModelWrapper(eng)
+    xt = torch.from_numpy(x).cuda()
+    for inp in (xt, xt[:, None, :], xt[:, None, None, :]):
+        out = wrap(inp)
+        assert out.shape == (3, 49)
+        assert rel_err(out.cpu().numpy(), ref_logits.max(-1).values.numpy()) < LOGIT_TOL
+    # B2: predict_function, float64 numpy in, float32 numpy out, 1-D promotion (w2v2conformer.py:116-131)
+    fn = P.make_predict_function(eng, 7, 11)
+    o = fn(x.astype(np.float64))
+    assert o.shape == (3,) and o.dtype == np.float32
+    assert np.abs(o - ref_logits[:, 7, 11].numpy()).max() < LOGIT_TOL * ref_logits.abs().max().item()
+    assert fn(x[0].astype(np.float64)).shape == (1,)
+    # B3: lime_predict_fn (lime_shap_wav2vec2_comparison.py:60-71)
+    o = P.make_lime_predict_fn(eng)(x)
+    assert o.shape == (3, 1)
+    assert np.abs(o - ref_logits.mean(-1).mean(1, keepdim=True).numpy()).max() < 5e-3
+
+
+def test_c1_kernelshap_matches_oracle(P, base_engine):
+    eng, model, cfg = base_engine
+    sd, d = W.state_dict_of(model), cfg.to_dict()
+    clip = P.synthetic_clip(16000)
+    M, K = 32, 256
+    res = P.KernelShapExplainer(eng, nsamples=K, seed=0).explain(clip, num_segments=M)
+    bounds = CB.segment_bounds(16000, M)
+    frames, tokens = res["frames"], res["tokens"]
+    f = lambda Z: CB.evaluate_coalitions(sd, d, clip, Z, bounds, mode="logprob", frames=frames, tokens=tokens, batch=32)
+    ref = KernelExplainerRef(f, M)
+    np.random.seed(0)
+    Zr, wr = ref.sample(K)
+    assert np.array_equal(res["Z"], Zr.astype(np.uint8)) and np.array_equal(res["weights"], wr)   # bit-exact coalitions
+    y_ref = f(Zr)
+    fx, fnull = f(np.ones((1, M)))[0], f(np.zeros((1, M)))[0]
+    phi_ref = ref.solve(y_ref, fx, fnull)
+    y = res["y"].cpu().numpy()
+    phi = res["phi"].cpu().numpy()
+    e_y = np.abs(y - y_ref).max()
+    e_phi = np.abs(phi - phi_ref).max() / np.abs(phi_ref).max()
+    rank = np.corrcoef(np.abs(phi).sum(1), np.abs(phi_ref).sum(1))[0, 1]
+    print(f"C1 KernelSHAP: y max abs err {e_y:.3e}; phi max rel err {e_phi:.3e}; |phi| corr {rank:.5f}; D={len(frames)}")
+    assert int(res["status"].item()) == 0
+    assert e_phi < PHI_TOL
+    assert rank > 0.99
+    # efficiency of the device solve: sum_m phi[m, d] = fx[d] - fnull[d]
+    assert np.abs(phi.sum(0) - (res["fx"] - res["fnull"]).cpu().numpy()).max() < 1e-6
+
+
+def test_full_size_properties_c2(P, base_engine):
+    """BASELINE config C2 (5 s clip, 100 segments): size-independent properties at full size."""
+    eng, model, cfg = base_engine
+    clip = P.synthetic_clip(80000)
+    M = 100
+    eng.set_clip(clip, num_segments=M)
+    Z, kw, _ = P.sample_coalitions(M, 2048, seed=0)
+    rows = np.concatenate([np.ones((1, M), np.uint8), np.zeros((1, M), np.uint8), Z[:94]])
+    frames = np.arange(0, 249, 3, dtype=np.int32)
+    tokens = (frames * 7 % 32).astype(np.int32)
+    eng.set_targets("logprob", frames, tokens)
+    bits = eng.bits_to_device(rows)
+    y1 = eng.eval_bits(bits)
+    # (1) an evaluation does not depend on its position in the batch: reversed order, different tiling
+    y2 = eng.eval_bits(bits.flip(0).contiguous()).flip(0)
+    assert torch.equal(y1, y2)
+    # (2) the all-ones coalition equals the explicit-waveform entry point on the unmasked clip
+    y3 = eng.eval_waveforms(torch.from_numpy(clip).cuda()[None])
+    assert torch.equal(y1[:1], y3)
+    # (3) masked rows equal the explicit-waveform path on the host-materialised waveform
+    Xm = torch.from_numpy(CB.materialize(clip, rows[2:6], CB.segment_bounds(80000, M))).cuda()
+    assert torch.equal(y1[2:6], eng.eval_waveforms(Xm))
+    # (4) log-probabilities: finite, <= 0, and logsumexp over the vocabulary of the full logits is 0
+    assert torch.isfinite(y1).all() and (y1 <= 0).all()
+    eng.set_targets("logits")
+    lg = eng.eval_bits(bits[:2]).view(2, 249, 32)
+    eng.set_targets("logprob", frames, tokens)
+    lp = torch.log_softmax(lg, -1)[:, torch.from_numpy(frames).long(), torch.from_numpy(tokens).long()]
+    assert (lp - y1[:2]).abs().max().item() < 1e-4
