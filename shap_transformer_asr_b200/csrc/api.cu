@@ -319,7 +319,6 @@ std::string ensure_workspace(w2s_handle* h, long long L) {
   W2S_TRY(dalloc(pool, &h->qkv, rows * 3 * H));
   W2S_TRY(dalloc(pool, &h->ctx, rows * H));
   W2S_TRY(dalloc(pool, &h->ffn, rows * I));
-  W2S_TRY(dalloc(pool, &h->vt, nb * (size_t)H * h->Tp, /*zero=*/true));
   if (c.kind == 0) {
     W2S_TRY(dalloc(pool, &h->hp,
                    nb * (size_t)(T + c.num_conv_pos_embeddings) * c.num_conv_pos_embedding_groups * 64));
@@ -466,10 +465,6 @@ struct PlanBuilder {
         GemmProblem p = plain(h->hb, rows, H, w.wqkv, 3 * H);
         p.epi.bias = w.bqkv;
         p.epi.out = h->qkv;
-        if (tc_attn) {
-          p.epi.vt = h->vt; p.epi.vt_n0 = 2 * H; p.epi.vt_T = T; p.epi.vt_Tp = h->Tp;
-          p.epi.vt_heads = ap.heads; p.epi.vt_hd = ap.hd;
-        }
         W2S_TRY(add_gemm(ls + "qkv", p));
       }
       if (tc_attn) add(ls + "attention", [=](cudaStream_t s) { return attention_tc_launch(apl, s); });
@@ -777,11 +772,13 @@ int w2s_debug_gemm(int use_tcgen05, const void* a_bf16, const void* w_bf16, cons
     GemmProblem p = PlanBuilder::plain((const bf16*)a_bf16, M, K, (const bf16*)w_bf16, N);
     p.epi.bias = bias; p.epi.act = act; p.epi.out = out; p.epi.out_fp32 = out_fp32;
     GemmLaunch gl;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceProp prop;
-    cudaGetDeviceProperties(&prop, dev);
-    e = gemm_prepare(p, prop.multiProcessorCount, &gl);
+    static int sms = 0;
+    if (sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    e = gemm_prepare(p, sms, &gl);
     if (e.empty()) e = use_tcgen05 ? gemm_launch_tc(gl, (cudaStream_t)stream) : gemm_launch_simt(gl, (cudaStream_t)stream);
   }
   if (!e.empty()) {

@@ -116,6 +116,7 @@ struct AttnTcDev {
   int B, T, Tp, H, heads;
   int nblk;       // 64-key blocks = Tp / 64
   int n0, n1;     // keys in the first / second S half (multiples of 64, <= 256 each)
+  int sv_off;     // smem offset of the V tiles
   float scale_log2e;
 };
 struct AttnTcPlan {
@@ -126,27 +127,39 @@ struct AttnTcPlan {
   int tmem_cols;
 };
 
-constexpr int ATT_SQ = 0;                       // 16 KB   Q   [128 x 64]
-constexpr int ATT_SK = 16384;                   // 64 KB   K   2 x [256 x 64]
-constexpr int ATT_SV = ATT_SK + 65536;          // 64 KB   V^T 8 x [64(d) x 64(keys)]
-constexpr int ATT_SP = ATT_SV + 65536;          // 64 KB   P   4 x [128 x 64(keys)]
-constexpr int ATT_BAR = ATT_SP + 65536;         // barriers + tmem slot
-constexpr size_t ATT_SMEM = ATT_BAR + 64 + 1024;
+// shared memory map (bytes from the 1024-aligned base):
+//   [0, 16K)          Q   [128 x 64]            \  dead once S = Q K^T has completed;
+//   [16K, 16K + Ksz)  K   1 or 2 x [256 x 64]   /  P (4 x [128 x 64 keys] = 64 KB) is written over them
+//   [sv_off, ...)     V   nblk x [64 keys x 64] straight from the qkv buffer (MN-major B operand)
+constexpr int ATT_SQ = 0;
+constexpr int ATT_SK = 16384;
+constexpr int ATT_SP = 0;
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
+  // MN-major operand (rows = K index, 128 contiguous bytes = 64 MN elements, 128B swizzle):
+  // 8-row (K) groups are 1024 B apart (SBO); LBO (next 64-wide MN block) unused for N = 64.
+  return umma_desc_sw128(smem_addr);
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(int M, int N) {
+  return umma_idesc_bf16(M, N) | (1u << 16);  // b_major = MN
+}
 
 template <int TMEM_COLS>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(256, (TMEM_COLS <= 256) ? 2 : 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                     const __grid_constant__ CUtensorMap mapV, const AttnTcDev p) {
   extern __shared__ uint8_t smem_raw[];
+  __shared__ float s_red[2][128];
+  __shared__ uint64_t s_bar[2];
+  __shared__ uint32_t s_tmem;
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  uint8_t* base_ptr = smem_raw + (base - raw);
-  const uint32_t bar_load = base + ATT_BAR, bar_mma = base + ATT_BAR + 8, tmem_slot = base + ATT_BAR + 16;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + ATT_BAR + 16);
+  const uint32_t bar_load = smem_u32(&s_bar[0]), bar_mma = smem_u32(&s_bar[1]);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qd = warp & 3, hf = warp >> 2;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int row = warp * 32 + lane;  // query row inside the tile == TMEM lane
+  const int row = qd * 32 + lane;  // query row inside the tile == TMEM lane
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapQ);
@@ -158,13 +171,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     fence_proxy_async();
   }
   if (warp == 0) {
-    tmem_alloc<TMEM_COLS>(tmem_slot);
+    tmem_alloc<TMEM_COLS>(smem_u32(&s_tmem));
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&s_tmem);
+  const uint32_t sV = base + p.sv_off;
 
   // ---- loads ---------------------------------------------------------------------------------------
   if (threadIdx.x == 0) {
@@ -173,13 +187,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     tma_load_4d(base + ATT_SQ, &mapQ, bar_load, 0, qt * 128, h, b);
     tma_load_4d(base + ATT_SK, &mapK, bar_load, 0, 0, h, b);
     if (p.n1 > 0) tma_load_4d(base + ATT_SK + 32768, &mapK, bar_load, 0, 256, h, b);
-    for (int kb = 0; kb < p.nblk; ++kb)
-      tma_load_3d(base + ATT_SV + kb * 8192, &mapV, bar_load, kb * 64, 0, b * p.heads + h);
-  }
-  mbar_wait(bar_load, 0);
-
-  // ---- S = Q K^T -------------------------------------------------------------------------------------
-  if (threadIdx.x == 0) {
+    for (int kb = 0; kb < p.nblk; ++kb) tma_load_4d(sV + kb * 8192, &mapV, bar_load, 0, kb * 64, h, b);
+    mbar_wait(bar_load, 0);
+    // ---- S = Q K^T ---------------------------------------------------------------------------------
     tc_fence_after();
     const uint64_t dq = umma_desc_sw128(base + ATT_SQ);
     {
@@ -199,30 +209,40 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   mbar_wait(bar_mma, 0);
   tc_fence_after();
 
-  const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t trow = tmem + (static_cast<uint32_t>(qd * 32) << 16);
 
-  // ---- pass 1: row maximum over the valid keys -----------------------------------------------------------
+  // ---- pass 1: row maximum over the valid keys (each half-warp-group scans its key blocks) -----------------
   float mx = -INFINITY;
-  for (int c = 0; c < p.Tp; c += 32) {
-    float v[32];
-    tmem_ld_32x32(trow + c, v);
+  for (int r0 = 0; r0 < p.nblk; r0 += 4) {
+    const int cnt = min(4, p.nblk - r0);
+    const int per = (cnt + 1) >> 1;
+    const int b0 = r0 + hf * per, b1 = min(r0 + cnt, b0 + per);
+    for (int c = b0 * 64; c < b1 * 64; c += 32) {
+      float v[32];
+      tmem_ld_32x32(trow + c, v);
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (c + j < p.T) mx = fmaxf(mx, v[j]);
+      for (int j = 0; j < 32; ++j)
+        if (c + j < p.T) mx = fmaxf(mx, v[j]);
+    }
   }
+  s_red[hf][row] = mx;
+  __syncthreads();
+  mx = fmaxf(s_red[0][row], s_red[1][row]);
   const float mscaled = mx * p.scale_log2e;
 
-  // ---- pass 2: P = exp2(S*scale - max) as bf16 into swizzled smem, then O (+)= P V -------------------------
+  // ---- pass 2: P = exp2(S*scale - max) as bf16 into swizzled smem (over Q/K), then O (+)= P V -----------------
   float sum = 0.f;
   uint32_t mma_parity = 1;
   for (int r0 = 0; r0 < p.nblk; r0 += 4) {
-    const int r1 = min(r0 + 4, p.nblk);
+    const int cnt = min(4, p.nblk - r0);
+    const int per = (cnt + 1) >> 1;
+    const int b0 = r0 + hf * per, b1 = min(r0 + cnt, b0 + per);
     if (r0 > 0) {
       mbar_wait(bar_mma, mma_parity);  // previous P V chain has finished reading sP
       mma_parity ^= 1u;
       tc_fence_after();
     }
-    for (int kb = r0; kb < r1; ++kb) {
+    for (int kb = b0; kb < b1; ++kb) {
       const uint32_t sp_row = base + ATT_SP + (kb - r0) * 16384 + row * 128;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -231,7 +251,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         tmem_ld_32x32(trow + c, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float e = (c + j < p.T) ? exp2f(fmaf(v[j], p.scale_log2e, -mscaled)) : 0.f;
+          const float e = (c + j < p.T) ? ex2_approx(fmaf(v[j], p.scale_log2e, -mscaled)) : 0.f;
           v[j] = e;
           sum += e;
         }
@@ -253,27 +273,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     __syncthreads();
     if (threadIdx.x == 0) {
       tc_fence_after();
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
-      for (int kb = r0; kb < r1; ++kb) {
+      constexpr uint32_t idesc = umma_idesc_bf16_bmn(128, 64);
+      for (int kb = r0; kb < r0 + cnt; ++kb) {
         const uint64_t dp = umma_desc_sw128(base + ATT_SP + (kb - r0) * 16384);
-        const uint64_t dv = umma_desc_sw128(base + ATT_SV + kb * 8192);
+        const uint64_t dv = umma_desc_sw128_mn(sV + kb * 8192);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem, dp + 2u * k, dv + 2u * k, idesc, (kb | k) != 0);
+        for (int k = 0; k < 4; ++k)  // 16 keys per MMA: +32 B along P's rows, +16 rows (2048 B) down V
+          umma_bf16(tmem, dp + 2u * k, dv + 128u * k, idesc, (kb | k) != 0);
       }
       umma_commit(bar_mma);
     }
   }
+  s_red[hf][row] = sum;   // safe: every thread passed the barrier above after reading the maxima
   mbar_wait(bar_mma, mma_parity);
   tc_fence_after();
+  __syncthreads();
+  sum = s_red[0][row] + s_red[1][row];
 
-  // ---- epilogue: O / rowsum -> ctx ----------------------------------------------------------------------------
+  // ---- epilogue: O / rowsum -> ctx (each half takes 32 of the 64 output columns) ----------------------------------
   const int i = qt * 128 + row;
   const float inv = 1.0f / sum;
-  __nv_bfloat16* orow = p.ctx + ((long long)b * p.T + i) * p.H + h * 64;
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
+  __nv_bfloat16* orow = p.ctx + ((long long)b * p.T + i) * p.H + h * 64 + hf * 32;
+  {
     float v[32];
-    tmem_ld_32x32(trow + half * 32, v);
+    tmem_ld_32x32(trow + hf * 32, v);
     if (i < p.T) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
@@ -282,7 +305,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         u.y = pack_bf16x2(v[j + 2] * inv, v[j + 3] * inv);
         u.z = pack_bf16x2(v[j + 4] * inv, v[j + 5] * inv);
         u.w = pack_bf16x2(v[j + 6] * inv, v[j + 7] * inv);
-        *reinterpret_cast<uint4*>(orow + half * 32 + j) = u;
+        *reinterpret_cast<uint4*>(orow + j) = u;
       }
     }
   }
@@ -298,11 +321,14 @@ bool attention_tc_supported(const AttnParams& p) {
   return p.hd == 64 && p.T <= 512 && p.pos_proj == nullptr && (p.H % 8 == 0);
 }
 
+static size_t att_smem(int Tp) { return (Tp <= 256 ? 65536 : 81920) + (size_t)(Tp / 64) * 8192 + 1024; }
+
 std::string attention_tc_init() {
-  cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM);
+  const int mx = (int)att_smem(512);
+  cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
   if (e != cudaSuccess) return std::string("cudaFuncSetAttribute(attention_tc_kernel): ") + cudaGetErrorString(e);
   return "";
 }
@@ -320,9 +346,10 @@ std::string attention_tc_prepare(const AttnParams& p, AttnTcPlan** out) {
   pl->dev.nblk = Tp / 64;
   pl->dev.n0 = Tp < 256 ? Tp : 256;
   pl->dev.n1 = Tp > 256 ? Tp - 256 : 0;
+  pl->dev.sv_off = Tp <= 256 ? 65536 : 81920;
   pl->dev.scale_log2e = p.scale * 1.4426950408889634f;
   pl->grid = dim3((p.T + 127) / 128, p.heads, p.B);
-  pl->smem = ATT_SMEM;
+  pl->smem = att_smem(Tp);
   pl->tmem_cols = Tp <= 64 ? 64 : (Tp <= 128 ? 128 : (Tp <= 256 ? 256 : 512));
   const uint64_t H3 = 3ull * p.H;
   std::string err;
@@ -331,14 +358,10 @@ std::string attention_tc_prepare(const AttnParams& p, AttnTcPlan** out) {
     uint64_t str[3] = {H3 * 2, 128, (uint64_t)p.T * H3 * 2};
     uint32_t boxq[4] = {64, 128, 1, 1};
     uint32_t boxk[4] = {64, 256, 1, 1};
+    uint32_t boxv[4] = {64, 64, 1, 1};
     err = make_tensor_map_bf16(&pl->mapQ, p.qkv, 4, dims, str, boxq);
     if (err.empty()) err = make_tensor_map_bf16(&pl->mapK, p.qkv + p.H, 4, dims, str, boxk);
-  }
-  if (err.empty()) {
-    uint64_t dims[3] = {(uint64_t)Tp, 64, (uint64_t)p.heads * p.B};
-    uint64_t str[2] = {(uint64_t)Tp * 2, (uint64_t)Tp * 128};
-    uint32_t box[3] = {64, 64, 1};
-    err = make_tensor_map_bf16(&pl->mapV, p.vt, 3, dims, str, box);
+    if (err.empty()) err = make_tensor_map_bf16(&pl->mapV, p.qkv + 2 * p.H, 4, dims, str, boxv);
   }
   if (!err.empty()) {
     delete pl;
@@ -350,10 +373,10 @@ std::string attention_tc_prepare(const AttnParams& p, AttnTcPlan** out) {
 
 std::string attention_tc_launch(const AttnTcPlan* pl, cudaStream_t s) {
   switch (pl->tmem_cols) {
-    case 64: attention_tc_kernel<64><<<pl->grid, 128, pl->smem, s>>>(pl->mapQ, pl->mapK, pl->mapV, pl->dev); break;
-    case 128: attention_tc_kernel<128><<<pl->grid, 128, pl->smem, s>>>(pl->mapQ, pl->mapK, pl->mapV, pl->dev); break;
-    case 256: attention_tc_kernel<256><<<pl->grid, 128, pl->smem, s>>>(pl->mapQ, pl->mapK, pl->mapV, pl->dev); break;
-    default: attention_tc_kernel<512><<<pl->grid, 128, pl->smem, s>>>(pl->mapQ, pl->mapK, pl->mapV, pl->dev); break;
+    case 64: attention_tc_kernel<64><<<pl->grid, 256, pl->smem, s>>>(pl->mapQ, pl->mapK, pl->mapV, pl->dev); break;
+    case 128: attention_tc_kernel<128><<<pl->grid, 256, pl->smem, s>>>(pl->mapQ, pl->mapK, pl->mapV, pl->dev); break;
+    case 256: attention_tc_kernel<256><<<pl->grid, 256, pl->smem, s>>>(pl->mapQ, pl->mapK, pl->mapV, pl->dev); break;
+    default: attention_tc_kernel<512><<<pl->grid, 256, pl->smem, s>>>(pl->mapQ, pl->mapK, pl->mapV, pl->dev); break;
   }
   W2S_CUDA_OK(cudaGetLastError());
   return "";

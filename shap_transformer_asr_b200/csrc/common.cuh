@@ -31,15 +31,26 @@ namespace w2s {
 // ---------------------------------------------------------------------------------------------
 enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_SWISH = 2 };
 
-// erfc(z), z >= 0, Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): one ex2 + one rcp + 5 FMA.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// erfc(z), z >= 0, Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): one MUFU.EX2 + one MUFU.RCP + 7 FMA-pipe ops.
 __device__ __forceinline__ float erfc_pos(float z) {
-  float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
   p *= t;
-  return p * __expf(-z * z);
+  return p * ex2_approx(-1.4426950408889634f * z * z);
 }
 
 // exact-erf GELU (HF ACT2FN["gelu"]): 0.5 v (1 + erf(v / sqrt 2))
@@ -48,7 +59,7 @@ __device__ __forceinline__ float gelu_erf(float v) {
   return v >= 0.f ? fmaf(-v, q, v) : v * q;
 }
 
-__device__ __forceinline__ float swish(float v) { return v * __frcp_rn(1.0f + __expf(-v)); }
+__device__ __forceinline__ float swish(float v) { return v * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v)); }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_GELU) return gelu_erf(v);

@@ -314,14 +314,89 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
   }
 }
 
+// vectorised variant: H = 128 * NV, each lane owns NV float4 (columns 4*(lane + 32*i) ..)
+template <bool IN_F32, int NV>
+__global__ void __launch_bounds__(256) layernorm_vec_kernel(const void* __restrict__ in, long long rows,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float eps, int act,
+                                                             __nv_bfloat16* __restrict__ out,
+                                                             float* __restrict__ out_f32) {
+  constexpr int H = 128 * NV;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float4 v[NV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + 32 * i;
+    if constexpr (IN_F32) {
+      v[i] = __ldcs(reinterpret_cast<const float4*>(in) + row * (H / 4) + c4);
+    } else {
+      const uint2 u = __ldcs(reinterpret_cast<const uint2*>(in) + row * (H / 4) + c4);
+      v[i] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+    }
+    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(sum) * (1.0f / H);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    sq += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(sq) * (1.0f / H) + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c4 = lane + 32 * i;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+    const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+    float4 y;
+    y.x = fmaf((v[i].x - mean) * rstd, g.x, bt.x);
+    y.y = fmaf((v[i].y - mean) * rstd, g.y, bt.y);
+    y.z = fmaf((v[i].z - mean) * rstd, g.z, bt.z);
+    y.w = fmaf((v[i].w - mean) * rstd, g.w, bt.w);
+    if (act == ACT_GELU) {
+      y.x = gelu_erf(y.x); y.y = gelu_erf(y.y); y.z = gelu_erf(y.z); y.w = gelu_erf(y.w);
+    } else if (act == ACT_SWISH) {
+      y.x = swish(y.x); y.y = swish(y.y); y.z = swish(y.z); y.w = swish(y.w);
+    }
+    if (out) {
+      uint2 u;
+      u.x = pack_bf16x2(y.x, y.y);
+      u.y = pack_bf16x2(y.z, y.w);
+      reinterpret_cast<uint2*>(out)[row * (H / 4) + c4] = u;
+    }
+    if (out_f32) reinterpret_cast<float4*>(out_f32)[row * (H / 4) + c4] = y;
+  }
+}
+
+template <bool IN_F32>
+static bool launch_ln_vec(const void* in, long long rows, int H, const float* gamma, const float* beta, float eps,
+                          int act, __nv_bfloat16* out, float* out_f32, cudaStream_t s) {
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  switch (H) {
+    case 128: layernorm_vec_kernel<IN_F32, 1><<<grid, 256, 0, s>>>(in, rows, gamma, beta, eps, act, out, out_f32); return true;
+    case 256: layernorm_vec_kernel<IN_F32, 2><<<grid, 256, 0, s>>>(in, rows, gamma, beta, eps, act, out, out_f32); return true;
+    case 512: layernorm_vec_kernel<IN_F32, 4><<<grid, 256, 0, s>>>(in, rows, gamma, beta, eps, act, out, out_f32); return true;
+    case 768: layernorm_vec_kernel<IN_F32, 6><<<grid, 256, 0, s>>>(in, rows, gamma, beta, eps, act, out, out_f32); return true;
+    case 1024: layernorm_vec_kernel<IN_F32, 8><<<grid, 256, 0, s>>>(in, rows, gamma, beta, eps, act, out, out_f32); return true;
+    default: return false;
+  }
+}
+
 std::string launch_layernorm(const void* in, int in_fp32, long long rows, int H, const float* gamma,
                              const float* beta, float eps, int act, __nv_bfloat16* out, float* out_f32,
                              cudaStream_t s) {
   if (H > 1024) return "layernorm: H > 1024 not supported";
   if (rows == 0) return "";
-  const unsigned grid = (unsigned)((rows + 7) / 8);
-  if (in_fp32) layernorm_kernel<true><<<grid, 256, 0, s>>>(in, rows, H, gamma, beta, eps, act, out, out_f32);
-  else layernorm_kernel<false><<<grid, 256, 0, s>>>(in, rows, H, gamma, beta, eps, act, out, out_f32);
+  const bool vec = in_fp32 ? launch_ln_vec<true>(in, rows, H, gamma, beta, eps, act, out, out_f32, s)
+                           : launch_ln_vec<false>(in, rows, H, gamma, beta, eps, act, out, out_f32, s);
+  if (!vec) {
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    if (in_fp32) layernorm_kernel<true><<<grid, 256, 0, s>>>(in, rows, H, gamma, beta, eps, act, out, out_f32);
+    else layernorm_kernel<false><<<grid, 256, 0, s>>>(in, rows, H, gamma, beta, eps, act, out, out_f32);
+  }
   W2S_CUDA_OK(cudaGetLastError());
   return "";
 }

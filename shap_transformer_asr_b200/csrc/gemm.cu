@@ -5,7 +5,7 @@
 //   warp 1 lane 0 : MMA issuer     -- tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16 per instruction,
 //                                     accumulating in one of two TMEM accumulator slots
 //   warp 2        : TMEM allocator
-//   warps 4..7    : epilogue       -- tcgen05.ld the finished accumulator (thread = row), bias / activation /
+//   warps 4..11   : epilogue       -- tcgen05.ld the finished accumulator (thread = row), bias / activation /
 //                                     GLU / residual, vectorised global stores, while the MMA warp already
 //                                     works on the next tile in the other TMEM slot
 // Pipelines: full/empty mbarriers per smem stage (TMA <-> MMA), tmem_full/tmem_empty per accumulator slot
@@ -22,21 +22,30 @@ namespace w2s {
 // ------------------------------------------------------------------------------------------------
 template <int CH>
 __device__ __forceinline__ void epi_store(const EpiParams& e, int N, int g, int b, int m, int ncol0, float* v) {
+  // N is a multiple of the column chunk in both kernels (N % 4 == 0; tcgen05 tiles divide N exactly)
   if (ncol0 >= N) return;
   if (e.bias) {
-    const float* bp = e.bias + (long long)g * N + ncol0;
+    const float4* bp = reinterpret_cast<const float4*>(e.bias + (long long)g * N + ncol0);
 #pragma unroll
-    for (int j = 0; j < CH; ++j)
-      if (ncol0 + j < N) v[j] += __ldg(bp + j);
+    for (int j = 0; j < CH / 4; ++j) {
+      const float4 t = __ldg(bp + j);
+      v[4 * j] += t.x;
+      v[4 * j + 1] += t.y;
+      v[4 * j + 2] += t.z;
+      v[4 * j + 3] += t.w;
+    }
   }
-  if (e.act != ACT_NONE) {
+  if (e.act == ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < CH; ++j) v[j] = apply_act(v[j], e.act);
+    for (int j = 0; j < CH; ++j) v[j] = gelu_erf(v[j]);
+  } else if (e.act == ACT_SWISH) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) v[j] = swish(v[j]);
   }
   int nout0 = ncol0, nvals = CH, Nout = N;
   if (e.glu) {
 #pragma unroll
-    for (int j = 0; j < CH / 2; ++j) v[j] = v[2 * j] * __frcp_rn(1.0f + __expf(-v[2 * j + 1]));
+    for (int j = 0; j < CH / 2; ++j) v[j] = v[2 * j] * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v[2 * j + 1]));
     nout0 = ncol0 >> 1;
     nvals = CH / 2;
     Nout = N >> 1;
@@ -155,7 +164,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int tile, int
 }
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                const GemmDev p) {
   using C = TcCfg<BN>;
@@ -185,7 +194,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), 8);
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -264,8 +273,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const int m = tc.m0 + q * 32 + lane;
       const bool row_ok = m < p.M;
       const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C::ACC_COLS;
+      // warps 4..7 take the even column chunks of their lane quadrant, warps 8..11 the odd ones
 #pragma unroll 1
-      for (int c = 0; c < BN; c += C::CH) {
+      for (int c = ((warp - 4) >> 2) * C::CH; c < BN; c += 2 * C::CH) {
         float v[C::CH];
         if constexpr (C::CH == 32) tmem_ld_32x32(t0 + c, v);
         else tmem_ld_32x16(t0 + c, v);
@@ -451,11 +461,11 @@ std::string gemm_prepare(const GemmProblem& p, int num_sms, GemmLaunch* out) {
 
 std::string gemm_launch_tc(const GemmLaunch& l, cudaStream_t s) {
   switch (l.bn) {
-    case 256: gemm_tc_kernel<256><<<l.grid, 256, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
-    case 128: gemm_tc_kernel<128><<<l.grid, 256, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
-    case 64: gemm_tc_kernel<64><<<l.grid, 256, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
-    case 48: gemm_tc_kernel<48><<<l.grid, 256, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
-    case 32: gemm_tc_kernel<32><<<l.grid, 256, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
+    case 256: gemm_tc_kernel<256><<<l.grid, 384, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
+    case 128: gemm_tc_kernel<128><<<l.grid, 384, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
+    case 64: gemm_tc_kernel<64><<<l.grid, 384, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
+    case 48: gemm_tc_kernel<48><<<l.grid, 384, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
+    case 32: gemm_tc_kernel<32><<<l.grid, 384, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
     default: return "gemm: bad BN";
   }
   W2S_CUDA_OK(cudaGetLastError());
