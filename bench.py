@@ -179,7 +179,15 @@ def run_b200(args):
 
     wl, cfg, clip, Z, kw = build_problem(args.workload)
     model = make_hf_model(cfg)
-    eng = Engine(model, cfg, device=local, max_batch=args.batch)
+    # batch tile: rows = B * T' should fill whole waves of 128-row tiles on 148 SMs (B = floor(148*128*k / T'))
+    T = cfg.num_frames(wl.num_samples)
+    batch = args.batch
+    if batch <= 0:
+        k = 1
+        while (148 * 128 * k) // T < 64:
+            k += 1
+        batch = min(wl.num_coalitions, (148 * 128 * k) // T)
+    eng = Engine(model, cfg, device=local, max_batch=batch)
     eng.set_clip(clip, num_segments=wl.num_segments)
     # targets: per-character frames of the unmasked clip (all frames if the random-init transcript is empty)
     eng.set_targets("logits")
@@ -304,7 +312,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="C2")
-    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--batch", type=int, default=0, help="coalitions per batch tile (0 = fill whole waves)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

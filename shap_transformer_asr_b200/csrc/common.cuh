@@ -59,6 +59,26 @@ __device__ __forceinline__ float gelu_erf(float v) {
   return v >= 0.f ? fmaf(-v, q, v) : v * q;
 }
 
+// Two GELUs at once on Blackwell's packed fp32 pipe (FFMA2/FMUL2: fma.rn.f32x2): ~10 issue slots per element
+// instead of ~17.  Phi(v) = v >= 0 ? 1 - q : q with q = 0.5 erfc(|v|/sqrt 2); the 0.5 is folded into the
+// A&S 7.1.26 coefficients.
+__device__ __forceinline__ float2 gelu_erf2(float2 v) {
+  const float2 z = __fmul2_rn(make_float2(fabsf(v.x), fabsf(v.y)), make_float2(0.70710678118654752f, 0.70710678118654752f));
+  const float2 den = __ffma2_rn(z, make_float2(0.3275911f, 0.3275911f), make_float2(1.0f, 1.0f));
+  const float2 t = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+  float2 p = __ffma2_rn(t, make_float2(0.5f * 1.061405429f, 0.5f * 1.061405429f),
+                        make_float2(0.5f * -1.453152027f, 0.5f * -1.453152027f));
+  p = __ffma2_rn(p, t, make_float2(0.5f * 1.421413741f, 0.5f * 1.421413741f));
+  p = __ffma2_rn(p, t, make_float2(0.5f * -0.284496736f, 0.5f * -0.284496736f));
+  p = __ffma2_rn(p, t, make_float2(0.5f * 0.254829592f, 0.5f * 0.254829592f));
+  p = __fmul2_rn(p, t);
+  const float2 a = __fmul2_rn(__fmul2_rn(z, z), make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  const float2 q = __fmul2_rn(p, make_float2(ex2_approx(a.x), ex2_approx(a.y)));
+  const float2 omq = __ffma2_rn(q, make_float2(-1.0f, -1.0f), make_float2(1.0f, 1.0f));
+  const float2 phi = make_float2(v.x >= 0.f ? omq.x : q.x, v.y >= 0.f ? omq.y : q.y);
+  return __fmul2_rn(v, phi);
+}
+
 __device__ __forceinline__ float swish(float v) { return v * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v)); }
 
 __device__ __forceinline__ float apply_act(float v, int act) {

@@ -140,12 +140,17 @@ __global__ void __launch_bounds__(256, 2) conv0_kernel(const Conv0Params p, int 
   float* xs = sm;                      // FT*stride + KW window
   float* fmean = xs + FT * p.stride + KW;  // [FT] (layer variant)
   float* frstd = fmean + FT;
+  float2* xs2 = reinterpret_cast<float2*>(frstd + FT + ((FT * p.stride + KW) & 1));  // (x, x) pairs, 8-byte aligned
   const int row = blockIdx.y;
   const int f0 = blockIdx.x * FT;
   const int nf = min(FT, p.T0 - f0);
   const float* x = p.x + (long long)row * p.ld + (long long)f0 * p.stride;
   const int nwin = (nf - 1) * p.stride + KW;
-  for (int i = threadIdx.x; i < nwin; i += blockDim.x) xs[i] = __ldg(x + i);
+  for (int i = threadIdx.x; i < nwin; i += blockDim.x) {
+    const float t = __ldg(x + i);
+    xs[i] = t;
+    xs2[i] = make_float2(t, t);
+  }
   __syncthreads();
 
   if constexpr (LAYER) {
@@ -175,43 +180,45 @@ __global__ void __launch_bounds__(256, 2) conv0_kernel(const Conv0Params p, int 
   const int fpar = blockDim.x / tpf;   // frames in flight per CTA
   const int c0 = (threadIdx.x % tpf) * 8;
   const int fslot = threadIdx.x / tpf;
-  float w[8][KW], ca[8], cb[8];
+  // channel pairs on the packed fp32 pipe: (y[2i], y[2i+1]) += (w[2i][j], w[2i+1][j]) * (x[j], x[j])
+  float2 w2[4][KW], ca2[4], cb2[4], bias2[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 4; ++i) {
 #pragma unroll
-    for (int j = 0; j < KW; ++j) w[i][j] = __ldg(p.w + (c0 + i) * KW + j);
+    for (int j = 0; j < KW; ++j)
+      w2[i][j] = make_float2(__ldg(p.w + (c0 + 2 * i) * KW + j), __ldg(p.w + (c0 + 2 * i + 1) * KW + j));
     if constexpr (LAYER) {
-      ca[i] = __ldg(p.gamma + c0 + i);
-      cb[i] = __ldg(p.beta + c0 + i);
+      ca2[i] = make_float2(__ldg(p.gamma + c0 + 2 * i), __ldg(p.gamma + c0 + 2 * i + 1));
+      cb2[i] = make_float2(__ldg(p.beta + c0 + 2 * i), __ldg(p.beta + c0 + 2 * i + 1));
+      bias2[i] = p.bias ? make_float2(__ldg(p.bias + c0 + 2 * i), __ldg(p.bias + c0 + 2 * i + 1)) : make_float2(0.f, 0.f);
     } else {
-      ca[i] = p.gn_a[(long long)row * p.C + c0 + i];
-      cb[i] = p.gn_b[(long long)row * p.C + c0 + i];
+      const float* ga = p.gn_a + (long long)row * p.C + c0 + 2 * i;
+      const float* gb = p.gn_b + (long long)row * p.C + c0 + 2 * i;
+      ca2[i] = make_float2(ga[0], ga[1]);
+      cb2[i] = make_float2(gb[0], gb[1]);
+      bias2[i] = make_float2(0.f, 0.f);
     }
   }
-  float bias[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) bias[i] = (LAYER && p.bias) ? __ldg(p.bias + c0 + i) : 0.f;
 
   __nv_bfloat16* out = p.out + ((long long)row * p.T0 + f0) * p.C + c0;
   for (int f = fslot; f < nf; f += fpar) {
-    float xv[KW];
+    float2 xv[KW];
 #pragma unroll
-    for (int j = 0; j < KW; ++j) xv[j] = xs[f * p.stride + j];
-    float y[8];
+    for (int j = 0; j < KW; ++j) xv[j] = xs2[f * p.stride + j];
+    uint32_t packed[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float a = bias[i];
+    for (int i = 0; i < 4; ++i) {
+      float2 a = bias2[i];
 #pragma unroll
-      for (int j = 0; j < KW; ++j) a = fmaf(w[i][j], xv[j], a);
-      if constexpr (LAYER) a = (a - fmean[f]) * frstd[f];
-      y[i] = gelu_erf(fmaf(a, ca[i], cb[i]));
+      for (int j = 0; j < KW; ++j) a = __ffma2_rn(w2[i][j], xv[j], a);
+      if constexpr (LAYER) {
+        const float m = fmean[f], r = frstd[f];
+        a = __fmul2_rn(__fadd2_rn(a, make_float2(-m, -m)), make_float2(r, r));
+      }
+      const float2 y = gelu_erf2(__ffma2_rn(a, ca2[i], cb2[i]));
+      packed[i] = pack_bf16x2(y.x, y.y);
     }
-    uint4 u;
-    u.x = pack_bf16x2(y[0], y[1]);
-    u.y = pack_bf16x2(y[2], y[3]);
-    u.z = pack_bf16x2(y[4], y[5]);
-    u.w = pack_bf16x2(y[6], y[7]);
-    *reinterpret_cast<uint4*>(out + (long long)f * p.C) = u;
+    *reinterpret_cast<uint4*>(out + (long long)f * p.C) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
   }
 }
 
@@ -220,9 +227,9 @@ std::string launch_conv0(const Conv0Params& p, bool layer_norm, cudaStream_t s) 
   const int tpf = p.C / 8;
   if (p.C % 8 || tpf > 256 || (256 % tpf)) return "conv0: channel count must be 8 * (a divisor of 256)";
   if (p.n == 0) return "";
-  const int FT = 128;
+  const int FT = p.T0 >= 4096 ? 512 : 128;
   dim3 grid((p.T0 + FT - 1) / FT, p.n);
-  const size_t smem = (size_t)(FT * p.stride + p.kw + 2 * FT) * sizeof(float);
+  const size_t smem = (size_t)(3 * (FT * p.stride + p.kw) + 2 * FT + 2) * sizeof(float);
   if (layer_norm) conv0_kernel<10, true><<<grid, 256, smem, s>>>(p, FT);
   else conv0_kernel<10, false><<<grid, 256, smem, s>>>(p, FT);
   W2S_CUDA_OK(cudaGetLastError());
@@ -407,28 +414,37 @@ std::string launch_layernorm(const void* in, int in_fp32, long long rows, int H,
 // =================================================================================================
 __global__ void __launch_bounds__(256) pos_pad_kernel(const __nv_bfloat16* __restrict__ h, int T, int H, int G,
                                                        int kpos, __nv_bfloat16* __restrict__ out) {
+  // one thread = 8 consecutive channels (16 bytes) of one padded row
   const int cpg = H / G;
   const int Tp = T + kpos;
-  const int W = G * 64;
-  const long long total = (long long)gridDim.y * Tp * W;
-  (void)total;
+  const int W8 = G * 8;
   const int b = blockIdx.y;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)Tp * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)Tp * W8;
        i += (long long)gridDim.x * blockDim.x) {
-    const int tp = (int)(i / W);
-    const int col = (int)(i - (long long)tp * W);
-    const int g = col >> 6, c = col & 63;
+    const int tp = (int)(i / W8);
+    const int c8 = (int)(i - (long long)tp * W8);
+    const int g = c8 >> 3, c = (c8 & 7) * 8;
     const int t = tp - kpos / 2;
-    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
-    if (t >= 0 && t < T && c < cpg) v = h[((long long)b * T + t) * H + g * cpg + c];
-    out[(long long)b * Tp * W + i] = v;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (t >= 0 && t < T && c < cpg) {
+      const __nv_bfloat16* src = h + ((long long)b * T + t) * H + g * cpg + c;
+      if (c + 8 <= cpg && (cpg % 8) == 0) {
+        v = *reinterpret_cast<const uint4*>(src);
+      } else {
+        __nv_bfloat16 tmp[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tmp[k] = (c + k < cpg) ? src[k] : __float2bfloat16_rn(0.f);
+        v = *reinterpret_cast<uint4*>(tmp);
+      }
+    }
+    reinterpret_cast<uint4*>(out + (long long)b * Tp * G * 64)[i] = v;
   }
 }
 std::string launch_pos_pad(const __nv_bfloat16* h, int B, int T, int H, int G, int kpos, __nv_bfloat16* out,
                            cudaStream_t s) {
   if (H % G || H / G > 64) return "pos_pad: channels per group must be <= 64";
   if (B == 0) return "";
-  const long long per = (long long)(T + kpos) * G * 64;
+  const long long per = (long long)(T + kpos) * G * 8;
   dim3 grid((unsigned)((per + 255) / 256 > 1024 ? 1024 : (per + 255) / 256), B);
   pos_pad_kernel<<<grid, 256, 0, s>>>(h, T, H, G, kpos, out);
   W2S_CUDA_OK(cudaGetLastError());

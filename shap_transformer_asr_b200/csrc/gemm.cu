@@ -37,7 +37,11 @@ __device__ __forceinline__ void epi_store(const EpiParams& e, int N, int g, int 
   }
   if (e.act == ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < CH; ++j) v[j] = gelu_erf(v[j]);
+    for (int j = 0; j < CH; j += 2) {
+      const float2 r = gelu_erf2(make_float2(v[j], v[j + 1]));
+      v[j] = r.x;
+      v[j + 1] = r.y;
+    }
   } else if (e.act == ACT_SWISH) {
 #pragma unroll
     for (int j = 0; j < CH; ++j) v[j] = swish(v[j]);
