@@ -108,6 +108,7 @@ struct w2s_handle {
   bf16 *fpn = nullptr, *h0 = nullptr, *hp = nullptr, *hb = nullptr, *h1 = nullptr, *qkv = nullptr, *vt = nullptr,
        *ctx = nullptr, *ffn = nullptr;
   float* pre = nullptr;
+  bf16* hrot = nullptr;
   double* wls_work = nullptr;
   long long wls_cap = 0;
   std::map<int, std::unique_ptr<Plan>> plans;
@@ -258,13 +259,81 @@ std::string load_weights(w2s_handle* h, const WeightTable& wt) {
       W2S_TRY(copy_f32(h, wt, lp + "final_layer_norm.bias", H, &w.ln2_b));
     }
   } else {
-    return "Wav2Vec2ConformerForCTC weights: conformer encoder is not built into this library yet";
+    const int kd = c.conv_depthwise_kernel_size;
+    for (int l = 0; l < c.num_hidden_layers; ++l) {
+      LayerW& w = h->layers[l];
+      const std::string lp = P + "encoder.layers." + std::to_string(l) + ".";
+      auto lin = [&](const std::string& nm, int64_t out, int64_t in, bf16** wdst, float** bdst) -> std::string {
+        W2S_TRY(dalloc(h->allocs, wdst, (size_t)out * in));
+        W2S_TRY(copy_bf16(h, wt, lp + nm + ".weight", out * in, *wdst));
+        if (bdst) W2S_TRY(copy_f32(h, wt, lp + nm + ".bias", out, bdst));
+        return "";
+      };
+      W2S_TRY(copy_f32(h, wt, lp + "ffn1_layer_norm.weight", H, &w.lnf1_g));
+      W2S_TRY(copy_f32(h, wt, lp + "ffn1_layer_norm.bias", H, &w.lnf1_b));
+      W2S_TRY(lin("ffn1.intermediate_dense", I, H, &w.w1, &w.b1));
+      W2S_TRY(lin("ffn1.output_dense", H, I, &w.w2, &w.b2));
+      W2S_TRY(copy_f32(h, wt, lp + "self_attn_layer_norm.weight", H, &w.ln1_g));
+      W2S_TRY(copy_f32(h, wt, lp + "self_attn_layer_norm.bias", H, &w.ln1_b));
+      W2S_TRY(dalloc(h->allocs, &w.wqkv, (size_t)3 * H * H));
+      W2S_TRY(copy_bf16(h, wt, lp + "self_attn.linear_q.weight", (int64_t)H * H, w.wqkv));
+      W2S_TRY(copy_bf16(h, wt, lp + "self_attn.linear_k.weight", (int64_t)H * H, w.wqkv + (size_t)H * H));
+      W2S_TRY(copy_bf16(h, wt, lp + "self_attn.linear_v.weight", (int64_t)H * H, w.wqkv + (size_t)2 * H * H));
+      W2S_TRY(dalloc(h->allocs, &w.bqkv, (size_t)3 * H));
+      const char* nm[3] = {"self_attn.linear_q.bias", "self_attn.linear_k.bias", "self_attn.linear_v.bias"};
+      for (int j = 0; j < 3; ++j) {
+        const float* b = nullptr;
+        W2S_TRY(wt.get(lp + nm[j], H, &b));
+        W2S_CUDA_OK(cudaMemcpy(w.bqkv + (size_t)j * H, b, sizeof(float) * H, cudaMemcpyDeviceToDevice));
+      }
+      W2S_TRY(lin("self_attn.linear_out", H, H, &w.wo, &w.bo));
+      if (c.position_embeddings_type == 1) {
+        W2S_TRY(lin("self_attn.linear_pos", H, H, &w.wpos, nullptr));
+        W2S_TRY(copy_f32(h, wt, lp + "self_attn.pos_bias_u", H, &w.bias_u));
+        W2S_TRY(copy_f32(h, wt, lp + "self_attn.pos_bias_v", H, &w.bias_v));
+      }
+      W2S_TRY(copy_f32(h, wt, lp + "conv_module.layer_norm.weight", H, &w.lnc_g));
+      W2S_TRY(copy_f32(h, wt, lp + "conv_module.layer_norm.bias", H, &w.lnc_b));
+      {
+        const float* src = nullptr;
+        W2S_TRY(wt.get(lp + "conv_module.pointwise_conv1.weight", (int64_t)2 * H * H, &src));
+        W2S_TRY(dalloc(h->allocs, &w.pw1, (size_t)2 * H * H));
+        W2S_TRY(launch_repack_glu(src, w.pw1, H, H, 0));
+      }
+      W2S_TRY(copy_f32(h, wt, lp + "conv_module.depthwise_conv.weight", (int64_t)H * kd, &w.dw_w));
+      {
+        const float *g = nullptr, *b = nullptr, *mu = nullptr, *var = nullptr;
+        W2S_TRY(wt.get(lp + "conv_module.batch_norm.weight", H, &g));
+        W2S_TRY(wt.get(lp + "conv_module.batch_norm.bias", H, &b));
+        W2S_TRY(wt.get(lp + "conv_module.batch_norm.running_mean", H, &mu));
+        W2S_TRY(wt.get(lp + "conv_module.batch_norm.running_var", H, &var));
+        W2S_TRY(dalloc(h->allocs, &w.dw_scale, (size_t)H));
+        W2S_TRY(dalloc(h->allocs, &w.dw_shift, (size_t)H));
+        W2S_TRY(launch_bn_fold(g, b, mu, var, H, 1e-5f, w.dw_scale, w.dw_shift, 0));
+      }
+      W2S_TRY(lin("conv_module.pointwise_conv2", H, H, &w.pw2, nullptr));
+      W2S_TRY(copy_f32(h, wt, lp + "ffn2_layer_norm.weight", H, &w.lnf2_g));
+      W2S_TRY(copy_f32(h, wt, lp + "ffn2_layer_norm.bias", H, &w.lnf2_b));
+      W2S_TRY(lin("ffn2.intermediate_dense", I, H, &w.f2w1, &w.f2b1));
+      W2S_TRY(lin("ffn2.output_dense", H, I, &w.f2w2, &w.f2b2));
+      W2S_TRY(copy_f32(h, wt, lp + "final_layer_norm.weight", H, &w.lnfin_g));
+      W2S_TRY(copy_f32(h, wt, lp + "final_layer_norm.bias", H, &w.lnfin_b));
+    }
   }
   W2S_TRY(dalloc(h->allocs, &h->head_w, (size_t)V * H));
   W2S_TRY(copy_bf16(h, wt, "lm_head.weight", (int64_t)V * H, h->head_w));
   W2S_TRY(copy_f32(h, wt, "lm_head.bias", V, &h->head_b));
   W2S_CUDA_OK(cudaDeviceSynchronize());
   return "";
+}
+
+GemmProblem plain_problem(const bf16* a, long long rows, int K, const bf16* w, int N) {
+  GemmProblem p;
+  p.a = a; p.a_cols = K; p.a_rows = rows; p.a_batches = 1; p.a_row_stride = K; p.a_batch_stride = rows * (long long)K;
+  p.a_kb_per_row = K / 64; p.a_g_col = 0;
+  p.w = w; p.M = (int)rows; p.N = N; p.K = K; p.Bz = 1; p.G = 1;
+  p.epi.ldg = 0; p.epi.ldb = 0; p.epi.ldm = N;
+  return p;
 }
 
 int64_t num_frames(const w2s_config& c, int64_t L, std::vector<int>* lens) {
@@ -322,6 +391,26 @@ std::string ensure_workspace(w2s_handle* h, long long L) {
   if (c.kind == 0) {
     W2S_TRY(dalloc(pool, &h->hp,
                    nb * (size_t)(T + c.num_conv_pos_embeddings) * c.num_conv_pos_embedding_groups * 64));
+  } else {
+    if (c.position_embeddings_type == 2) W2S_TRY(dalloc(pool, &h->hrot, rows * H));
+    if (c.position_embeddings_type == 1) {
+      // relative position table and its per-layer projection linear_pos(pe): input independent, built once per
+      // clip length (HF modeling_wav2vec2_conformer.py:159-205, :509-518)
+      const long long R = 2 * T - 1;
+      bf16* pe = nullptr;
+      W2S_TRY(dalloc(pool, &pe, (size_t)R * H));
+      W2S_TRY(launch_relpos((int)T, H, pe, 0));
+      for (int l = 0; l < c.num_hidden_layers; ++l) {
+        LayerW& w = h->layers[l];
+        W2S_TRY(dalloc(pool, &w.pos_proj, (size_t)R * H));
+        GemmProblem p = plain_problem(pe, R, H, w.wpos, H);
+        p.epi.out = w.pos_proj;
+        GemmLaunch gl;
+        W2S_TRY(gemm_prepare(p, h->num_sms, &gl));
+        W2S_TRY((h->cfg.flags & W2S_FLAG_VALIDATE_GEMM) ? gemm_launch_simt(gl, 0) : gemm_launch_tc(gl, 0));
+      }
+      W2S_CUDA_OK(cudaDeviceSynchronize());
+    }
   }
   h->ws_L = L;
   return "";
@@ -358,13 +447,10 @@ struct PlanBuilder {
     return "";
   }
   static GemmProblem plain(const bf16* a, long long rows, int K, const bf16* w, int N) {
-    GemmProblem p;
-    p.a = a; p.a_cols = K; p.a_rows = rows; p.a_batches = 1; p.a_row_stride = K; p.a_batch_stride = rows * (long long)K;
-    p.a_kb_per_row = K / 64; p.a_g_col = 0;
-    p.w = w; p.M = (int)rows; p.N = N; p.K = K; p.Bz = 1; p.G = 1;
-    p.epi.ldg = 0; p.epi.ldb = 0; p.epi.ldm = N;
-    return p;
+    return plain_problem(a, rows, K, w, N);
   }
+
+  std::string build_conformer();
 
   std::string build() {
     const w2s_config& c = h->cfg;
@@ -423,10 +509,15 @@ struct PlanBuilder {
     {
       GemmProblem p = plain(h->fpn, rows, Cl, h->fp_w, H);
       p.epi.bias = h->fp_b;
-      p.epi.out = h->h0;
+      if (c.kind == 0) {
+        p.epi.out = h->h0;
+      } else {  // conformer: the un-normalised residual stream lives in fp32
+        p.epi.out = h->pre;
+        p.epi.out_fp32 = 1;
+      }
       W2S_TRY(add_gemm("featproj", p));
     }
-    if (c.kind != 0) return "conformer encoder not built yet";
+    if (c.kind != 0) return build_conformer();
     const bool stable = c.do_stable_layer_norm != 0;
     // ---- K4: positional conv (grouped, k=128) + GELU + residual (+ LayerNorm) ----------------------------
     {
@@ -508,6 +599,104 @@ struct PlanBuilder {
     return "";
   }
 };
+
+std::string PlanBuilder::build_conformer() {
+  // HF wav2vec2_conformer/modeling_wav2vec2_conformer.py:633-717 (encoder), :568-630 (layer).  The residual
+  // stream `pre` is fp32; every sub-block reads a LayerNorm'd bf16 copy and adds its result back in the
+  // GEMM epilogue (alpha = 0.5 for the two macaron feed-forward blocks).
+  const w2s_config& c = h->cfg;
+  const int T = h->T, H = c.hidden_size, I = c.intermediate_size;
+  const long long rows = (long long)n * T;
+  const int act = c.hidden_act == 1 ? ACT_SWISH : ACT_GELU;
+  w2s_handle* hh = h;
+  const int nn = n;
+  AttnParams ap{};
+  ap.qkv = h->qkv; ap.ctx = h->ctx; ap.B = n; ap.T = T; ap.Tp = h->Tp; ap.H = H;
+  ap.heads = c.num_attention_heads; ap.hd = H / c.num_attention_heads;
+  ap.scale = 1.0f / sqrtf((float)ap.hd);
+  const bool rel = c.position_embeddings_type == 1, rotary = c.position_embeddings_type == 2;
+  AttnTcPlan* apl = nullptr;
+  const bool tc_attn = !rel && !simt_attn && attention_tc_supported(ap);
+  if (tc_attn) {
+    W2S_TRY(attention_tc_prepare(ap, &apl));
+    plan->attn.push_back(apl);
+  }
+  auto ffn = [&](const std::string& ls, const float* lg, const float* lb, const bf16* w1, const float* b1,
+                 const bf16* w2, const float* b2) -> std::string {
+    add_ln(ls + "ln", h->pre, 1, rows, H, lg, lb, 1e-5f, ACT_NONE, h->hb, nullptr);
+    GemmProblem p = plain(h->hb, rows, H, w1, I);
+    p.epi.bias = b1; p.epi.act = act; p.epi.out = h->ffn;
+    W2S_TRY(add_gemm(ls + "ffn1", p));
+    GemmProblem q = plain(h->ffn, rows, I, w2, H);
+    q.epi.bias = b2; q.epi.alpha = 0.5f;
+    q.epi.residual = h->pre; q.epi.res_fp32 = 1; q.epi.out = h->pre; q.epi.out_fp32 = 1;
+    W2S_TRY(add_gemm(ls + "ffn2", q));
+    return "";
+  };
+  for (int l = 0; l < c.num_hidden_layers; ++l) {
+    const LayerW& w = h->layers[l];
+    const std::string ls = "L" + std::to_string(l) + ".";
+    W2S_TRY(ffn(ls + "mac1_", w.lnf1_g, w.lnf1_b, w.w1, w.b1, w.w2, w.b2));
+    // ---- self-attention ----
+    add_ln(ls + "attn_ln", h->pre, 1, rows, H, w.ln1_g, w.ln1_b, 1e-5f, ACT_NONE, h->hb, nullptr);
+    if (rotary) {
+      const int base = c.rotary_embedding_base, hd = ap.hd;
+      add(ls + "rotary", [=](cudaStream_t s) { return launch_rotary(hh->hb, rows, T, H, hd, base, hh->hrot, s); });
+      GemmProblem p = plain(h->hrot, rows, H, w.wqkv, 2 * H);
+      p.epi.bias = w.bqkv; p.epi.out = h->qkv; p.epi.ldm = 3 * H;
+      W2S_TRY(add_gemm(ls + "qk", p));
+      GemmProblem v = plain(h->hb, rows, H, w.wqkv + (size_t)2 * H * H, H);
+      v.epi.bias = w.bqkv + 2 * H; v.epi.out = h->qkv + 2 * H; v.epi.ldm = 3 * H;
+      W2S_TRY(add_gemm(ls + "v", v));
+    } else {
+      GemmProblem p = plain(h->hb, rows, H, w.wqkv, 3 * H);
+      p.epi.bias = w.bqkv; p.epi.out = h->qkv;
+      W2S_TRY(add_gemm(ls + "qkv", p));
+    }
+    if (tc_attn) {
+      add(ls + "attention", [=](cudaStream_t s) { return attention_tc_launch(apl, s); });
+    } else {
+      AttnParams lp = ap;
+      if (rel) {
+        lp.pos_proj = w.pos_proj; lp.bias_u = w.bias_u; lp.bias_v = w.bias_v;
+      }
+      add(ls + "attention", [=](cudaStream_t s) { return launch_attention_simt(lp, s); });
+    }
+    {
+      GemmProblem p = plain(h->ctx, rows, H, w.wo, H);
+      p.epi.bias = w.bo; p.epi.residual = h->pre; p.epi.res_fp32 = 1; p.epi.out = h->pre; p.epi.out_fp32 = 1;
+      W2S_TRY(add_gemm(ls + "out_proj", p));
+    }
+    // ---- convolution module: LN -> pointwise (GLU epilogue) -> depthwise + BatchNorm + act -> pointwise ----
+    add_ln(ls + "conv_ln", h->pre, 1, rows, H, w.lnc_g, w.lnc_b, 1e-5f, ACT_NONE, h->hb, nullptr);
+    {
+      GemmProblem p = plain(h->hb, rows, H, w.pw1, 2 * H);
+      p.epi.glu = 1; p.epi.out = h->h1; p.epi.ldm = H;
+      W2S_TRY(add_gemm(ls + "pw1_glu", p));
+    }
+    {
+      const int kd = c.conv_depthwise_kernel_size;
+      const float *dw = w.dw_w, *sc = w.dw_scale, *sh = w.dw_shift;
+      add(ls + "depthwise", [=](cudaStream_t s) { return launch_depthwise(hh->h1, nn, T, H, kd, dw, sc, sh, act, hh->ctx, s); });
+    }
+    {
+      GemmProblem p = plain(h->ctx, rows, H, w.pw2, H);
+      p.epi.residual = h->pre; p.epi.res_fp32 = 1; p.epi.out = h->pre; p.epi.out_fp32 = 1;
+      W2S_TRY(add_gemm(ls + "pw2", p));
+    }
+    W2S_TRY(ffn(ls + "mac2_", w.lnf2_g, w.lnf2_b, w.f2w1, w.f2b1, w.f2w2, w.f2b2));
+    add_ln(ls + "final_ln", h->pre, 1, rows, H, w.lnfin_g, w.lnfin_b, 1e-5f, ACT_NONE, nullptr, h->pre);
+  }
+  add_ln("encoder_ln", h->pre, 1, rows, H, h->enc_ln_g, h->enc_ln_b, c.layer_norm_eps, ACT_NONE, h->hb, nullptr);
+  add("head", [=](cudaStream_t s) {
+    HeadParams hp{};
+    hp.h = hh->hb; hp.w = hh->head_w; hp.bias = hh->head_b;
+    hp.n = nn; hp.T = T; hp.H = H; hp.V = hh->cfg.vocab_size; hp.mode = hh->mode; hp.D = hh->D;
+    hp.frames = hh->frames; hp.tokens = hh->tokens; hp.out = hh->cur_out;
+    return launch_head(hp, s);
+  });
+  return "";
+}
 
 std::string get_plan(w2s_handle* h, int n, Plan** out) {
   auto it = h->plans.find(n);

@@ -63,6 +63,15 @@ std::string attention_tc_launch(const AttnTcPlan* plan, cudaStream_t s);
 void attention_tc_free(AttnTcPlan* plan);
 bool attention_tc_supported(const AttnParams& p);
 
+// ---- conformer-only CUDA-core kernels (conformer.cu) ---------------------------------------------------------
+std::string launch_bn_fold(const float* g, const float* b, const float* mean, const float* var, int n, float eps,
+                           float* scale, float* shift, cudaStream_t s);
+std::string launch_depthwise(const __nv_bfloat16* in, int B, int T, int H, int k, const float* w, const float* scale,
+                             const float* shift, int act, __nv_bfloat16* out, cudaStream_t s);
+std::string launch_rotary(const __nv_bfloat16* x, long long rows, int T, int H, int hd, int base, __nv_bfloat16* out,
+                          cudaStream_t s);
+std::string launch_relpos(int T, int H, __nv_bfloat16* out, cudaStream_t s);
+
 // ---- K9: lm_head + log-softmax + gather -----------------------------------------------------------------
 struct HeadParams {
   const __nv_bfloat16* h;     // [n*T, H]

@@ -21,7 +21,7 @@ pytestmark = pytest.mark.gpu
 LOGIT_TOL = 0.04
 PHI_TOL = 0.10
 
-IMPLEMENTED = ["tiny_group", "tiny_layer_stable"]
+IMPLEMENTED = ["tiny_group", "tiny_layer_stable", "tiny_conformer_rel", "tiny_conformer_rotary"]
 
 
 @pytest.fixture(scope="module")
