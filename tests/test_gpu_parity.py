@@ -18,7 +18,8 @@ from shap_transformer_asr_b200.config import MODELS
 
 pytestmark = pytest.mark.gpu
 
-LOGIT_TOL = 0.04
+LOGIT_TOL = 0.04        # 12-layer models and the tiny variants
+LOGIT_TOL_DEEP = 0.06   # 24-layer models (bf16 rounding accumulates with depth; measured 0.020 / 0.041 on C3 / C4)
 PHI_TOL = 0.10
 
 IMPLEMENTED = ["tiny_group", "tiny_layer_stable", "tiny_conformer_rel", "tiny_conformer_rotary"]
@@ -156,3 +157,58 @@ def test_full_size_properties_c2(P, base_engine):
     eng.set_targets("logprob", frames, tokens)
     lp = torch.log_softmax(lg, -1)[:, torch.from_numpy(frames).long(), torch.from_numpy(tokens).long()]
     assert (lp - y1[:2]).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("name,L", [("tiny_group", 100000), ("tiny_group", 160000), ("tiny_conformer_rel", 100000),
+                                    ("tiny_conformer_rotary", 160000), ("tiny_layer_stable", 47000)])
+def test_long_clips_cover_multi_block_attention(P, name, L):
+    """T' = 312 / 499 / 146: exercises the second S half (keys 256..511), ragged key blocks and two P V rounds."""
+    cfg = VARIANTS[name]
+    model = build_model(cfg)
+    x = np.random.default_rng(L).standard_normal((2, L)).astype(np.float32)
+    with torch.no_grad():
+        ref = W.ctc_logits(W.state_dict_of(model), cfg.to_dict(), torch.from_numpy(x)).numpy()
+    eng = P.Engine(model, cfg, max_batch=2)
+    eng.set_targets("logits")
+    out = eng.eval_waveforms(torch.from_numpy(x).cuda()).view(ref.shape).cpu().numpy()
+    err = rel_err(out, ref)
+    print(f"{name} L={L} T'={ref.shape[1]} logits rel err {err:.3e}")
+    assert err < LOGIT_TOL
+    eng.close()
+
+
+@pytest.mark.parametrize("workload", ["C3", "C4"])
+def test_full_size_large_models_match_reference(P, workload):
+    """BASELINE configs C3 (wav2vec2-large, 10 s, 200 segments) and C4 (conformer-large rel-pos, 5 s, 100 segments):
+    a few coalitions at FULL size against the transformers fp32 forward."""
+    from shap_transformer_asr_b200.config import WORKLOADS
+    wl = WORKLOADS[workload]
+    cfg = MODELS[wl.model]
+    model = build_model(cfg)
+    clip = P.synthetic_clip(wl.num_samples)
+    M = wl.num_segments
+    Z, kw, _ = P.sample_coalitions(M, wl.num_coalitions, seed=0)
+    rows = np.concatenate([np.ones((1, M), np.uint8), np.zeros((1, M), np.uint8), Z[[0, 1, 2 * M + 3]]])
+    bounds = CB.segment_bounds(wl.num_samples, M)
+    X = torch.from_numpy(CB.materialize(clip, rows, bounds))
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        ref = model(X).logits.numpy()
+    frames, tokens = P.char_targets(ref[0])
+    eng = P.Engine(model, cfg, max_batch=4)
+    eng.set_clip(clip, num_segments=M)
+    eng.set_targets("logits")
+    out = eng.eval_bits(eng.bits_to_device(rows)).view(ref.shape).cpu().numpy()
+    err = rel_err(out, ref)
+    same = (out[0].argmax(-1) == ref[0].argmax(-1)).mean()
+    print(f"{workload} full-size logits rel err {err:.3e}; argmax agreement on unmasked clip {same:.4f}; D={len(frames)}")
+    assert err < LOGIT_TOL_DEEP
+    # identical argmax transcript on the unmasked clip; only frames whose top-2 margin is inside the error band may differ
+    top2 = np.sort(ref[0], -1)
+    near_tie = (top2[:, -1] - top2[:, -2]) < 2 * np.abs(out[0] - ref[0]).max()
+    assert np.all((out[0].argmax(-1) == ref[0].argmax(-1)) | near_tie)
+    eng.set_targets("logprob", frames, tokens)
+    lp = eng.eval_bits(eng.bits_to_device(rows)).cpu().numpy()
+    ref_lp = torch.log_softmax(torch.from_numpy(ref), -1)[:, torch.from_numpy(frames).long(), torch.from_numpy(tokens).long()].numpy()
+    assert np.abs(lp - ref_lp).max() < LOGIT_TOL_DEEP * np.abs(ref).max()
+    eng.close()
