@@ -51,9 +51,11 @@ struct Plan {
   std::vector<Step> steps;
   std::vector<GemmLaunch*> gemms;
   std::vector<AttnTcPlan*> attn;
+  std::vector<AttnRelPlan*> attn_rel;
   ~Plan() {
     for (auto* g : gemms) delete g;
     for (auto* a : attn) attention_tc_free(a);
+    for (auto* a : attn_rel) attention_rel_free(a);
   }
 };
 
@@ -105,8 +107,8 @@ struct w2s_handle {
   long long xm_ld = 0;
   float *gn_a = nullptr, *gn_b = nullptr;
   bf16 *bufA = nullptr, *bufB = nullptr;
-  bf16 *fpn = nullptr, *h0 = nullptr, *hp = nullptr, *hb = nullptr, *h1 = nullptr, *qkv = nullptr, *vt = nullptr,
-       *ctx = nullptr, *ffn = nullptr;
+  bf16 *fpn = nullptr, *h0 = nullptr, *hp = nullptr, *hb = nullptr, *h1 = nullptr, *qkv = nullptr, *ctx = nullptr,
+       *ffn = nullptr;
   float* pre = nullptr;
   bf16* hrot = nullptr;
   double* wls_work = nullptr;
@@ -275,22 +277,34 @@ std::string load_weights(w2s_handle* h, const WeightTable& wt) {
       W2S_TRY(lin("ffn1.output_dense", H, I, &w.w2, &w.b2));
       W2S_TRY(copy_f32(h, wt, lp + "self_attn_layer_norm.weight", H, &w.ln1_g));
       W2S_TRY(copy_f32(h, wt, lp + "self_attn_layer_norm.bias", H, &w.ln1_b));
-      W2S_TRY(dalloc(h->allocs, &w.wqkv, (size_t)3 * H * H));
-      W2S_TRY(copy_bf16(h, wt, lp + "self_attn.linear_q.weight", (int64_t)H * H, w.wqkv));
-      W2S_TRY(copy_bf16(h, wt, lp + "self_attn.linear_k.weight", (int64_t)H * H, w.wqkv + (size_t)H * H));
-      W2S_TRY(copy_bf16(h, wt, lp + "self_attn.linear_v.weight", (int64_t)H * H, w.wqkv + (size_t)2 * H * H));
-      W2S_TRY(dalloc(h->allocs, &w.bqkv, (size_t)3 * H));
-      const char* nm[3] = {"self_attn.linear_q.bias", "self_attn.linear_k.bias", "self_attn.linear_v.bias"};
-      for (int j = 0; j < 3; ++j) {
-        const float* b = nullptr;
-        W2S_TRY(wt.get(lp + nm[j], H, &b));
-        W2S_CUDA_OK(cudaMemcpy(w.bqkv + (size_t)j * H, b, sizeof(float) * H, cudaMemcpyDeviceToDevice));
+      // relative positions: the query projection is emitted twice, (q + u | q + v | k | v), with pos_bias_u / pos_bias_v
+      // folded into the fp32 bias of the respective copy (HF :524-527 adds them to q before the two score matmuls)
+      const bool relp = c.position_embeddings_type == 1;
+      const int nq = relp ? 2 : 1;
+      W2S_TRY(dalloc(h->allocs, &w.wqkv, (size_t)(nq + 2) * H * H));
+      W2S_TRY(dalloc(h->allocs, &w.bqkv, (size_t)(nq + 2) * H));
+      for (int j = 0; j < nq; ++j)
+        W2S_TRY(copy_bf16(h, wt, lp + "self_attn.linear_q.weight", (int64_t)H * H, w.wqkv + (size_t)j * H * H));
+      W2S_TRY(copy_bf16(h, wt, lp + "self_attn.linear_k.weight", (int64_t)H * H, w.wqkv + (size_t)nq * H * H));
+      W2S_TRY(copy_bf16(h, wt, lp + "self_attn.linear_v.weight", (int64_t)H * H, w.wqkv + (size_t)(nq + 1) * H * H));
+      {
+        const float *bq = nullptr, *bk = nullptr, *bv = nullptr;
+        W2S_TRY(wt.get(lp + "self_attn.linear_q.bias", H, &bq));
+        W2S_TRY(wt.get(lp + "self_attn.linear_k.bias", H, &bk));
+        W2S_TRY(wt.get(lp + "self_attn.linear_v.bias", H, &bv));
+        for (int j = 0; j < nq; ++j)
+          W2S_CUDA_OK(cudaMemcpy(w.bqkv + (size_t)j * H, bq, sizeof(float) * H, cudaMemcpyDeviceToDevice));
+        W2S_CUDA_OK(cudaMemcpy(w.bqkv + (size_t)nq * H, bk, sizeof(float) * H, cudaMemcpyDeviceToDevice));
+        W2S_CUDA_OK(cudaMemcpy(w.bqkv + (size_t)(nq + 1) * H, bv, sizeof(float) * H, cudaMemcpyDeviceToDevice));
       }
       W2S_TRY(lin("self_attn.linear_out", H, H, &w.wo, &w.bo));
-      if (c.position_embeddings_type == 1) {
+      if (relp) {
         W2S_TRY(lin("self_attn.linear_pos", H, H, &w.wpos, nullptr));
-        W2S_TRY(copy_f32(h, wt, lp + "self_attn.pos_bias_u", H, &w.bias_u));
-        W2S_TRY(copy_f32(h, wt, lp + "self_attn.pos_bias_v", H, &w.bias_v));
+        const float *u = nullptr, *v = nullptr;
+        W2S_TRY(wt.get(lp + "self_attn.pos_bias_u", H, &u));
+        W2S_TRY(wt.get(lp + "self_attn.pos_bias_v", H, &v));
+        W2S_TRY(launch_axpy(u, w.bqkv, H, 0));
+        W2S_TRY(launch_axpy(v, w.bqkv + H, H, 0));
       }
       W2S_TRY(copy_f32(h, wt, lp + "conv_module.layer_norm.weight", H, &w.lnc_g));
       W2S_TRY(copy_f32(h, wt, lp + "conv_module.layer_norm.bias", H, &w.lnc_b));
@@ -385,7 +399,7 @@ std::string ensure_workspace(w2s_handle* h, long long L) {
   W2S_TRY(dalloc(pool, &h->hb, rows * H));
   W2S_TRY(dalloc(pool, &h->h1, rows * H));
   W2S_TRY(dalloc(pool, &h->pre, rows * H));
-  W2S_TRY(dalloc(pool, &h->qkv, rows * 3 * H));
+  W2S_TRY(dalloc(pool, &h->qkv, rows * 4 * H));
   W2S_TRY(dalloc(pool, &h->ctx, rows * H));
   W2S_TRY(dalloc(pool, &h->ffn, rows * I));
   if (c.kind == 0) {
@@ -538,8 +552,9 @@ struct PlanBuilder {
     }
     // ---- K5-K8: transformer layers ------------------------------------------------------------------------
     AttnParams ap{};
-    ap.qkv = h->qkv; ap.vt = h->vt; ap.ctx = h->ctx; ap.B = n; ap.T = T; ap.Tp = h->Tp; ap.H = H;
+    ap.qkv = h->qkv; ap.ctx = h->ctx; ap.B = n; ap.T = T; ap.Tp = h->Tp; ap.H = H;
     ap.heads = c.num_attention_heads; ap.hd = H / c.num_attention_heads;
+    ap.ld = 3 * H; ap.q_off = 0; ap.qv_off = 0; ap.k_off = H; ap.v_off = 2 * H;
     ap.scale = 1.0f / sqrtf((float)ap.hd);
     const bool tc_attn = !simt_attn && attention_tc_supported(ap);
     AttnTcPlan* apl = nullptr;
@@ -611,10 +626,12 @@ std::string PlanBuilder::build_conformer() {
   w2s_handle* hh = h;
   const int nn = n;
   AttnParams ap{};
+  const bool rel = c.position_embeddings_type == 1, rotary = c.position_embeddings_type == 2;
   ap.qkv = h->qkv; ap.ctx = h->ctx; ap.B = n; ap.T = T; ap.Tp = h->Tp; ap.H = H;
   ap.heads = c.num_attention_heads; ap.hd = H / c.num_attention_heads;
   ap.scale = 1.0f / sqrtf((float)ap.hd);
-  const bool rel = c.position_embeddings_type == 1, rotary = c.position_embeddings_type == 2;
+  const int nq = rel ? 2 : 1;
+  ap.ld = (nq + 2) * H; ap.q_off = 0; ap.qv_off = rel ? H : 0; ap.k_off = nq * H; ap.v_off = (nq + 1) * H;
   AttnTcPlan* apl = nullptr;
   const bool tc_attn = !rel && !simt_attn && attention_tc_supported(ap);
   if (tc_attn) {
@@ -649,7 +666,7 @@ std::string PlanBuilder::build_conformer() {
       v.epi.bias = w.bqkv + 2 * H; v.epi.out = h->qkv + 2 * H; v.epi.ldm = 3 * H;
       W2S_TRY(add_gemm(ls + "v", v));
     } else {
-      GemmProblem p = plain(h->hb, rows, H, w.wqkv, 3 * H);
+      GemmProblem p = plain(h->hb, rows, H, w.wqkv, (nq + 2) * H);
       p.epi.bias = w.bqkv; p.epi.out = h->qkv;
       W2S_TRY(add_gemm(ls + "qkv", p));
     }
@@ -657,10 +674,15 @@ std::string PlanBuilder::build_conformer() {
       add(ls + "attention", [=](cudaStream_t s) { return attention_tc_launch(apl, s); });
     } else {
       AttnParams lp = ap;
-      if (rel) {
-        lp.pos_proj = w.pos_proj; lp.bias_u = w.bias_u; lp.bias_v = w.bias_v;
+      if (rel) lp.pos_proj = w.pos_proj;
+      if (rel && !simt_attn && attention_rel_supported(lp)) {
+        AttnRelPlan* rp = nullptr;
+        W2S_TRY(attention_rel_prepare(lp, &rp));
+        plan->attn_rel.push_back(rp);
+        add(ls + "attention", [=](cudaStream_t s) { return attention_rel_launch(rp, s); });
+      } else {
+        add(ls + "attention", [=](cudaStream_t s) { return launch_attention_simt(lp, s); });
       }
-      add(ls + "attention", [=](cudaStream_t s) { return launch_attention_simt(lp, s); });
     }
     {
       GemmProblem p = plain(h->ctx, rows, H, w.wo, H);
@@ -825,6 +847,7 @@ int w2s_create(const w2s_config* cfg, const char* const* names, const float* con
   }
   std::string e = gemm_init();
   if (e.empty()) e = attention_tc_init();
+  if (e.empty()) e = attention_rel_init();
   if (e.empty()) {
     WeightTable wt;
     wt.prefix = cfg->kind == 1 ? "wav2vec2_conformer." : "wav2vec2.";

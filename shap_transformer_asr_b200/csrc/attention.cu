@@ -27,12 +27,11 @@ __global__ void __launch_bounds__(128) attention_simt_kernel(const AttnParams p)
   const int i = (int)(gw % p.T);
   const int h = (int)((gw / p.T) % p.heads);
   const int b = (int)(gw / ((long long)p.T * p.heads));
-  const int H3 = 3 * p.H;
+  const int H3 = p.ld;
   const __nv_bfloat16* qrow = p.qkv + ((long long)b * p.T + i) * H3 + h * p.hd;
   for (int d = lane; d < p.hd; d += 32) {
-    const float q = __bfloat162float(qrow[d]);
-    qs[warp][0][d] = q + (p.bias_u ? p.bias_u[h * p.hd + d] : 0.f);
-    qs[warp][1][d] = q + (p.bias_v ? p.bias_v[h * p.hd + d] : 0.f);
+    qs[warp][0][d] = __bfloat162float(qrow[p.q_off + d]);
+    qs[warp][1][d] = p.pos_proj ? __bfloat162float(qrow[p.qv_off + d]) : 0.f;
   }
   __syncwarp();
   float s[SIMT_MAXC];
@@ -42,7 +41,7 @@ __global__ void __launch_bounds__(128) attention_simt_kernel(const AttnParams p)
     const int j = c * 32 + lane;
     float acc = -INFINITY;
     if (j < p.T) {
-      const __nv_bfloat16* krow = p.qkv + ((long long)b * p.T + j) * H3 + p.H + h * p.hd;
+      const __nv_bfloat16* krow = p.qkv + ((long long)b * p.T + j) * H3 + p.k_off + h * p.hd;
       acc = 0.f;
       for (int d = 0; d < p.hd; d += 2) {
         const uint32_t kk = *reinterpret_cast<const uint32_t*>(krow + d);
@@ -81,7 +80,7 @@ __global__ void __launch_bounds__(128) attention_simt_kernel(const AttnParams p)
       const int j = c * 32 + l;
       const float pj = __shfl_sync(0xffffffffu, s[c], l);
       if (j < p.T) {
-        const __nv_bfloat16* vrow = p.qkv + ((long long)b * p.T + j) * H3 + 2 * p.H + h * p.hd;
+        const __nv_bfloat16* vrow = p.qkv + ((long long)b * p.T + j) * H3 + p.v_off + h * p.hd;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           const int d = lane + 32 * r;
@@ -351,7 +350,7 @@ std::string attention_tc_prepare(const AttnParams& p, AttnTcPlan** out) {
   pl->grid = dim3((p.T + 127) / 128, p.heads, p.B);
   pl->smem = att_smem(Tp);
   pl->tmem_cols = Tp <= 64 ? 64 : (Tp <= 128 ? 128 : (Tp <= 256 ? 256 : 512));
-  const uint64_t H3 = 3ull * p.H;
+  const uint64_t H3 = (uint64_t)p.ld;
   std::string err;
   {
     uint64_t dims[4] = {64, (uint64_t)p.T, (uint64_t)p.heads, (uint64_t)p.B};
@@ -359,9 +358,9 @@ std::string attention_tc_prepare(const AttnParams& p, AttnTcPlan** out) {
     uint32_t boxq[4] = {64, 128, 1, 1};
     uint32_t boxk[4] = {64, 256, 1, 1};
     uint32_t boxv[4] = {64, 64, 1, 1};
-    err = make_tensor_map_bf16(&pl->mapQ, p.qkv, 4, dims, str, boxq);
-    if (err.empty()) err = make_tensor_map_bf16(&pl->mapK, p.qkv + p.H, 4, dims, str, boxk);
-    if (err.empty()) err = make_tensor_map_bf16(&pl->mapV, p.qkv + 2 * p.H, 4, dims, str, boxv);
+    err = make_tensor_map_bf16(&pl->mapQ, p.qkv + p.q_off, 4, dims, str, boxq);
+    if (err.empty()) err = make_tensor_map_bf16(&pl->mapK, p.qkv + p.k_off, 4, dims, str, boxk);
+    if (err.empty()) err = make_tensor_map_bf16(&pl->mapV, p.qkv + p.v_off, 4, dims, str, boxv);
   }
   if (!err.empty()) {
     delete pl;
@@ -383,5 +382,254 @@ std::string attention_tc_launch(const AttnTcPlan* pl, cudaStream_t s) {
 }
 
 void attention_tc_free(AttnTcPlan* plan) { delete plan; }
+
+// =================================================================================================
+// conformer relative-position attention on tcgen05 (HF wav2vec2_conformer/modeling_wav2vec2_conformer.py:509-565)
+//   scores[i, j] = ((q_i + u) . k_j + (q_i + v) . pp[T-1-i+j]) / sqrt(d)
+// One CTA per (128-query tile, head, coalition), keys in halves of 128.  Per half two MMA chains fill TMEM:
+//   AC  [128 x 128] = (Q+u) K^T                               columns   0..127
+//   BD  [128 x 256] = (Q+v) PP_window^T, window row w <-> r = r_lo + w  columns 128..383
+// and the "shift trick" of the reference is an index shift per query row: bd[i, j] = BD[i, 127 - i_local + (j - j0)].
+// Each warp reads its 64 raw BD columns per 32-key chunk, stages them in its private shared-memory strip and reads
+// them back with the lane-dependent offset.  Each half keeps its own softmax maximum and its own O accumulator
+// (columns 384..447 / 448..511); the halves are merged in the epilogue, so nothing in TMEM is ever rescaled.
+// =================================================================================================
+struct AttnRelDev {
+  __nv_bfloat16* ctx;
+  int B, T, H, heads, nh;
+  float scale_log2e;
+};
+struct AttnRelPlan {
+  CUtensorMap mapQU, mapQV, mapK, mapV, mapP;
+  AttnRelDev dev;
+  dim3 grid;
+};
+constexpr int REL_QU = 0, REL_QV = 16384, REL_K = 32768, REL_V = 49152, REL_PP = 65536, REL_P = 98304,
+              REL_STG = 131072, REL_STG_STRIDE = 67;
+constexpr size_t REL_SMEM = REL_STG + 8 * 32 * REL_STG_STRIDE * 4 + 1024;
+
+__global__ void __launch_bounds__(256, 1)
+attention_rel_kernel(const __grid_constant__ CUtensorMap mapQU, const __grid_constant__ CUtensorMap mapQV,
+                     const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV,
+                     const __grid_constant__ CUtensorMap mapP, const AttnRelDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ float s_red[2][128];
+  __shared__ float s_sum[2][2][128];
+  __shared__ uint64_t s_bar[4];
+  __shared__ uint32_t s_tmem;
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw_addr);
+  const uint32_t bar_q = smem_u32(&s_bar[0]), bar_load = smem_u32(&s_bar[1]), bar_mma = smem_u32(&s_bar[2]),
+                 bar_pv = smem_u32(&s_bar[3]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qd = warp & 3, hf = warp >> 2;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int row = qd * 32 + lane;
+  float* stg = reinterpret_cast<float*>(base_ptr + REL_STG) + warp * 32 * REL_STG_STRIDE + lane * REL_STG_STRIDE;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapQU);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    tma_prefetch_desc(&mapP);
+    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&s_bar[i]), 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 0) {
+    tmem_alloc<512>(smem_u32(&s_tmem));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&s_tmem);
+  const uint32_t trow = tmem + (static_cast<uint32_t>(qd * 32) << 16);
+
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar_q, 32768);
+    tma_load_4d(base + REL_QU, &mapQU, bar_q, 0, qt * 128, h, b);
+    tma_load_4d(base + REL_QV, &mapQV, bar_q, 0, qt * 128, h, b);
+  }
+
+  float m_h[2] = {-INFINITY, -INFINITY};
+  float l_h[2] = {0.f, 0.f};
+  for (int hk = 0; hk < p.nh; ++hk) {
+    const int j0 = hk * 128;
+    if (threadIdx.x == 0) {
+      if (hk > 0) mbar_wait(bar_pv, (hk - 1) & 1);  // previous P V has finished reading V and P
+      mbar_expect_tx(bar_load, 16384 + 16384 + 32768);
+      tma_load_4d(base + REL_K, &mapK, bar_load, 0, j0, h, b);
+      tma_load_4d(base + REL_V, &mapV, bar_load, 0, j0, h, b);
+      tma_load_4d(base + REL_V + 8192, &mapV, bar_load, 0, j0 + 64, h, b);
+      tma_load_3d(base + REL_PP, &mapP, bar_load, 0, p.T - 1 - (qt * 128 + 127) + j0, h);
+      if (hk == 0) mbar_wait(bar_q, 0);
+      mbar_wait(bar_load, hk & 1);
+      tc_fence_after();
+      const uint64_t dqu = umma_desc_sw128(base + REL_QU), dqv = umma_desc_sw128(base + REL_QV);
+      const uint64_t dk = umma_desc_sw128(base + REL_K), dp = umma_desc_sw128(base + REL_PP);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem, dqu + 2u * k, dk + 2u * k, umma_idesc_bf16(128, 128), k != 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem + 128, dqv + 2u * k, dp + 2u * k, umma_idesc_bf16(128, 256), k != 0);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, hk & 1);
+    tc_fence_after();
+
+    // ---- scores of this thread's 64 keys (two chunks of 32) --------------------------------------------------------
+    float sc[64];
+    float mx = -INFINITY;
+    const int base_q = 96 - 32 * qd;
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      const int c_local = hf * 64 + ch * 32;
+      float ac[32], r0[32], r1[32];
+      tmem_ld_32x32(trow + c_local, ac);
+      tmem_ld_32x32(trow + 128 + base_q + c_local, r0);
+      tmem_ld_32x32(trow + 128 + base_q + c_local + 32, r1);
+#pragma unroll
+      for (int k2 = 0; k2 < 32; ++k2) {
+        stg[k2] = r0[k2];
+        stg[32 + k2] = r1[k2];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        const float v = ac[t] + stg[31 - lane + t];
+        const bool ok = (j0 + c_local + t) < p.T;
+        sc[ch * 32 + t] = ok ? v : -INFINITY;
+        mx = fmaxf(mx, sc[ch * 32 + t]);
+      }
+      __syncwarp();
+    }
+    s_red[hf][row] = mx;
+    __syncthreads();
+    mx = fmaxf(s_red[0][row], s_red[1][row]);
+    m_h[hk] = mx;
+    const float mscaled = (mx == -INFINITY) ? 0.f : mx * p.scale_log2e;
+    float sum = 0.f;
+    const uint32_t sp_row = base + REL_P + hf * 16384 + row * 128;
+#pragma unroll
+    for (int c8 = 0; c8 < 8; ++c8) {
+      float e[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float s = sc[c8 * 8 + t];
+        e[t] = (s == -INFINITY) ? 0.f : ex2_approx(fmaf(s, p.scale_log2e, -mscaled));
+        sum += e[t];
+      }
+      const uint32_t addr = sp_row + (((uint32_t)c8 ^ ((uint32_t)row & 7u)) << 4);
+      const uint32_t u0 = pack_bf16x2(e[0], e[1]), u1 = pack_bf16x2(e[2], e[3]);
+      const uint32_t u2 = pack_bf16x2(e[4], e[5]), u3 = pack_bf16x2(e[6], e[7]);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u0), "r"(u1), "r"(u2), "r"(u3) : "memory");
+    }
+    l_h[hk] = sum;
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();   // also orders the s_red reads above before the next half overwrites it
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      constexpr uint32_t idesc = umma_idesc_bf16_bmn(128, 64);
+      for (int kb = 0; kb < 2; ++kb) {
+        const uint64_t dpp = umma_desc_sw128(base + REL_P + kb * 16384);
+        const uint64_t dv = umma_desc_sw128_mn(base + REL_V + kb * 8192);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem + 384 + 64 * hk, dpp + 2u * k, dv + 128u * k, idesc, (kb | k) != 0);
+      }
+      umma_commit(bar_pv);
+    }
+  }
+  // ---- merge the halves: out = (a0 O0 + a1 O1) / (a0 l0 + a1 l1), a_h = exp((m_h - m) scale) ------------------------------
+  s_sum[0][hf][row] = l_h[0];
+  s_sum[1][hf][row] = l_h[1];
+  mbar_wait(bar_pv, (p.nh - 1) & 1);
+  tc_fence_after();
+  __syncthreads();
+  const float l0 = s_sum[0][0][row] + s_sum[0][1][row];
+  const float l1 = s_sum[1][0][row] + s_sum[1][1][row];
+  const float m = fmaxf(m_h[0], m_h[1]);
+  const float a0 = ex2_approx((m_h[0] - m) * p.scale_log2e);
+  const float a1 = (p.nh > 1 && m_h[1] != -INFINITY) ? ex2_approx((m_h[1] - m) * p.scale_log2e) : 0.f;
+  const float inv = 1.0f / (a0 * l0 + a1 * l1);
+  const int i = qt * 128 + row;
+  __nv_bfloat16* orow = p.ctx + ((long long)b * p.T + i) * p.H + h * 64 + hf * 32;
+  {
+    float o0[32], o1[32];
+    tmem_ld_32x32(trow + 384 + hf * 32, o0);
+    if (p.nh > 1) {
+      tmem_ld_32x32(trow + 448 + hf * 32, o1);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) o1[j] = 0.f;
+    }
+    if (i < p.T) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        float y[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) y[t] = (a0 * o0[j + t] + a1 * o1[j + t]) * inv;
+        uint4 u;
+        u.x = pack_bf16x2(y[0], y[1]);
+        u.y = pack_bf16x2(y[2], y[3]);
+        u.z = pack_bf16x2(y[4], y[5]);
+        u.w = pack_bf16x2(y[6], y[7]);
+        *reinterpret_cast<uint4*>(orow + j) = u;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+bool attention_rel_supported(const AttnParams& p) {
+  return p.pos_proj != nullptr && p.hd == 64 && p.T <= 256 && (p.H % 8 == 0);
+}
+std::string attention_rel_init() {
+  cudaError_t e = cudaFuncSetAttribute(attention_rel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REL_SMEM);
+  if (e != cudaSuccess) return std::string("cudaFuncSetAttribute(attention_rel_kernel): ") + cudaGetErrorString(e);
+  return "";
+}
+std::string attention_rel_prepare(const AttnParams& p, AttnRelPlan** out) {
+  if (!attention_rel_supported(p)) return "attention (tcgen05, relative): unsupported shape";
+  AttnRelPlan* pl = new AttnRelPlan();
+  pl->dev.ctx = p.ctx;
+  pl->dev.B = p.B; pl->dev.T = p.T; pl->dev.H = p.H; pl->dev.heads = p.heads;
+  pl->dev.nh = (p.T + 127) / 128;
+  pl->dev.scale_log2e = p.scale * 1.4426950408889634f;
+  pl->grid = dim3((p.T + 127) / 128, p.heads, p.B);
+  const uint64_t ld = (uint64_t)p.ld;
+  uint64_t dims[4] = {64, (uint64_t)p.T, (uint64_t)p.heads, (uint64_t)p.B};
+  uint64_t str[3] = {ld * 2, 128, (uint64_t)p.T * ld * 2};
+  uint32_t box128[4] = {64, 128, 1, 1};
+  uint32_t box64[4] = {64, 64, 1, 1};
+  std::string err = make_tensor_map_bf16(&pl->mapQU, p.qkv + p.q_off, 4, dims, str, box128);
+  if (err.empty()) err = make_tensor_map_bf16(&pl->mapQV, p.qkv + p.qv_off, 4, dims, str, box128);
+  if (err.empty()) err = make_tensor_map_bf16(&pl->mapK, p.qkv + p.k_off, 4, dims, str, box128);
+  if (err.empty()) err = make_tensor_map_bf16(&pl->mapV, p.qkv + p.v_off, 4, dims, str, box64);
+  if (err.empty()) {
+    uint64_t pd[3] = {64, (uint64_t)(2 * p.T - 1), (uint64_t)p.heads};
+    uint64_t ps[2] = {(uint64_t)p.H * 2, 128};
+    uint32_t pb[3] = {64, 256, 1};
+    err = make_tensor_map_bf16(&pl->mapP, p.pos_proj, 3, pd, ps, pb);
+  }
+  if (!err.empty()) {
+    delete pl;
+    return err;
+  }
+  *out = pl;
+  return "";
+}
+std::string attention_rel_launch(const AttnRelPlan* pl, cudaStream_t s) {
+  attention_rel_kernel<<<pl->grid, 256, REL_SMEM, s>>>(pl->mapQU, pl->mapQV, pl->mapK, pl->mapV, pl->mapP, pl->dev);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+void attention_rel_free(AttnRelPlan* plan) { delete plan; }
 
 }  // namespace w2s

@@ -454,6 +454,16 @@ std::string launch_pos_pad(const __nv_bfloat16* h, int B, int T, int H, int G, i
 // =================================================================================================
 // one-off weight re-layout
 // =================================================================================================
+__global__ void axpy_kernel(const float* x, float* y, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] += x[i];
+}
+std::string launch_axpy(const float* x, float* y, int n, cudaStream_t s) {
+  axpy_kernel<<<(n + 255) / 256, 256, 0, s>>>(x, y, n);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
 __global__ void cast_bf16_kernel(const float* src, __nv_bfloat16* dst, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = __float2bfloat16_rn(src[i]);

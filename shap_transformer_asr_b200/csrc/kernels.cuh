@@ -45,15 +45,13 @@ std::string launch_pos_pad(const __nv_bfloat16* h, int B, int T, int H, int G, i
 
 // ---- attention -------------------------------------------------------------------------------------
 struct AttnParams {
-  const __nv_bfloat16* qkv;   // [B*T, 3H]  (q | k | v)
-  const __nv_bfloat16* vt;    // [B, heads, hd, Tp]  V^T (tcgen05 path)
+  const __nv_bfloat16* qkv;   // [B*T, ld]: plain models (q | k | v), ld = 3H; conformer relative (q+u | q+v | k | v), ld = 4H
   __nv_bfloat16* ctx;         // [B*T, H]
   int B, T, Tp, H, heads, hd;
+  int ld, q_off, qv_off, k_off, v_off;  // column offsets inside a qkv row (qv_off used with pos_proj only)
   float scale;
-  // conformer relative positions (null when unused)
+  // conformer relative positions (null when unused): the biases u / v are already folded into the q+u / q+v columns
   const __nv_bfloat16* pos_proj;  // [2T-1, H] linear_pos(rel_pos_emb), row r <-> relative position T-1-r
-  const float* bias_u;            // [H]
-  const float* bias_v;            // [H]
 };
 std::string launch_attention_simt(const AttnParams& p, cudaStream_t s);
 struct AttnTcPlan;  // opaque: tensor maps + launch geometry
@@ -62,6 +60,13 @@ std::string attention_tc_prepare(const AttnParams& p, AttnTcPlan** plan);
 std::string attention_tc_launch(const AttnTcPlan* plan, cudaStream_t s);
 void attention_tc_free(AttnTcPlan* plan);
 bool attention_tc_supported(const AttnParams& p);
+// conformer relative-position attention on tcgen05 (T' <= 256)
+struct AttnRelPlan;
+std::string attention_rel_init();
+bool attention_rel_supported(const AttnParams& p);
+std::string attention_rel_prepare(const AttnParams& p, AttnRelPlan** plan);
+std::string attention_rel_launch(const AttnRelPlan* plan, cudaStream_t s);
+void attention_rel_free(AttnRelPlan* plan);
 
 // ---- conformer-only CUDA-core kernels (conformer.cu) ---------------------------------------------------------
 std::string launch_bn_fold(const float* g, const float* b, const float* mean, const float* var, int n, float eps,
@@ -90,6 +95,8 @@ std::string launch_wls(const uint32_t* zbits, int zwords, const double* w, const
                        double* work /* (M-1)*(M-1) + (M-1)*D doubles */, cudaStream_t s);
 
 // ---- weight re-layout (run once at create) -------------------------------------------------------------------
+// y[i] += x[i]
+std::string launch_axpy(const float* x, float* y, int n, cudaStream_t s);
 std::string launch_cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t s);
 // conv weight [O][C][kw] fp32 -> [O][j*C + c] bf16
 std::string launch_repack_conv(const float* src, __nv_bfloat16* dst, int O, int C, int kw, cudaStream_t s);
