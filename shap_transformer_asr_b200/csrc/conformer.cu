@@ -24,46 +24,83 @@ std::string launch_bn_fold(const float* g, const float* b, const float* mean, co
 }
 
 // out[b, t, c] = act((sum_j w[c, j] in[b, t + j - pad, c]) * scale[c] + shift[c]), zero padding in time.
-// CTA = (64-frame tile, 64-channel block, row); the (64 + k - 1) x 64 input window is staged in shared memory.
-template <int KMAX>
-__global__ void __launch_bounds__(256) depthwise_kernel(const __nv_bfloat16* __restrict__ in, int T, int H, int k,
+// One warp = 16 consecutive frames x 64 channels (lane = channel pair on the packed fp32 pipe).  Output-stationary:
+// each input row is loaded once (128 B per warp, coalesced) and scattered into the <= 16 accumulators it touches;
+// all tap indices are compile-time after unrolling, so filters and accumulators stay in registers.
+template <int K>
+__global__ void __launch_bounds__(256) depthwise_kernel(const __nv_bfloat16* __restrict__ in, int T, int H,
                                                          const float* __restrict__ w, const float* __restrict__ scale,
                                                          const float* __restrict__ shift, int act,
                                                          __nv_bfloat16* __restrict__ out) {
-  __shared__ float xs[64 + KMAX][64 + 1];
-  const int t0 = blockIdx.x * 64, c0 = blockIdx.y * 64, b = blockIdx.z;
-  const int pad = (k - 1) / 2;
-  const int nrow = 64 + k - 1;
-  for (int i = threadIdx.x; i < nrow * 64; i += blockDim.x) {
-    const int r = i >> 6, c = i & 63;
-    const int t = t0 + r - pad;
-    float v = 0.f;
-    if (t >= 0 && t < T && c0 + c < H) v = __bfloat162float(in[((long long)b * T + t) * H + c0 + c]);
-    xs[r][c] = v;
+  constexpr int TT = 16, PAD = (K - 1) / 2, ROWS = 8 * TT + K - 1;
+  __shared__ uint4 xs[ROWS * 8];   // [ROWS][64 channels] bf16, staged by the whole CTA with 16-byte loads
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z;
+  const int c_blk = blockIdx.y * 64;
+  {
+    const int tb = blockIdx.x * 8 * TT - PAD;
+    const bool vec_ok = (H % 8 == 0) && (c_blk + 64 <= H);
+    for (int i = threadIdx.x; i < ROWS * 8; i += blockDim.x) {
+      const int r = i >> 3, q = i & 7;
+      const int ti = tb + r;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (ti >= 0 && ti < T) {
+        const __nv_bfloat16* src = in + ((long long)b * T + ti) * H + c_blk + q * 8;
+        if (vec_ok) {
+          v = *reinterpret_cast<const uint4*>(src);
+        } else {
+          __nv_bfloat16 tmp[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) tmp[e] = (c_blk + q * 8 + e < H) ? src[e] : __float2bfloat16_rn(0.f);
+          v = *reinterpret_cast<uint4*>(tmp);
+        }
+      }
+      xs[i] = v;
+    }
   }
   __syncthreads();
-  const int c = threadIdx.x & 63;
-  if (c0 + c >= H) return;
-  float wr[KMAX];
+  const int t0 = (blockIdx.x * 8 + warp) * TT;
+  const int c = c_blk + lane * 2;
+  if (t0 >= T || c >= H) return;
+  const uint32_t* xw = reinterpret_cast<const uint32_t*>(xs) + warp * TT * 32 + lane;
+  float2 wr[K];
 #pragma unroll
-  for (int j = 0; j < KMAX; ++j) wr[j] = j < k ? __ldg(w + (long long)(c0 + c) * k + j) : 0.f;
-  const float sc = scale[c0 + c], sh = shift[c0 + c];
-  for (int r = threadIdx.x >> 6; r < 64; r += 4) {
-    const int t = t0 + r;
-    if (t >= T) break;
-    float acc = 0.f;
+  for (int j = 0; j < K; ++j) wr[j] = make_float2(__ldg(w + (long long)c * K + j), __ldg(w + (long long)(c + 1) * K + j));
+  float2 acc[TT];
 #pragma unroll
-    for (int j = 0; j < KMAX; ++j)
-      if (j < k) acc = fmaf(wr[j], xs[r + j][c], acc);
-    out[((long long)b * T + t) * H + c0 + c] = __float2bfloat16_rn(apply_act(fmaf(acc, sc, sh), act));
+  for (int t = 0; t < TT; ++t) acc[t] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int r = 0; r < TT + K - 1; ++r) {
+    const uint32_t u = xw[r * 32];   // zero outside [0, T): staged that way
+    const float2 x = make_float2(bf16_lo(u), bf16_hi(u));
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+      const int j = r - t;  // tap index, static after unrolling
+      if (j >= 0 && j < K) acc[t] = __ffma2_rn(wr[j], x, acc[t]);
+    }
+  }
+  const float2 sc = make_float2(scale[c], scale[c + 1]), sh = make_float2(shift[c], shift[c + 1]);
+#pragma unroll
+  for (int t = 0; t < TT; ++t) {
+    if (t0 + t < T) {
+      const float2 y = __ffma2_rn(acc[t], sc, sh);
+      *reinterpret_cast<uint32_t*>(out + ((long long)b * T + t0 + t) * H + c) =
+          pack_bf16x2(apply_act(y.x, act), apply_act(y.y, act));
+    }
   }
 }
 std::string launch_depthwise(const __nv_bfloat16* in, int B, int T, int H, int k, const float* w, const float* scale,
                              const float* shift, int act, __nv_bfloat16* out, cudaStream_t s) {
-  if (k > 32 || (k & 1) == 0) return "depthwise conv: kernel size must be odd and <= 31";
+  if (H % 2) return "depthwise conv: channel count must be even";
   if (B == 0) return "";
-  dim3 grid((T + 63) / 64, (H + 63) / 64, B);
-  depthwise_kernel<32><<<grid, 256, 0, s>>>(in, T, H, k, w, scale, shift, act, out);
+  dim3 grid((T + 127) / 128, (H + 63) / 64, B);
+  switch (k) {
+    case 31: depthwise_kernel<31><<<grid, 256, 0, s>>>(in, T, H, w, scale, shift, act, out); break;
+    case 15: depthwise_kernel<15><<<grid, 256, 0, s>>>(in, T, H, w, scale, shift, act, out); break;
+    case 7: depthwise_kernel<7><<<grid, 256, 0, s>>>(in, T, H, w, scale, shift, act, out); break;
+    case 3: depthwise_kernel<3><<<grid, 256, 0, s>>>(in, T, H, w, scale, shift, act, out); break;
+    default: return "depthwise conv: kernel size " + std::to_string(k) + " not instantiated (31, 15, 7, 3)";
+  }
   W2S_CUDA_OK(cudaGetLastError());
   return "";
 }

@@ -1,11 +1,13 @@
 // tcgen05 / TMEM / TMA contraction kernel (sm_100a) and its CUDA-core validation twin.
 //
 // Roles inside one 256-thread CTA (persistent over output tiles, static round-robin schedule):
-//   warp 0 lane 0 : TMA producer   -- fills a STAGES-deep ring of {A 128x64, W BNx64} bf16 tiles (128B swizzle)
-//   warp 1 lane 0 : MMA issuer     -- tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16 per instruction,
+// (the warp scheduler favours high warp ids, so the two latency-critical single-thread roles sit above the
+//  ALU-heavy epilogue warps)
+//   warp 8 lane 0 : TMA producer   -- fills a STAGES-deep ring of {A 128x64, W BNx64} bf16 tiles (128B swizzle)
+//   warp 9 lane 0 : MMA issuer     -- tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16 per instruction,
 //                                     accumulating in one of two TMEM accumulator slots
-//   warp 2        : TMEM allocator
-//   warps 4..11   : epilogue       -- tcgen05.ld the finished accumulator (thread = row), bias / activation /
+//   warp 10       : TMEM allocator
+//   warps 0..7    : epilogue       -- tcgen05.ld the finished accumulator (thread = row), bias / activation /
 //                                     GLU / residual, vectorised global stores, while the MMA warp already
 //                                     works on the next tile in the other TMEM slot
 // Pipelines: full/empty mbarriers per smem stage (TMA <-> MMA), tmem_full/tmem_empty per accumulator slot
@@ -13,6 +15,7 @@
 #include "gemm.cuh"
 
 #include <cudaTypedefs.h>
+#include <cstdlib>
 #include <mutex>
 
 namespace w2s {
@@ -154,24 +157,28 @@ struct TcCfg {
 struct TileCoord {
   int g, b, m0, n0;
 };
-__device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int tile, int BN) {
+template <bool MC>
+__device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int unit, int rank, int BN) {
   TileCoord c;
-  int nt = tile % p.tiles_n;
-  int r = tile / p.tiles_n;
-  int mt = r % p.tiles_m;
-  r /= p.tiles_m;
+  int nt = unit % p.tiles_n;
+  int r = unit / p.tiles_n;
+  int mu = r % p.units_m;
+  r /= p.units_m;
   c.b = r % p.Bz;
   c.g = r / p.Bz;
-  c.m0 = mt * 128;
+  c.m0 = (MC ? 2 * mu + rank : mu) * 128;   // an odd tile count leaves the last pair's second tile empty (all rows masked)
   c.n0 = nt * BN;
   return c;
 }
 
-template <int BN>
+template <int BN, bool MC>
 __global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                const GemmDev p) {
   using C = TcCfg<BN>;
+  const int rank = MC ? (int)cluster_ctarank() : 0;
+  const int unit0 = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;
@@ -187,14 +194,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapW);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == 9 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), MC ? 2 : 1);   // multicast: the peer's W half also lands in this stage
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -203,21 +210,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 2) {
+  if (warp == 10) {
     tmem_alloc<C::TMEM_COLS>(tmem_slot);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();   // barrier inits visible to the peer before any multicast traffic
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 0) {
+  if (warp == 8) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(p, tile, BN);
+      for (int unit = unit0; unit < p.num_units; unit += unit_step) {
+        const TileCoord tc = decode_tile<MC>(p, unit, rank, BN);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
@@ -225,7 +233,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const int kcol = kb - krow * p.a_kb_per_row;
           const uint32_t sa = tiles + stage * C::STAGE_BYTES;
           tma_load_3d(sa, &mapA, full_bar(stage), tc.g * p.a_g_col + kcol * 64, tc.m0 + krow, tc.b);
-          tma_load_3d(sa + C::A_BYTES, &mapW, full_bar(stage), kb * 64, tc.n0, tc.g);
+          if constexpr (MC) {
+            // this CTA fetches half of the W tile and multicasts it to both CTAs of the pair
+            tma_load_3d_mc(sa + C::A_BYTES + rank * (C::B_BYTES / 2), &mapW, full_bar(stage), kb * 64,
+                           tc.n0 + rank * (BN / 2), tc.g, (uint16_t)0x3);
+          } else {
+            tma_load_3d(sa + C::A_BYTES, &mapW, full_bar(stage), kb * 64, tc.n0, tc.g);
+          }
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -233,14 +247,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int unit = unit0; unit < p.num_units; unit += unit_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * C::ACC_COLS;
@@ -255,7 +269,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             // +32 bytes per K=16 step inside the 128-byte swizzle row: +2 in the (addr >> 4) field
             umma_bf16(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));
+          if constexpr (MC) umma_commit_mc(empty_bar(stage), (uint16_t)0x3);
+          else umma_commit(empty_bar(stage));
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -266,20 +281,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (acc == 0) acc_phase ^= 1u;
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 8) {
     const int q = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(p, tile, BN);
+    for (int unit = unit0; unit < p.num_units; unit += unit_step) {
+      const TileCoord tc = decode_tile<MC>(p, unit, rank, BN);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int m = tc.m0 + q * 32 + lane;
       const bool row_ok = m < p.M;
       const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C::ACC_COLS;
-      // warps 4..7 take the even column chunks of their lane quadrant, warps 8..11 the odd ones
+      // warps 0..3 take the even column chunks of their lane quadrant, warps 4..7 the odd ones
 #pragma unroll 1
-      for (int c = ((warp - 4) >> 2) * C::CH; c < BN; c += 2 * C::CH) {
+      for (int c = (warp >> 2) * C::CH; c < BN; c += 2 * C::CH) {
         float v[C::CH];
         if constexpr (C::CH == 32) tmem_ld_32x32(t0 + c, v);
         else tmem_ld_32x16(t0 + c, v);
@@ -295,7 +310,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if constexpr (MC) cluster_sync_all();   // the peer may still be multicasting into / signalling this CTA
+  if (warp == 10) {
     tc_fence_after();
     tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }
@@ -366,8 +382,11 @@ static std::string g_init_err;
 
 template <int BN>
 static cudaError_t set_attr() {
-  return cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)TcCfg<BN>::SMEM);
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)TcCfg<BN>::SMEM);
+  if (e == cudaSuccess && BN >= 128)
+    e = cudaFuncSetAttribute(gemm_tc_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<BN>::SMEM);
+  return e;
 }
 
 std::string gemm_init() {
@@ -437,13 +456,23 @@ std::string gemm_prepare(const GemmProblem& p, int num_sms, GemmLaunch* out) {
   d.tiles_n = p.N / bn;
   d.num_tiles = d.tiles_m * d.tiles_n * p.Bz * p.G;
   d.num_kb = p.K / 64;
+  // W-tile multicast over CTA pairs: worth it when there are enough tiles to keep all pairs busy
+  static const bool mc_enabled = getenv("W2S_NO_MULTICAST") == nullptr;
+  out->mc = (mc_enabled && bn >= 128 && d.tiles_m >= 2 && d.num_tiles >= 2 * num_sms) ? 1 : 0;
+  d.units_m = out->mc ? (d.tiles_m + 1) / 2 : d.tiles_m;
+  d.num_units = d.units_m * d.tiles_n * p.Bz * p.G;
   d.a_kb_per_row = p.a_kb_per_row;
   d.a_g_col = p.a_g_col;
   d.a = p.a; d.w = p.w;
   d.a_cols = p.a_cols; d.a_rows = p.a_rows; d.a_row_stride = p.a_row_stride; d.a_batch_stride = p.a_batch_stride;
   d.epi = p.epi;
   out->bn = bn;
-  out->grid = d.num_tiles < num_sms ? d.num_tiles : num_sms;
+  if (out->mc) {
+    const int clusters = d.num_units < num_sms / 2 ? d.num_units : num_sms / 2;
+    out->grid = 2 * clusters;
+  } else {
+    out->grid = d.num_units < num_sms ? d.num_units : num_sms;
+  }
   out->smem = bn == 256 ? TcCfg<256>::SMEM : bn == 128 ? TcCfg<128>::SMEM : bn == 64 ? TcCfg<64>::SMEM
               : bn == 48 ? TcCfg<48>::SMEM : TcCfg<32>::SMEM;
   if ((p.a_row_stride * 2) % 16 || (p.a_batch_stride * 2) % 16 || (reinterpret_cast<uintptr_t>(p.a) % 16))
@@ -457,19 +486,42 @@ std::string gemm_prepare(const GemmProblem& p, int num_sms, GemmLaunch* out) {
   {
     uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)p.N, (uint64_t)p.G};
     uint64_t str[2] = {(uint64_t)p.K * 2, (uint64_t)p.K * p.N * 2};
-    uint32_t box[3] = {64, (uint32_t)bn, 1};
+    uint32_t box[3] = {64, (uint32_t)(out->mc ? bn / 2 : bn), 1};
     W2S_TRY(make_tensor_map_bf16(&out->mapW, p.w, 3, dims, str, box));
   }
   return "";
 }
 
+template <int BN>
+static cudaError_t launch_mc(const GemmLaunch& l, cudaStream_t s) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(l.grid);
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = l.smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, true>, l.mapA, l.mapW, l.dev);
+}
+
 std::string gemm_launch_tc(const GemmLaunch& l, cudaStream_t s) {
+  if (l.mc) {
+    if (l.bn == 256) W2S_CUDA_OK(launch_mc<256>(l, s));
+    else if (l.bn == 128) W2S_CUDA_OK(launch_mc<128>(l, s));
+    else return "gemm: multicast needs BN >= 128";
+    return "";
+  }
   switch (l.bn) {
-    case 256: gemm_tc_kernel<256><<<l.grid, 384, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
-    case 128: gemm_tc_kernel<128><<<l.grid, 384, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
-    case 64: gemm_tc_kernel<64><<<l.grid, 384, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
-    case 48: gemm_tc_kernel<48><<<l.grid, 384, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
-    case 32: gemm_tc_kernel<32><<<l.grid, 384, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
+    case 256: gemm_tc_kernel<256, false><<<l.grid, 384, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
+    case 128: gemm_tc_kernel<128, false><<<l.grid, 384, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
+    case 64: gemm_tc_kernel<64, false><<<l.grid, 384, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
+    case 48: gemm_tc_kernel<48, false><<<l.grid, 384, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
+    case 32: gemm_tc_kernel<32, false><<<l.grid, 384, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
     default: return "gemm: bad BN";
   }
   W2S_CUDA_OK(cudaGetLastError());

@@ -42,6 +42,7 @@ struct GemmProblem {
 struct GemmDev {
   int M, N, K, Bz, G;
   int tiles_m, tiles_n, num_tiles, num_kb;
+  int units_m, num_units;  // scheduling units: tiles, or M-pairs of tiles when the W tile is multicast over a CTA pair
   int a_kb_per_row, a_g_col;
   // validation-kernel addressing
   const __nv_bfloat16* a;
@@ -54,6 +55,7 @@ struct GemmLaunch {
   CUtensorMap mapA, mapW;
   GemmDev dev;
   int bn = 0;
+  int mc = 0;   // 1: clusters of 2 CTAs (adjacent M tiles) share every W tile through TMA multicast
   int grid = 0;
   size_t smem = 0;
 };
