@@ -178,6 +178,8 @@ def run_b200(args):
     peaks = load_peaks()
 
     wl, cfg, clip, Z, kw = build_problem(args.workload)
+    if args.coalitions > 0:
+        Z, kw = Z[:args.coalitions], kw[:args.coalitions]
     model = make_hf_model(cfg)
     # batch tile: rows = B * T' should fill whole waves of 128-row tiles on 148 SMs (B = floor(148*128*k / T'))
     T = cfg.num_frames(wl.num_samples)
@@ -315,6 +317,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="coalitions per batch tile (0 = fill whole waves)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--coalitions", type=int, default=0, help="profiling aid: evaluate only the first N coalitions per step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

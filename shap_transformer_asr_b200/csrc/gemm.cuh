@@ -56,6 +56,7 @@ struct GemmLaunch {
   GemmDev dev;
   int bn = 0;
   int mc = 0;   // 1: clusters of 2 CTAs (adjacent M tiles) share every W tile through TMA multicast
+                // 2: CTA pairs form one tcgen05.mma cta_group::2 unit (256-row tile, W split across the pair)
   int grid = 0;
   size_t smem = 0;
 };
@@ -63,6 +64,8 @@ struct GemmLaunch {
 std::string gemm_prepare(const GemmProblem& p, int num_sms, GemmLaunch* out);
 std::string gemm_launch_tc(const GemmLaunch& l, cudaStream_t s);
 std::string gemm_launch_simt(const GemmLaunch& l, cudaStream_t s);
+std::string gemm2_init();
+std::string gemm2_launch(const GemmLaunch& l, cudaStream_t s);
 std::string gemm_init();  // resolves cuTensorMapEncodeTiled, sets kernel attributes
 
 // shared by other translation units that build their own tensor maps (attention)
