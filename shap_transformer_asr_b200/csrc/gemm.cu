@@ -295,6 +295,11 @@ std::string gemm_init() {
 
 std::string make_tensor_map_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                                  const uint64_t* strides_bytes, const uint32_t* box) {
+  return make_tensor_map(map, base, 0, rank, dims, strides_bytes, box);
+}
+
+std::string make_tensor_map(CUtensorMap* map, const void* base, int fp32, int rank, const uint64_t* dims,
+                            const uint64_t* strides_bytes, const uint32_t* box) {
   if (!g_encode) return "tensor map encoder not initialised";
   cuuint64_t gdim[5];
   cuuint64_t gstr[5];
@@ -306,7 +311,7 @@ std::string make_tensor_map_bf16(CUtensorMap* map, const void* base, int rank, c
     es[i] = 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+  CUresult r = g_encode(map, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -373,6 +378,21 @@ std::string gemm_prepare(const GemmProblem& p, int num_sms, GemmLaunch* out) {
     uint64_t str[2] = {(uint64_t)p.K * 2, (uint64_t)p.K * p.N * 2};
     uint32_t box[3] = {64, (uint32_t)(out->mc ? bn / 2 : bn), 1};
     W2S_TRY(make_tensor_map_bf16(&out->mapW, p.w, 3, dims, str, box));
+  }
+  // pair kernel: TMA-store epilogue (not for the GLU epilogue, whose output width differs from the tile width)
+  out->tma_out = 0;
+  static const bool tma_out_enabled = getenv("W2S_NO_TMA_STORE") == nullptr;
+  if (out->mc == 2 && tma_out_enabled && !p.epi.glu && p.epi.vt == nullptr) {
+    const uint64_t es = p.epi.out_fp32 ? 4 : 2;
+    const uint64_t ldb = p.Bz > 1 ? (uint64_t)p.epi.ldb : (uint64_t)p.epi.ldm * p.M;
+    const uint64_t ldg = p.G > 1 ? (uint64_t)p.epi.ldg : ldb * p.Bz;
+    uint64_t dims[4] = {(uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.Bz, (uint64_t)p.G};
+    uint64_t str[3] = {(uint64_t)p.epi.ldm * es, ldb * es, ldg * es};
+    uint32_t box[4] = {p.epi.out_fp32 ? 32u : 64u, 32, 1, 1};
+    if (str[0] % 16 == 0 && str[1] % 16 == 0 && str[2] % 16 == 0 && reinterpret_cast<uintptr_t>(p.epi.out) % 16 == 0) {
+      W2S_TRY(make_tensor_map(&out->mapOut, p.epi.out, p.epi.out_fp32, 4, dims, str, box));
+      out->tma_out = 1;
+    }
   }
   return "";
 }

@@ -53,6 +53,8 @@ struct GemmDev {
 
 struct GemmLaunch {
   CUtensorMap mapA, mapW;
+  CUtensorMap mapOut;   // pair kernel: output tile written by TMA stores from a swizzled staging strip
+  int tma_out = 0;
   GemmDev dev;
   int bn = 0;
   int mc = 0;   // 1: clusters of 2 CTAs (adjacent M tiles) share every W tile through TMA multicast
@@ -71,5 +73,7 @@ std::string gemm_init();  // resolves cuTensorMapEncodeTiled, sets kernel attrib
 // shared by other translation units that build their own tensor maps (attention)
 std::string make_tensor_map_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                                  const uint64_t* strides_bytes, const uint32_t* box);
+std::string make_tensor_map(CUtensorMap* map, const void* base, int fp32, int rank, const uint64_t* dims,
+                            const uint64_t* strides_bytes, const uint32_t* box);
 
 }  // namespace w2s

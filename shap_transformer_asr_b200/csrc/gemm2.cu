@@ -18,16 +18,19 @@ struct Tc2Cfg {
   static constexpr int A_BYTES = 128 * 64 * 2;
   static constexpr int B_BYTES = (BN / 2) * 64 * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN >= 256 ? 6 : 8;
+  static constexpr int EPI_BYTES = 8 * 4096 + 8 * 512;   // per-warp 32 x 128 B output staging + bias strip
+  // the operand ring takes what the epilogue strips leave: 5 x 32 KB (BN = 256) or 7 x 24 KB (BN = 128)
+  static constexpr int STAGES = (227 * 1024 - 1024 - 256 - EPI_BYTES) / STAGE_BYTES > 8
+                                    ? 8 : (227 * 1024 - 1024 - 256 - EPI_BYTES) / STAGE_BYTES;
   static constexpr int ACC_COLS = BN;
   static constexpr int TMEM_COLS = 2 * ACC_COLS;
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(384, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
-                const GemmDev p) {
+                const __grid_constant__ CUtensorMap mapOut, const GemmDev p, const int tma_out) {
   using C = Tc2Cfg<BN>;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -36,19 +39,21 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;
   uint8_t* tiles_ptr = smem_raw + (tiles - raw);
-  const uint32_t bars = tiles + C::STAGES * C::STAGE_BYTES;
+  const uint32_t epi_smem = tiles + C::STAGES * C::STAGE_BYTES;   // 1024-aligned: staging strips, then bias strips
+  const uint32_t bars = epi_smem + C::EPI_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(tiles_ptr + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
+      reinterpret_cast<volatile uint32_t*>(tiles_ptr + C::STAGES * C::STAGE_BYTES + C::EPI_BYTES + 8 * (2 * C::STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapW);
+    if (tma_out) tma_prefetch_desc(&mapOut);
   }
   if (warp == 9 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -132,7 +137,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       }
     }
   } else if (warp < 8) {
-    const int q = warp & 3;
+    const int q = warp & 3, hsel = warp >> 2;
+    const uint32_t stg = epi_smem + warp * 4096;              // this warp's 32 rows x 128 B staging strip
+    const uint32_t stg_row = stg + lane * 128;
+    float* sbias = reinterpret_cast<float*>(tiles_ptr + C::STAGES * C::STAGE_BYTES + 8 * 4096 + warp * 512);
+    const bool f32 = p.epi.out_fp32 != 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int unit = unit0; unit < p.num_units; unit += unit_step) {
@@ -142,16 +151,64 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       r /= p.units_m;
       const int b = r % p.Bz, g = r / p.Bz;
       const int m0 = (2 * mu + (int)rank) * 128, n0 = nt * BN;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
       const int m = m0 + q * 32 + lane;
       const bool row_ok = m < p.M;
       const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C::ACC_COLS;
+      if (tma_out) {
+        // Column ownership: blocks of 128 B of output (32 fp32 / 64 bf16 columns); warps 0..3 take the even blocks of
+        // their lane quadrant, warps 4..7 the odd ones.  The bias values of the warp's columns are fetched into its
+        // shared-memory strip BEFORE the accumulator wait, so the global latency hides behind the MMAs.
+        const int bw = f32 ? 32 : 64;
+        const int nblk = BN / (2 * bw);
+        if (p.epi.bias) {
+          for (int i = lane; i < nblk * bw; i += 32) {
+            const int col = (2 * (i / bw) + hsel) * bw + (i % bw);
+            sbias[i] = __ldg(p.epi.bias + (long long)g * p.N + n0 + col);
+          }
+        }
+        __syncwarp();
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c = (warp >> 2) * 32; c < BN; c += 64) {
-        float v[32];
-        tmem_ld_32x32(t0 + c, v);
-        if (row_ok) epi_store<32>(p.epi, p.N, g, b, m, n0 + c, v);
+        for (int ib = 0; ib < nblk; ++ib) {
+          const int cblk = (2 * ib + hsel) * bw;
+          if (lane == 0) tma_store_wait_read();   // the previous store of this warp has drained the strip
+          __syncwarp();
+#pragma unroll 1
+          for (int sub = 0; sub < (f32 ? 1 : 2); ++sub) {
+            const int c = cblk + sub * 32;
+            float v[32];
+            tmem_ld_32x32(t0 + c, v);
+            epi_math32(p.epi, p.epi.bias ? sbias + ib * bw + sub * 32 : nullptr, p.N, g, b, m, n0 + c, row_ok, v);
+            if (f32) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                sts128(stg_row + (((uint32_t)j ^ ((uint32_t)lane & 7u)) << 4), __float_as_uint(v[4 * j]),
+                       __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                sts128(stg_row + (((uint32_t)(sub * 4 + j) ^ ((uint32_t)lane & 7u)) << 4),
+                       pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                       pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&mapOut, stg, n0 + cblk, m0 + q * 32, b, g);   // rows >= M are clipped by the tensor map
+            tma_store_commit();
+          }
+        }
+      } else {
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = hsel * 32; c < BN; c += 64) {
+          float v[32];
+          tmem_ld_32x32(t0 + c, v);
+          if (row_ok) epi_store<32>(p.epi, p.N, g, b, m, n0 + c, v);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -162,6 +219,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (tma_out && lane == 0) tma_store_wait_all();   // global writes complete before the CTA retires
   }
 
   tc_fence_before();
@@ -198,7 +256,7 @@ static cudaError_t launch2(const GemmLaunch& l, cudaStream_t s) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<BN>, l.mapA, l.mapW, l.dev);
+  return cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<BN>, l.mapA, l.mapW, l.tma_out ? l.mapOut : l.mapA, l.dev, l.tma_out);
 }
 
 std::string gemm2_launch(const GemmLaunch& l, cudaStream_t s) {

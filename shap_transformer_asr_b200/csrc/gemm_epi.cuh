@@ -122,4 +122,65 @@ __device__ __forceinline__ void epi_store(const EpiParams& e, int N, int g, int 
   }
 }
 
+
+// Pair-kernel epilogue, first half: bias (from the warp's shared-memory strip) + activation + alpha / residual on
+// 32 consecutive columns of one row; the caller stores the result (TMA staging).
+__device__ __forceinline__ void epi_math32(const EpiParams& e, const float* sbias, int N, int g, int b, int m,
+                                           int ncol0, bool row_ok, float* v) {
+  if (sbias) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = *reinterpret_cast<const float4*>(sbias + 4 * j);
+      v[4 * j] += t.x;
+      v[4 * j + 1] += t.y;
+      v[4 * j + 2] += t.z;
+      v[4 * j + 3] += t.w;
+    }
+  }
+  if (e.act == ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      const float2 r = gelu_erf2(make_float2(v[j], v[j + 1]));
+      v[j] = r.x;
+      v[j + 1] = r.y;
+    }
+  } else if (e.act == ACT_SWISH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = swish(v[j]);
+  }
+  if (e.residual) {
+    if (row_ok) {
+      const long long off = (long long)g * e.ldg + (long long)b * e.ldb + (long long)m * e.ldm + ncol0;
+      if (e.res_fp32) {
+        const float* rp = reinterpret_cast<const float*>(e.residual) + off;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 r = *reinterpret_cast<const float4*>(rp + j);
+          v[j] = fmaf(v[j], e.alpha, r.x);
+          v[j + 1] = fmaf(v[j + 1], e.alpha, r.y);
+          v[j + 2] = fmaf(v[j + 2], e.alpha, r.z);
+          v[j + 3] = fmaf(v[j + 3], e.alpha, r.w);
+        }
+      } else {
+        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(e.residual) + off;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const uint4 r = *reinterpret_cast<const uint4*>(rp + j);
+          v[j] = fmaf(v[j], e.alpha, bf16_lo(r.x));
+          v[j + 1] = fmaf(v[j + 1], e.alpha, bf16_hi(r.x));
+          v[j + 2] = fmaf(v[j + 2], e.alpha, bf16_lo(r.y));
+          v[j + 3] = fmaf(v[j + 3], e.alpha, bf16_hi(r.y));
+          v[j + 4] = fmaf(v[j + 4], e.alpha, bf16_lo(r.z));
+          v[j + 5] = fmaf(v[j + 5], e.alpha, bf16_hi(r.z));
+          v[j + 6] = fmaf(v[j + 6], e.alpha, bf16_lo(r.w));
+          v[j + 7] = fmaf(v[j + 7], e.alpha, bf16_hi(r.w));
+        }
+      }
+    }
+  } else if (e.alpha != 1.0f) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= e.alpha;
+  }
+}
+
 }  // namespace w2s
