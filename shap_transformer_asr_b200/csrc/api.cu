@@ -5,6 +5,7 @@
 #include "gemm.cuh"
 #include "kernels.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -52,7 +53,9 @@ struct Plan {
   std::vector<GemmLaunch*> gemms;
   std::vector<AttnTcPlan*> attn;
   std::vector<AttnRelPlan*> attn_rel;
+  std::vector<PosConvPlan*> posconv;
   ~Plan() {
+    for (auto* pc : posconv) posconv_free(pc);
     for (auto* g : gemms) delete g;
     for (auto* a : attn) attention_tc_free(a);
     for (auto* a : attn_rel) attention_rel_free(a);
@@ -546,7 +549,15 @@ struct PlanBuilder {
       p.epi.residual = h->h0; p.epi.res_fp32 = 0;
       p.epi.out = h->pre; p.epi.out_fp32 = 1;
       p.epi.ldg = cpg; p.epi.ldb = (long long)T * H; p.epi.ldm = H;
-      W2S_TRY(add_gemm("pos_conv", p));
+      static const bool pc_enabled = getenv("W2S_NO_POSCONV_KERNEL") == nullptr;
+      if (pc_enabled && !simt_gemm && posconv_supported(H, G, kp)) {
+        PosConvPlan* pc = nullptr;
+        W2S_TRY(posconv_prepare(h->hp, h->pos_w, n, T, H, G, kp, p.epi, h->num_sms, &pc));
+        plan->posconv.push_back(pc);
+        add("pos_conv", [=](cudaStream_t s) { return posconv_launch(pc, s); }, 2.0 * n * T * (double)H * cpg * kp);
+      } else {
+        W2S_TRY(add_gemm("pos_conv", p));
+      }
       if (!stable)
         add_ln("encoder_ln", h->pre, 1, rows, H, h->enc_ln_g, h->enc_ln_b, c.layer_norm_eps, ACT_NONE, h->hb, nullptr);
     }
@@ -848,6 +859,7 @@ int w2s_create(const w2s_config* cfg, const char* const* names, const float* con
   std::string e = gemm_init();
   if (e.empty()) e = attention_tc_init();
   if (e.empty()) e = attention_rel_init();
+  if (e.empty()) e = posconv_init();
   if (e.empty()) {
     WeightTable wt;
     wt.prefix = cfg->kind == 1 ? "wav2vec2_conformer." : "wav2vec2.";

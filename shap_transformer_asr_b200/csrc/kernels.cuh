@@ -43,6 +43,16 @@ std::string launch_layernorm(const void* in, int in_fp32, long long rows, int H,
 std::string launch_pos_pad(const __nv_bfloat16* h, int B, int T, int H, int G, int kpos, __nv_bfloat16* out,
                            cudaStream_t s);
 
+// ---- K4: positional conv on tcgen05 with a resident input window (posconv.cu) --------------------------------
+struct EpiParams;
+struct PosConvPlan;
+std::string posconv_init();
+bool posconv_supported(int H, int G, int kpos);
+std::string posconv_prepare(const __nv_bfloat16* x, const __nv_bfloat16* w, int B, int T, int H, int G, int kpos,
+                            const EpiParams& epi, int num_sms, PosConvPlan** out);
+std::string posconv_launch(const PosConvPlan* plan, cudaStream_t s);
+void posconv_free(PosConvPlan* plan);
+
 // ---- attention -------------------------------------------------------------------------------------
 struct AttnParams {
   const __nv_bfloat16* qkv;   // [B*T, ld]: plain models (q | k | v), ld = 3H; conformer relative (q+u | q+v | k | v), ld = 4H

@@ -1,0 +1,237 @@
+// K4: grouped positional convolution (HF wav2vec2/modeling_wav2vec2.py:326-379: Conv1d(H, H, k=128, pad=64,
+// groups=16), last frame dropped, GELU) + residual, as a tcgen05 kernel specialised for its Toeplitz structure.
+//
+// For one (coalition, group) the 128 taps all read the SAME input window shifted by one frame per tap.  The generic
+// contraction kernel reloads a 128x64 A tile for every tap (16 KB per 96 MMA cycles -- far beyond what shared memory
+// can absorb); here the whole window (up to 256 + 127 frames x 64 channels, 48 KB, 128B swizzle) is loaded ONCE and
+// each tap's A operand is just a descriptor whose start address is advanced by one 128-byte row.  Only the 6-8 KB
+// weight slice of the tap streams through the TMA ring.  One unit = (coalition, group, 256-frame chunk): two
+// 128-row accumulators share every weight slice.
+#include "gemm.cuh"
+#include "gemm_epi.cuh"
+#include "kernels.cuh"
+
+namespace w2s {
+
+struct PosConvDev {
+  int T, cpg, G, B, kpos, chunks, num_units;
+  EpiParams epi;
+};
+
+constexpr int PC_WIN_BYTES = 3 * 16384;   // 384 rows x 128 B
+constexpr int PC_WSTAGES = 12;
+
+template <int NG>
+struct PcCfg {
+  static constexpr int W_BYTES = NG * 128;
+  static constexpr size_t SMEM = 2 * PC_WIN_BYTES + (size_t)PC_WSTAGES * W_BYTES + 1024 + 512;
+};
+
+template <int NG>
+__global__ void __launch_bounds__(384, 1)
+posconv_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW, const PosConvDev p) {
+  using C = PcCfg<NG>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t sWin = base, sW = base + 2 * PC_WIN_BYTES;
+  const uint32_t bars = sW + PC_WSTAGES * C::W_BYTES;
+  auto wfull = [&](int s) { return bars + 8u * s; };
+  auto wempty = [&](int s) { return bars + 8u * (PC_WSTAGES + s); };
+  auto winfull = [&](int i) { return bars + 8u * (2 * PC_WSTAGES + i); };
+  auto winempty = [&](int i) { return bars + 8u * (2 * PC_WSTAGES + 2 + i); };
+  auto tfull = [&](int a) { return bars + 8u * (2 * PC_WSTAGES + 4 + a); };
+  auto tempty = [&](int a) { return bars + 8u * (2 * PC_WSTAGES + 6 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * PC_WSTAGES + 8);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+      base_ptr + 2 * PC_WIN_BYTES + PC_WSTAGES * C::W_BYTES + 8 * (2 * PC_WSTAGES + 8));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&mapX);
+    tma_prefetch_desc(&mapW);
+  }
+  if (warp == 9 && lane == 0) {
+    for (int s = 0; s < PC_WSTAGES; ++s) {
+      mbar_init(wfull(s), 1);
+      mbar_init(wempty(s), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(winfull(i), 1);
+      mbar_init(winempty(i), 1);
+      mbar_init(tfull(i), 1);
+      mbar_init(tempty(i), 8);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 10) {
+    tmem_alloc<256>(tmem_slot);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      int ws = 0;
+      uint32_t wphase = 0;
+      int it = 0;
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
+        const int ch = unit % p.chunks;
+        const int g = (unit / p.chunks) % p.G;
+        const int b = unit / (p.chunks * p.G);
+        const int buf = it & 1;
+        const uint32_t bphase = (it >> 1) & 1;
+        mbar_wait(winempty(buf), bphase ^ 1u);
+        mbar_expect_tx(winfull(buf), PC_WIN_BYTES);
+        for (int i = 0; i < 3; ++i)
+          tma_load_3d(sWin + buf * PC_WIN_BYTES + i * 16384, &mapX, winfull(buf), g * 64, ch * 256 + i * 128, b);
+        for (int j = 0; j < p.kpos; ++j) {
+          mbar_wait(wempty(ws), wphase ^ 1u);
+          mbar_expect_tx(wfull(ws), C::W_BYTES);
+          tma_load_3d(sW + ws * C::W_BYTES, &mapW, wfull(ws), j * 64, 0, g);
+          if (++ws == PC_WSTAGES) {
+            ws = 0;
+            wphase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, NG);
+      int ws = 0;
+      uint32_t wphase = 0;
+      int it = 0;
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t bphase = (it >> 1) & 1;
+        mbar_wait(tempty(buf), bphase ^ 1u);
+        mbar_wait(winfull(buf), bphase);
+        tc_fence_after();
+        const uint32_t win = sWin + buf * PC_WIN_BYTES;
+        for (int j = 0; j < p.kpos; ++j) {
+          mbar_wait(wfull(ws), wphase);
+          tc_fence_after();
+          const uint64_t dw = umma_desc_sw128(sW + ws * C::W_BYTES);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            // tap j of output rows [128 half, 128 half + 128): window rows start at 128 half + j (one row = 128 B)
+            const uint64_t da = umma_desc_sw128(win + (uint32_t)(half * 128 + j) * 128u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + buf * 128 + half * 64, da + 2u * k, dw + 2u * k, idesc, (j | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(wempty(ws));
+          if (++ws == PC_WSTAGES) {
+            ws = 0;
+            wphase ^= 1u;
+          }
+        }
+        umma_commit(winempty(buf));
+        umma_commit(tfull(buf));
+      }
+    }
+  } else if (warp < 8) {
+    const int q = warp & 3, half = warp >> 2;
+    int it = 0;
+    for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
+      const int ch = unit % p.chunks;
+      const int g = (unit / p.chunks) % p.G;
+      const int b = unit / (p.chunks * p.G);
+      const int buf = it & 1;
+      const uint32_t bphase = (it >> 1) & 1;
+      mbar_wait(tfull(buf), bphase);
+      tc_fence_after();
+      const int t = ch * 256 + half * 128 + q * 32 + lane;
+      const bool row_ok = t < p.T;
+      const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 128 + half * 64;
+#pragma unroll 1
+      for (int c = 0; c < NG; c += 16) {
+        float v[16];
+        tmem_ld_32x16(t0 + c, v);
+        if (row_ok) epi_store<16>(p.epi, p.cpg, g, b, t, c, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(buf));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
+struct PosConvPlan {
+  CUtensorMap mapX, mapW;
+  PosConvDev dev;
+  int ng, grid;
+};
+
+std::string posconv_init() {
+  cudaError_t e = cudaFuncSetAttribute(posconv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PcCfg<32>::SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(posconv_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PcCfg<48>::SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(posconv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PcCfg<64>::SMEM);
+  if (e != cudaSuccess) return std::string("cudaFuncSetAttribute(posconv_kernel): ") + cudaGetErrorString(e);
+  return "";
+}
+
+bool posconv_supported(int H, int G, int kpos) {
+  const int cpg = H / G;
+  return (cpg == 32 || cpg == 48 || cpg == 64) && kpos >= 1 && kpos <= 128;
+}
+
+// x: padded input [B, T + kpos, G*64] bf16; w: [G][cpg][kpos*64] bf16; epilogue as for the generic kernel
+std::string posconv_prepare(const __nv_bfloat16* x, const __nv_bfloat16* w, int B, int T, int H, int G, int kpos,
+                            const EpiParams& epi, int num_sms, PosConvPlan** out) {
+  if (!posconv_supported(H, G, kpos)) return "positional conv kernel: unsupported channels per group";
+  PosConvPlan* pl = new PosConvPlan();
+  const int cpg = H / G;
+  pl->ng = cpg;
+  pl->dev.T = T; pl->dev.cpg = cpg; pl->dev.G = G; pl->dev.B = B; pl->dev.kpos = kpos;
+  pl->dev.chunks = (T + 255) / 256;
+  pl->dev.num_units = pl->dev.chunks * G * B;
+  pl->dev.epi = epi;
+  pl->grid = pl->dev.num_units < num_sms ? pl->dev.num_units : num_sms;
+  std::string err;
+  {
+    uint64_t dims[3] = {(uint64_t)G * 64, (uint64_t)(T + kpos), (uint64_t)B};
+    uint64_t str[2] = {(uint64_t)G * 64 * 2, (uint64_t)(T + kpos) * G * 64 * 2};
+    uint32_t box[3] = {64, 128, 1};
+    err = make_tensor_map_bf16(&pl->mapX, x, 3, dims, str, box);
+  }
+  if (err.empty()) {
+    uint64_t dims[3] = {(uint64_t)kpos * 64, (uint64_t)cpg, (uint64_t)G};
+    uint64_t str[2] = {(uint64_t)kpos * 64 * 2, (uint64_t)kpos * 64 * cpg * 2};
+    uint32_t box[3] = {64, (uint32_t)cpg, 1};
+    err = make_tensor_map_bf16(&pl->mapW, w, 3, dims, str, box);
+  }
+  if (!err.empty()) {
+    delete pl;
+    return err;
+  }
+  *out = pl;
+  return "";
+}
+
+std::string posconv_launch(const PosConvPlan* pl, cudaStream_t s) {
+  switch (pl->ng) {
+    case 32: posconv_kernel<32><<<pl->grid, 384, PcCfg<32>::SMEM, s>>>(pl->mapX, pl->mapW, pl->dev); break;
+    case 48: posconv_kernel<48><<<pl->grid, 384, PcCfg<48>::SMEM, s>>>(pl->mapX, pl->mapW, pl->dev); break;
+    case 64: posconv_kernel<64><<<pl->grid, 384, PcCfg<64>::SMEM, s>>>(pl->mapX, pl->mapW, pl->dev); break;
+    default: return "positional conv kernel: bad group width";
+  }
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+void posconv_free(PosConvPlan* pl) { delete pl; }
+
+}  // namespace w2s
