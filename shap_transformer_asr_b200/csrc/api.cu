@@ -113,6 +113,7 @@ struct w2s_handle {
   bf16 *fpn = nullptr, *h0 = nullptr, *hp = nullptr, *hb = nullptr, *h1 = nullptr, *qkv = nullptr, *ctx = nullptr,
        *ffn = nullptr;
   float* pre = nullptr;
+  float* logits = nullptr;
   bf16* hrot = nullptr;
   double* wls_work = nullptr;
   long long wls_cap = 0;
@@ -405,6 +406,7 @@ std::string ensure_workspace(w2s_handle* h, long long L) {
   W2S_TRY(dalloc(pool, &h->qkv, rows * 4 * H));
   W2S_TRY(dalloc(pool, &h->ctx, rows * H));
   W2S_TRY(dalloc(pool, &h->ffn, rows * I));
+  W2S_TRY(dalloc(pool, &h->logits, rows * (size_t)c.vocab_size));
   if (c.kind == 0) {
     W2S_TRY(dalloc(pool, &h->hp,
                    nb * (size_t)(T + c.num_conv_pos_embeddings) * c.num_conv_pos_embedding_groups * 64));
@@ -468,6 +470,41 @@ struct PlanBuilder {
   }
 
   std::string build_conformer();
+
+  // K9: lm_head on the contraction kernel (N = vocab) into an fp32 logits buffer, then the warp-level reduction.
+  // LOGITS mode writes straight into the caller's buffer; vocabularies that are not a multiple of 32 use the
+  // fused CUDA-core head kernel.
+  std::string add_head() {
+    const w2s_config& c = h->cfg;
+    const int T = h->T, H = c.hidden_size, V = c.vocab_size;
+    w2s_handle* hh = h;
+    const int nn = n;
+    auto params = [=]() {
+      HeadParams hp{};
+      hp.h = hh->hb; hp.w = hh->head_w; hp.bias = hh->head_b;
+      hp.n = nn; hp.T = T; hp.H = H; hp.V = V; hp.mode = hh->mode; hp.D = hh->D;
+      hp.frames = hh->frames; hp.tokens = hh->tokens; hp.out = hh->cur_out;
+      return hp;
+    };
+    if (V % 32 != 0 || simt_gemm) {
+      add("head", [=](cudaStream_t s) { return launch_head(params(), s); });
+      return "";
+    }
+    GemmProblem p = plain(h->hb, (long long)n * T, H, h->head_w, V);
+    p.epi.bias = h->head_b;
+    p.epi.out = h->logits;
+    p.epi.out_fp32 = 1;
+    W2S_TRY(add_gemm("lm_head", p));
+    add("head_reduce", [=](cudaStream_t s) -> std::string {
+      HeadParams hp = params();
+      if (hp.mode == W2S_OUT_LOGITS) {
+        W2S_CUDA_OK(cudaMemcpyAsync(hp.out, hh->logits, sizeof(float) * (size_t)nn * T * V, cudaMemcpyDeviceToDevice, s));
+        return "";
+      }
+      return launch_head_reduce(hh->logits, hp, s);
+    });
+    return "";
+  }
 
   std::string build() {
     const w2s_config& c = h->cfg;
@@ -615,13 +652,7 @@ struct PlanBuilder {
     if (stable)
       add_ln("encoder_ln", h->pre, 1, rows, H, h->enc_ln_g, h->enc_ln_b, c.layer_norm_eps, ACT_NONE, h->hb, nullptr);
     // ---- K9: lm_head + reduction ---------------------------------------------------------------------------
-    add("head", [=](cudaStream_t s) {
-      HeadParams hp{};
-      hp.h = hh->hb; hp.w = hh->head_w; hp.bias = hh->head_b;
-      hp.n = nn; hp.T = T; hp.H = H; hp.V = hh->cfg.vocab_size; hp.mode = hh->mode; hp.D = hh->D;
-      hp.frames = hh->frames; hp.tokens = hh->tokens; hp.out = hh->cur_out;
-      return launch_head(hp, s);
-    });
+    W2S_TRY(add_head());
     return "";
   }
 };
@@ -721,13 +752,7 @@ std::string PlanBuilder::build_conformer() {
     add_ln(ls + "final_ln", h->pre, 1, rows, H, w.lnfin_g, w.lnfin_b, 1e-5f, ACT_NONE, nullptr, h->pre);
   }
   add_ln("encoder_ln", h->pre, 1, rows, H, h->enc_ln_g, h->enc_ln_b, c.layer_norm_eps, ACT_NONE, h->hb, nullptr);
-  add("head", [=](cudaStream_t s) {
-    HeadParams hp{};
-    hp.h = hh->hb; hp.w = hh->head_w; hp.bias = hh->head_b;
-    hp.n = nn; hp.T = T; hp.H = H; hp.V = hh->cfg.vocab_size; hp.mode = hh->mode; hp.D = hh->D;
-    hp.frames = hh->frames; hp.tokens = hh->tokens; hp.out = hh->cur_out;
-    return launch_head(hp, s);
-  });
+  W2S_TRY(add_head());
   return "";
 }
 

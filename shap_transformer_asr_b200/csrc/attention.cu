@@ -149,11 +149,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
                     const __grid_constant__ CUtensorMap mapV, const AttnTcDev p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ float s_red[2][128];
-  __shared__ uint64_t s_bar[2];
+  __shared__ uint64_t s_bar[3];
   __shared__ uint32_t s_tmem;
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t bar_load = smem_u32(&s_bar[0]), bar_mma = smem_u32(&s_bar[1]);
+  const uint32_t bar_load = smem_u32(&s_bar[0]), bar_mma = smem_u32(&s_bar[1]), bar_v = smem_u32(&s_bar[2]);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qd = warp & 3, hf = warp >> 2;
@@ -166,6 +166,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     tma_prefetch_desc(&mapV);
     mbar_init(bar_load, 1);
     mbar_init(bar_mma, 1);
+    mbar_init(bar_v, 1);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -181,12 +182,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
 
   // ---- loads ---------------------------------------------------------------------------------------
   if (threadIdx.x == 0) {
-    const uint32_t bytes = 16384u + (p.n1 > 0 ? 65536u : 32768u) + 8192u * p.nblk;
-    mbar_expect_tx(bar_load, bytes);
+    // Q and K gate the score MMAs; V is only needed for P V, so it lands behind the softmax on its own barrier
+    mbar_expect_tx(bar_load, 16384u + (p.n1 > 0 ? 65536u : 32768u));
     tma_load_4d(base + ATT_SQ, &mapQ, bar_load, 0, qt * 128, h, b);
     tma_load_4d(base + ATT_SK, &mapK, bar_load, 0, 0, h, b);
     if (p.n1 > 0) tma_load_4d(base + ATT_SK + 32768, &mapK, bar_load, 0, 256, h, b);
-    for (int kb = 0; kb < p.nblk; ++kb) tma_load_4d(sV + kb * 8192, &mapV, bar_load, 0, kb * 64, h, b);
+    mbar_expect_tx(bar_v, 8192u * p.nblk);
+    for (int kb = 0; kb < p.nblk; ++kb) tma_load_4d(sV + kb * 8192, &mapV, bar_v, 0, kb * 64, h, b);
     mbar_wait(bar_load, 0);
     // ---- S = Q K^T ---------------------------------------------------------------------------------
     tc_fence_after();
@@ -271,6 +273,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) {
+      if (r0 == 0) mbar_wait(bar_v, 0);
       tc_fence_after();
       constexpr uint32_t idesc = umma_idesc_bf16_bmn(128, 64);
       for (int kb = r0; kb < r0 + cnt; ++kb) {

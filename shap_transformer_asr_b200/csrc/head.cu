@@ -94,6 +94,69 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p, long long
   }
 }
 
+// second stage of the tensor-core head: logits[rows, V] (fp32, bias included) -> reduction; one warp per work item
+__global__ void __launch_bounds__(256) head_reduce_kernel(const float* __restrict__ logits, const HeadParams p,
+                                                           long long items) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool targeted = (p.mode == W2S_OUT_LOGIT || p.mode == W2S_OUT_LOGPROB);
+  const int per = targeted ? p.D : p.T;
+  for (long long it = (long long)blockIdx.x * 8 + warp; it < items; it += (long long)gridDim.x * 8) {
+    const int b = (int)(it / per);
+    const int d = (int)(it - (long long)b * per);
+    const int t = targeted ? p.frames[d] : d;
+    const float* row = logits + ((long long)b * p.T + t) * p.V;
+    float logit[HEAD_MAXJ];
+    float mx = -INFINITY, sm = 0.f;
+#pragma unroll
+    for (int j = 0; j < HEAD_MAXJ; ++j) {
+      const int v = lane + 32 * j;
+      logit[j] = v < p.V ? row[v] : -INFINITY;
+      if (v < p.V) {
+        mx = fmaxf(mx, logit[j]);
+        sm += logit[j];
+      }
+    }
+    mx = warp_max(mx);
+    if (p.mode == W2S_OUT_MAX) {
+      if (lane == 0) p.out[(long long)b * p.T + t] = mx;
+    } else if (p.mode == W2S_OUT_MEAN) {
+      sm = warp_sum(sm);
+      if (lane == 0) atomicAdd(p.out + b, sm / ((float)p.V * (float)p.T));
+    } else {
+      const int tok = p.tokens[d];
+      float sel = 0.f;
+#pragma unroll
+      for (int j = 0; j < HEAD_MAXJ; ++j) {
+        const float cand = __shfl_sync(0xffffffffu, logit[j], tok & 31);
+        if ((tok >> 5) == j) sel = cand;
+      }
+      if (p.mode == W2S_OUT_LOGPROB) {
+        float se = 0.f;
+#pragma unroll
+        for (int j = 0; j < HEAD_MAXJ; ++j)
+          if (lane + 32 * j < p.V) se += __expf(logit[j] - mx);
+        se = warp_sum(se);
+        sel -= mx + __logf(se);
+      }
+      if (lane == 0) p.out[(long long)b * p.D + d] = sel;
+    }
+  }
+}
+
+std::string launch_head_reduce(const float* logits, const HeadParams& p, cudaStream_t s) {
+  if (p.V > 32 * HEAD_MAXJ) return "head: vocab_size > 128 not supported";
+  const bool targeted = (p.mode == W2S_OUT_LOGIT || p.mode == W2S_OUT_LOGPROB);
+  if (targeted && (p.D <= 0 || !p.frames || !p.tokens)) return "head: targets not set (w2s_set_targets)";
+  const long long items = (long long)p.n * (targeted ? p.D : p.T);
+  if (items == 0) return "";
+  if (p.mode == W2S_OUT_MEAN) W2S_CUDA_OK(cudaMemsetAsync(p.out, 0, sizeof(float) * p.n, s));
+  long long blocks = (items + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  head_reduce_kernel<<<(unsigned)blocks, 256, 0, s>>>(logits, p, items);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
 static bool g_head_attr = false;
 
 std::string launch_head(const HeadParams& p, cudaStream_t s) {

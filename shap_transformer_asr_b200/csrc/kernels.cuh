@@ -98,6 +98,8 @@ struct HeadParams {
   float* out;                 // [n, width]
 };
 std::string launch_head(const HeadParams& p, cudaStream_t s);
+// tensor-core variant: the contraction kernel writes logits[n*T, V] (fp32, bias added), this reduces them
+std::string launch_head_reduce(const float* logits, const HeadParams& p, cudaStream_t s);
 
 // ---- K12: KernelSHAP constrained WLS -----------------------------------------------------------------------
 std::string launch_wls(const uint32_t* zbits, int zwords, const double* w, const float* y, long long K, int M,
