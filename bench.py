@@ -186,7 +186,7 @@ def run_b200(args):
     batch = args.batch
     if batch <= 0:
         k = 1
-        while (148 * 128 * k) // T < 64:
+        while (148 * 128 * k) // T < 128:
             k += 1
         batch = min(wl.num_coalitions, (148 * 128 * k) // T)
     eng = Engine(model, cfg, device=local, max_batch=batch)

@@ -189,6 +189,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     if (p.n1 > 0) tma_load_4d(base + ATT_SK + 32768, &mapK, bar_load, 0, 256, h, b);
     mbar_expect_tx(bar_v, 8192u * p.nblk);
     for (int kb = 0; kb < p.nblk; ++kb) tma_load_4d(sV + kb * 8192, &mapV, bar_v, 0, kb * 64, h, b);
+    {
+      // warm L2 for the CTA that will follow on this SM slot (CTAs are dispatched in linear block order, two per SM)
+      const long long nx = (long long)gridDim.x * gridDim.y;
+      const long long lin = ((long long)b * gridDim.y + h) * gridDim.x + qt + 2LL * 148;
+      if (lin < nx * gridDim.z) {
+        const int nb = (int)(lin / nx), nh2 = (int)((lin / gridDim.x) % gridDim.y), nq = (int)(lin % gridDim.x);
+        tma_prefetch_l2_4d(&mapQ, 0, nq * 128, nh2, nb);
+        tma_prefetch_l2_4d(&mapK, 0, 0, nh2, nb);
+        if (p.n1 > 0) tma_prefetch_l2_4d(&mapK, 0, 256, nh2, nb);
+        for (int kb = 0; kb < p.nblk; ++kb) tma_prefetch_l2_4d(&mapV, 0, kb * 64, nh2, nb);
+      }
+    }
     mbar_wait(bar_load, 0);
     // ---- S = Q K^T ---------------------------------------------------------------------------------
     tc_fence_after();
