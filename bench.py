@@ -41,6 +41,16 @@ def load_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
 
 
+def ncu_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if workload != "C2" or not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return {"dram_bytes_per_launch": d["mean_traffic_bytes_per_launch"],
+            "algorithmic_bytes_per_launch": d["mean_algorithmic_bytes_per_launch"], "source": "profiles/r01_ncu_traffic.json"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -306,7 +316,7 @@ def run_b200(args):
         "gpu_launches": int(args.steps * (n_batches * launches_per_batch + 1)),
         "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (all contraction launches)", "achieved": achieved,
                      "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
-                     "traffic": None, "peak_source": peaks["source"] + " bf16_tflops_sustained",
+                     "traffic": ncu_traffic(wl.name), "peak_source": peaks["source"] + " bf16_tflops_sustained",
                      "launches": int(gemm_n), "share_of_step": gemm_ms / total_prof_ms,
                      "profiled_ms_per_step": prof_ms / args.steps,
                      "whole_step_tflops": value * flops_fwd / 1e12 / world},
