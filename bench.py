@@ -274,6 +274,19 @@ def run_b200(args):
         e2e_s = float(t.item())
     e2e = world * K * args.steps / e2e_s
 
+    # ---- seconds per explained clip: sampler + target selection + all coalitions + all-gather + device WLS, end to end ----
+    from shap_transformer_asr_b200 import KernelShapExplainer
+    ex = KernelShapExplainer(eng, nsamples=wl.num_coalitions, seed=0)
+    ex.explain(clip, num_segments=wl.num_segments)            # warm-up (plans for the sharded row counts)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = ex.explain(clip, num_segments=wl.num_segments)
+    torch.cuda.synchronize()
+    sec_per_clip = time.perf_counter() - t0
+    wls_status = int(res["status"].item())
+    eng.set_clip(clip, num_segments=wl.num_segments)
+    eng.set_targets("logprob", frames, tokens)
+
     if rank != 0:
         td.destroy_process_group()
         return
@@ -310,7 +323,10 @@ def run_b200(args):
         "config": {"workload": f"{wl.name}: {wl.description}", "coalitions_per_step_per_gpu": K, "outputs_per_coalition": D,
                    "batch_tile": tile, "gflop_per_forward": flops_fwd / 1e9,
                    "l2": "256 MB flush write between steps; per-step activation stream >> 126 MB L2",
-                   "weights": "random-init (seed 0)", "sec_per_clip_forward_part": ms / args.steps / 1e3},
+                   "weights": "random-init (seed 0)", "sec_per_clip_forward_part": ms / args.steps / 1e3,
+                   "sec_per_explained_clip": sec_per_clip, "sec_per_explained_clip_note":
+                   f"KernelShapExplainer.explain on {world} GPU(s): host sampler + target selection + {K} coalitions sharded over ranks "
+                   f"+ all-gather + device WLS (status {wls_status})"},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(cb.h2d_bytes), "d2h_bytes_per_step": int(cb.d2h_bytes)},
         "gpu_launches": int(args.steps * (n_batches * launches_per_batch + 1)),

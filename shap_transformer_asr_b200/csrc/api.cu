@@ -461,8 +461,8 @@ struct PlanBuilder {
     plan->steps.push_back(std::move(st));
   }
   std::string add_ln(const std::string& name, const void* in, int in_fp32, long long rows, int H, const float* g,
-                     const float* b, float eps, int act, bf16* out, float* out_f32) {
-    add(name, [=](cudaStream_t s) { return launch_layernorm(in, in_fp32, rows, H, g, b, eps, act, out, out_f32, s); });
+                     const float* b, float eps, int act, bf16* out, float* out_f32, const bf16* residual = nullptr) {
+    add(name, [=](cudaStream_t s) { return launch_layernorm(in, in_fp32, rows, H, g, b, eps, act, out, out_f32, s, residual); });
     return "";
   }
   static GemmProblem plain(const bf16* a, long long rows, int K, const bf16* w, int N) {
@@ -611,6 +611,7 @@ struct PlanBuilder {
       plan->attn.push_back(apl);
     }
     const int act = c.hidden_act == 1 ? ACT_SWISH : ACT_GELU;
+    const bool ln_res = !stable && (H == 128 || H == 256 || H == 512 || H == 768 || H == 1024);
     for (int l = 0; l < c.num_hidden_layers; ++l) {
       const LayerW& w = h->layers[l];
       const std::string ls = "L" + std::to_string(l) + ".";
@@ -626,13 +627,17 @@ struct PlanBuilder {
       {
         GemmProblem p = plain(h->ctx, rows, H, w.wo, H);
         p.epi.bias = w.bo;
-        p.epi.residual = stable ? (const void*)h->pre : (const void*)h->hb;
-        p.epi.res_fp32 = stable ? 1 : 0;
+        // post-LN: the bf16 residual is added by the LayerNorm kernel (coalesced), not by the GEMM epilogue
+        if (stable || !ln_res) {
+          p.epi.residual = stable ? (const void*)h->pre : (const void*)h->hb;
+          p.epi.res_fp32 = stable ? 1 : 0;
+        }
         p.epi.out = h->pre; p.epi.out_fp32 = 1;
         W2S_TRY(add_gemm(ls + "out_proj", p));
       }
       if (stable) add_ln(ls + "ln2", h->pre, 1, rows, H, w.ln2_g, w.ln2_b, c.layer_norm_eps, ACT_NONE, h->h1, nullptr);
-      else add_ln(ls + "ln1", h->pre, 1, rows, H, w.ln1_g, w.ln1_b, c.layer_norm_eps, ACT_NONE, h->h1, nullptr);
+      else add_ln(ls + "ln1", h->pre, 1, rows, H, w.ln1_g, w.ln1_b, c.layer_norm_eps, ACT_NONE, h->h1, nullptr,
+                  ln_res ? h->hb : nullptr);
       {
         GemmProblem p = plain(h->h1, rows, H, w.w1, I);
         p.epi.bias = w.b1; p.epi.act = act;
@@ -642,12 +647,15 @@ struct PlanBuilder {
       {
         GemmProblem p = plain(h->ffn, rows, I, w.w2, H);
         p.epi.bias = w.b2;
-        p.epi.residual = stable ? (const void*)h->pre : (const void*)h->h1;
-        p.epi.res_fp32 = stable ? 1 : 0;
+        if (stable || !ln_res) {
+          p.epi.residual = stable ? (const void*)h->pre : (const void*)h->h1;
+          p.epi.res_fp32 = stable ? 1 : 0;
+        }
         p.epi.out = h->pre; p.epi.out_fp32 = 1;
         W2S_TRY(add_gemm(ls + "ffn2", p));
       }
-      if (!stable) add_ln(ls + "ln2", h->pre, 1, rows, H, w.ln2_g, w.ln2_b, c.layer_norm_eps, ACT_NONE, h->hb, nullptr);
+      if (!stable) add_ln(ls + "ln2", h->pre, 1, rows, H, w.ln2_g, w.ln2_b, c.layer_norm_eps, ACT_NONE, h->hb, nullptr,
+                          ln_res ? h->h1 : nullptr);
     }
     if (stable)
       add_ln("encoder_ln", h->pre, 1, rows, H, h->enc_ln_g, h->enc_ln_b, c.layer_norm_eps, ACT_NONE, h->hb, nullptr);

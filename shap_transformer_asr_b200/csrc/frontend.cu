@@ -323,7 +323,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
 
 // vectorised variant: H = 128 * NV, each lane owns NV float4 (columns 4*(lane + 32*i) ..)
 template <bool IN_F32, int NV>
-__global__ void __launch_bounds__(256) layernorm_vec_kernel(const void* __restrict__ in, long long rows,
+__global__ void __launch_bounds__(256) layernorm_vec_kernel(const void* __restrict__ in,
+                                                             const __nv_bfloat16* __restrict__ residual, long long rows,
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float eps, int act,
                                                              __nv_bfloat16* __restrict__ out,
@@ -342,6 +343,13 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const void* __restri
     } else {
       const uint2 u = __ldcs(reinterpret_cast<const uint2*>(in) + row * (H / 4) + c4);
       v[i] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+    }
+    if (residual) {   // post-LN blocks: LayerNorm(sublayer output + its bf16 input), HF wav2vec2 :597-602
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(residual) + row * (H / 4) + c4);
+      v[i].x += bf16_lo(u.x);
+      v[i].y += bf16_hi(u.x);
+      v[i].z += bf16_lo(u.y);
+      v[i].w += bf16_hi(u.y);
     }
     sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
@@ -379,27 +387,28 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const void* __restri
 }
 
 template <bool IN_F32>
-static bool launch_ln_vec(const void* in, long long rows, int H, const float* gamma, const float* beta, float eps,
-                          int act, __nv_bfloat16* out, float* out_f32, cudaStream_t s) {
+static bool launch_ln_vec(const void* in, const __nv_bfloat16* residual, long long rows, int H, const float* gamma,
+                          const float* beta, float eps, int act, __nv_bfloat16* out, float* out_f32, cudaStream_t s) {
   const unsigned grid = (unsigned)((rows + 7) / 8);
   switch (H) {
-    case 128: layernorm_vec_kernel<IN_F32, 1><<<grid, 256, 0, s>>>(in, rows, gamma, beta, eps, act, out, out_f32); return true;
-    case 256: layernorm_vec_kernel<IN_F32, 2><<<grid, 256, 0, s>>>(in, rows, gamma, beta, eps, act, out, out_f32); return true;
-    case 512: layernorm_vec_kernel<IN_F32, 4><<<grid, 256, 0, s>>>(in, rows, gamma, beta, eps, act, out, out_f32); return true;
-    case 768: layernorm_vec_kernel<IN_F32, 6><<<grid, 256, 0, s>>>(in, rows, gamma, beta, eps, act, out, out_f32); return true;
-    case 1024: layernorm_vec_kernel<IN_F32, 8><<<grid, 256, 0, s>>>(in, rows, gamma, beta, eps, act, out, out_f32); return true;
+    case 128: layernorm_vec_kernel<IN_F32, 1><<<grid, 256, 0, s>>>(in, residual, rows, gamma, beta, eps, act, out, out_f32); return true;
+    case 256: layernorm_vec_kernel<IN_F32, 2><<<grid, 256, 0, s>>>(in, residual, rows, gamma, beta, eps, act, out, out_f32); return true;
+    case 512: layernorm_vec_kernel<IN_F32, 4><<<grid, 256, 0, s>>>(in, residual, rows, gamma, beta, eps, act, out, out_f32); return true;
+    case 768: layernorm_vec_kernel<IN_F32, 6><<<grid, 256, 0, s>>>(in, residual, rows, gamma, beta, eps, act, out, out_f32); return true;
+    case 1024: layernorm_vec_kernel<IN_F32, 8><<<grid, 256, 0, s>>>(in, residual, rows, gamma, beta, eps, act, out, out_f32); return true;
     default: return false;
   }
 }
 
 std::string launch_layernorm(const void* in, int in_fp32, long long rows, int H, const float* gamma,
                              const float* beta, float eps, int act, __nv_bfloat16* out, float* out_f32,
-                             cudaStream_t s) {
+                             cudaStream_t s, const __nv_bfloat16* residual) {
   if (H > 1024) return "layernorm: H > 1024 not supported";
   if (rows == 0) return "";
-  const bool vec = in_fp32 ? launch_ln_vec<true>(in, rows, H, gamma, beta, eps, act, out, out_f32, s)
-                           : launch_ln_vec<false>(in, rows, H, gamma, beta, eps, act, out, out_f32, s);
+  const bool vec = in_fp32 ? launch_ln_vec<true>(in, residual, rows, H, gamma, beta, eps, act, out, out_f32, s)
+                           : launch_ln_vec<false>(in, residual, rows, H, gamma, beta, eps, act, out, out_f32, s);
   if (!vec) {
+    if (residual) return "layernorm: fused residual needs H in {128, 256, 512, 768, 1024}";
     const unsigned grid = (unsigned)((rows + 7) / 8);
     if (in_fp32) layernorm_kernel<true><<<grid, 256, 0, s>>>(in, rows, H, gamma, beta, eps, act, out, out_f32);
     else layernorm_kernel<false><<<grid, 256, 0, s>>>(in, rows, H, gamma, beta, eps, act, out, out_f32);

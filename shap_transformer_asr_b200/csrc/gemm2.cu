@@ -142,6 +142,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const uint32_t stg_row = stg + lane * 128;
     float* sbias = reinterpret_cast<float*>(tiles_ptr + C::STAGES * C::STAGE_BYTES + 8 * 4096 + warp * 512);
     const bool f32 = p.epi.out_fp32 != 0;
+    // in-place fp32 accumulation (out == residual): let the TMA engine add in L2 instead of loading the residual
+    const bool reduce_add = tma_out && f32 && p.epi.res_fp32 && p.epi.residual == p.epi.out;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int unit = unit0; unit < p.num_units; unit += unit_step) {
@@ -179,7 +181,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const int c = cblk + sub * 32;
             float v[32];
             tmem_ld_32x32(t0 + c, v);
-            epi_math32(p.epi, p.epi.bias ? sbias + ib * bw + sub * 32 : nullptr, p.N, g, b, m, n0 + c, row_ok, v);
+            epi_math32(p.epi, p.epi.bias ? sbias + ib * bw + sub * 32 : nullptr, p.N, g, b, m, n0 + c, row_ok, v,
+                       reduce_add);
             if (f32) {
 #pragma unroll
               for (int j = 0; j < 8; ++j)
@@ -196,7 +199,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            tma_store_4d(&mapOut, stg, n0 + cblk, m0 + q * 32, b, g);   // rows >= M are clipped by the tensor map
+            if (reduce_add) tma_reduce_add_4d(&mapOut, stg, n0 + cblk, m0 + q * 32, b, g);
+            else tma_store_4d(&mapOut, stg, n0 + cblk, m0 + q * 32, b, g);   // rows >= M are clipped by the tensor map
             tma_store_commit();
           }
         }

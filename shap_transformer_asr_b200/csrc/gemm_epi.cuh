@@ -126,7 +126,7 @@ __device__ __forceinline__ void epi_store(const EpiParams& e, int N, int g, int 
 // Pair-kernel epilogue, first half: bias (from the warp's shared-memory strip) + activation + alpha / residual on
 // 32 consecutive columns of one row; the caller stores the result (TMA staging).
 __device__ __forceinline__ void epi_math32(const EpiParams& e, const float* sbias, int N, int g, int b, int m,
-                                           int ncol0, bool row_ok, float* v) {
+                                           int ncol0, bool row_ok, float* v, bool skip_residual = false) {
   if (sbias) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -148,7 +148,7 @@ __device__ __forceinline__ void epi_math32(const EpiParams& e, const float* sbia
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = swish(v[j]);
   }
-  if (e.residual) {
+  if (e.residual && !skip_residual) {
     if (row_ok) {
       const long long off = (long long)g * e.ldg + (long long)b * e.ldb + (long long)m * e.ldm + ncol0;
       if (e.res_fp32) {

@@ -35,9 +35,10 @@ std::string launch_conv0_ln_prep(const float* w, const float* bias, int C, int k
                                  float* wb, float* scalars /*[2]: mean b, mean b^2*/, cudaStream_t s);
 
 // ---- LayerNorm over the last dimension (fp32 or bf16 in, bf16 out), optional activation ---------------
+// `residual` (bf16, optional): normalises in + residual (post-LN transformer blocks)
 std::string launch_layernorm(const void* in, int in_fp32, long long rows, int H, const float* gamma,
                              const float* beta, float eps, int act, __nv_bfloat16* out, float* out_f32,
-                             cudaStream_t s);
+                             cudaStream_t s, const __nv_bfloat16* residual = nullptr);
 
 // ---- positional-conv input staging: [B, T, H] -> zero-padded [B, T + kpos, G*64] ------------------------
 std::string launch_pos_pad(const __nv_bfloat16* h, int B, int T, int H, int G, int kpos, __nv_bfloat16* out,
