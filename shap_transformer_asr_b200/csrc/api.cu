@@ -54,7 +54,9 @@ struct Plan {
   std::vector<AttnTcPlan*> attn;
   std::vector<AttnRelPlan*> attn_rel;
   std::vector<PosConvPlan*> posconv;
+  std::vector<AttnFaPlan*> attn_fa;
   ~Plan() {
+    for (auto* f : attn_fa) attention_fa_free(f);
     for (auto* pc : posconv) posconv_free(pc);
     for (auto* g : gemms) delete g;
     for (auto* a : attn) attention_tc_free(a);
@@ -318,7 +320,12 @@ std::string load_weights(w2s_handle* h, const WeightTable& wt) {
         W2S_TRY(dalloc(h->allocs, &w.pw1, (size_t)2 * H * H));
         W2S_TRY(launch_repack_glu(src, w.pw1, H, H, 0));
       }
-      W2S_TRY(copy_f32(h, wt, lp + "conv_module.depthwise_conv.weight", (int64_t)H * kd, &w.dw_w));
+      {
+        const float* src = nullptr;
+        W2S_TRY(wt.get(lp + "conv_module.depthwise_conv.weight", (int64_t)H * kd, &src));
+        W2S_TRY(dalloc(h->allocs, &w.dw_w, (size_t)H * kd));
+        W2S_TRY(launch_transpose_f32(src, w.dw_w, H, kd, 0));   // [H][k] -> [k][H]: lanes read consecutive channels
+      }
       {
         const float *g = nullptr, *b = nullptr, *mu = nullptr, *var = nullptr;
         W2S_TRY(wt.get(lp + "conv_module.batch_norm.weight", H, &g));
@@ -604,8 +611,15 @@ struct PlanBuilder {
     ap.heads = c.num_attention_heads; ap.hd = H / c.num_attention_heads;
     ap.ld = 3 * H; ap.q_off = 0; ap.qv_off = 0; ap.k_off = H; ap.v_off = 2 * H;
     ap.scale = 1.0f / sqrtf((float)ap.hd);
-    const bool tc_attn = !simt_attn && attention_tc_supported(ap);
+    static const bool fa_enabled = getenv("W2S_ATTN_V1") == nullptr;
+    const bool fa_attn = fa_enabled && !simt_attn && attention_fa_supported(ap);
+    const bool tc_attn = !fa_attn && !simt_attn && attention_tc_supported(ap);
     AttnTcPlan* apl = nullptr;
+    AttnFaPlan* afl = nullptr;
+    if (fa_attn) {
+      W2S_TRY(attention_fa_prepare(ap, h->num_sms, &afl));
+      plan->attn_fa.push_back(afl);
+    }
     if (tc_attn) {
       W2S_TRY(attention_tc_prepare(ap, &apl));
       plan->attn.push_back(apl);
@@ -622,7 +636,8 @@ struct PlanBuilder {
         p.epi.out = h->qkv;
         W2S_TRY(add_gemm(ls + "qkv", p));
       }
-      if (tc_attn) add(ls + "attention", [=](cudaStream_t s) { return attention_tc_launch(apl, s); });
+      if (fa_attn) add(ls + "attention", [=](cudaStream_t s) { return attention_fa_launch(afl, s); });
+      else if (tc_attn) add(ls + "attention", [=](cudaStream_t s) { return attention_tc_launch(apl, s); });
       else add(ls + "attention", [=](cudaStream_t s) { return launch_attention_simt(ap, s); });
       {
         GemmProblem p = plain(h->ctx, rows, H, w.wo, H);
@@ -683,7 +698,14 @@ std::string PlanBuilder::build_conformer() {
   const int nq = rel ? 2 : 1;
   ap.ld = (nq + 2) * H; ap.q_off = 0; ap.qv_off = rel ? H : 0; ap.k_off = nq * H; ap.v_off = (nq + 1) * H;
   AttnTcPlan* apl = nullptr;
-  const bool tc_attn = !rel && !simt_attn && attention_tc_supported(ap);
+  AttnFaPlan* afl = nullptr;
+  static const bool fa_enabled = getenv("W2S_ATTN_V1") == nullptr;
+  const bool fa_attn = fa_enabled && !rel && !simt_attn && attention_fa_supported(ap);
+  const bool tc_attn = !fa_attn && !rel && !simt_attn && attention_tc_supported(ap);
+  if (fa_attn) {
+    W2S_TRY(attention_fa_prepare(ap, h->num_sms, &afl));
+    plan->attn_fa.push_back(afl);
+  }
   if (tc_attn) {
     W2S_TRY(attention_tc_prepare(ap, &apl));
     plan->attn.push_back(apl);
@@ -720,7 +742,9 @@ std::string PlanBuilder::build_conformer() {
       p.epi.bias = w.bqkv; p.epi.out = h->qkv;
       W2S_TRY(add_gemm(ls + "qkv", p));
     }
-    if (tc_attn) {
+    if (fa_attn) {
+      add(ls + "attention", [=](cudaStream_t s) { return attention_fa_launch(afl, s); });
+    } else if (tc_attn) {
       add(ls + "attention", [=](cudaStream_t s) { return attention_tc_launch(apl, s); });
     } else {
       AttnParams lp = ap;
@@ -893,6 +917,7 @@ int w2s_create(const w2s_config* cfg, const char* const* names, const float* con
   if (e.empty()) e = attention_tc_init();
   if (e.empty()) e = attention_rel_init();
   if (e.empty()) e = posconv_init();
+  if (e.empty()) e = attention_fa_init();
   if (e.empty()) {
     WeightTable wt;
     wt.prefix = cfg->kind == 1 ? "wav2vec2_conformer." : "wav2vec2.";

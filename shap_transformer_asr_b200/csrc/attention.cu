@@ -514,7 +514,7 @@ attention_rel_kernel(const __grid_constant__ CUtensorMap mapQU, const __grid_con
       for (int t = 0; t < 32; ++t) {
         const float v = ac[t] + stg[31 - lane + t];
         const bool ok = (j0 + c_local + t) < p.T;
-        sc[ch * 32 + t] = ok ? v : -INFINITY;
+        sc[ch * 32 + t] = ok ? v : -3.0e38f;   // finite sentinel: exp2 underflows to 0 without a select
         mx = fmaxf(mx, sc[ch * 32 + t]);
       }
       __syncwarp();
@@ -523,24 +523,23 @@ attention_rel_kernel(const __grid_constant__ CUtensorMap mapQU, const __grid_con
     __syncthreads();
     mx = fmaxf(s_red[0][row], s_red[1][row]);
     m_h[hk] = mx;
-    const float mscaled = (mx == -INFINITY) ? 0.f : mx * p.scale_log2e;
-    float sum = 0.f;
+    const float2 sc2 = make_float2(p.scale_log2e, p.scale_log2e);
+    const float2 nm2 = make_float2(-mx * p.scale_log2e, -mx * p.scale_log2e);
+    float2 acc2 = make_float2(0.f, 0.f);
     const uint32_t sp_row = base + REL_P + hf * 16384 + row * 128;
 #pragma unroll
     for (int c8 = 0; c8 < 8; ++c8) {
-      float e[8];
+      float2 e[4];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const float s = sc[c8 * 8 + t];
-        e[t] = (s == -INFINITY) ? 0.f : ex2_approx(fmaf(s, p.scale_log2e, -mscaled));
-        sum += e[t];
+      for (int t = 0; t < 4; ++t) {
+        const float2 a = __ffma2_rn(make_float2(sc[c8 * 8 + 2 * t], sc[c8 * 8 + 2 * t + 1]), sc2, nm2);
+        e[t] = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+        acc2 = __fadd2_rn(acc2, e[t]);
       }
-      const uint32_t addr = sp_row + (((uint32_t)c8 ^ ((uint32_t)row & 7u)) << 4);
-      const uint32_t u0 = pack_bf16x2(e[0], e[1]), u1 = pack_bf16x2(e[2], e[3]);
-      const uint32_t u2 = pack_bf16x2(e[4], e[5]), u3 = pack_bf16x2(e[6], e[7]);
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u0), "r"(u1), "r"(u2), "r"(u3) : "memory");
+      sts128(sp_row + (((uint32_t)c8 ^ ((uint32_t)row & 7u)) << 4), pack_bf16x2(e[0].x, e[0].y),
+             pack_bf16x2(e[1].x, e[1].y), pack_bf16x2(e[2].x, e[2].y), pack_bf16x2(e[3].x, e[3].y));
     }
-    l_h[hk] = sum;
+    l_h[hk] = acc2.x + acc2.y;
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();   // also orders the s_red reads above before the next half overwrites it
@@ -566,7 +565,7 @@ attention_rel_kernel(const __grid_constant__ CUtensorMap mapQU, const __grid_con
   const float l1 = s_sum[1][0][row] + s_sum[1][1][row];
   const float m = fmaxf(m_h[0], m_h[1]);
   const float a0 = ex2_approx((m_h[0] - m) * p.scale_log2e);
-  const float a1 = (p.nh > 1 && m_h[1] != -INFINITY) ? ex2_approx((m_h[1] - m) * p.scale_log2e) : 0.f;
+  const float a1 = (p.nh > 1) ? ex2_approx((m_h[1] - m) * p.scale_log2e) : 0.f;
   const float inv = 1.0f / (a0 * l0 + a1 * l1);
   const int i = qt * 128 + row;
   __nv_bfloat16* orow = p.ctx + ((long long)b * p.T + i) * p.H + h * 64 + hf * 32;

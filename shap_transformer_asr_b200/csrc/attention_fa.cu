@@ -1,0 +1,331 @@
+// Self-attention (no mask, head_dim 64, T' <= 512) as a persistent, warp-specialised tcgen05 kernel.
+//
+// Work item = (128-query tile, head, coalition); keys are walked in blocks of 128.  Blocks are made INDEPENDENT:
+// every block keeps its own softmax maximum m_j, partial sum l_j and its own O_j accumulator in TMEM (4 x 64
+// columns), and the epilogue merges them,  out = sum_j a_j O_j / sum_j a_j l_j,  a_j = exp(m_j - max_j m_j),
+// so nothing is ever rescaled in TMEM and the three engines run decoupled:
+//   warp 8  (TMA)     Q tile per item, {K_j, V_j} through a 3-stage ring
+//   warp 9  (MMA)     S_j = Q K_j^T into one of two S buffers (128 fp32 columns each), O_j = P_j V_j one block behind
+//   warps 0-7 (softmax) read S_j from TMEM (two threads per query row, 64 keys each), write P_j = exp(S_j - m_j) as bf16
+//                     into one of two swizzled smem buffers, finally merge the O_j and store the context rows
+// HF wav2vec2/modeling_wav2vec2.py:438-463 (softmax(Q K^T / sqrt d) V, no mask, eval mode).
+#include "kernels.cuh"
+#include "gemm.cuh"
+
+namespace w2s {
+
+struct AttnFaDev {
+  __nv_bfloat16* ctx;
+  int B, T, H, heads, qtiles, num_items;
+  float scale_log2e;
+};
+struct AttnFaPlan {
+  CUtensorMap mapQ, mapK, mapV;
+  AttnFaDev dev;
+  int nb, grid;
+};
+
+constexpr int FA_KVS = 3;
+constexpr int FA_SQ = 0, FA_SKV = 16384, FA_SP = FA_SKV + FA_KVS * 32768, FA_RED = FA_SP + 2 * 32768,
+              FA_BAR = FA_RED + 2 * 2 * 128 * 4 + 4 * 2 * 128 * 4;
+constexpr size_t FA_SMEM = FA_BAR + 256 + 1024;
+
+__device__ __forceinline__ uint64_t fa_desc_mn(uint32_t a) { return umma_desc_sw128(a); }
+
+template <int NB>
+__global__ void __launch_bounds__(384, 1)
+attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                    const __grid_constant__ CUtensorMap mapV, const AttnFaDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  float* s_m = reinterpret_cast<float*>(base_ptr + FA_RED);               // [2][2][128] block maxima exchange
+  float* s_l = s_m + 2 * 2 * 128;                                          // [4][2][128] partial sums exchange
+  const uint32_t bars = base + FA_BAR;
+  const uint32_t q_full = bars, q_empty = bars + 8, o_full = bars + 16, o_empty = bars + 24;
+  auto kv_full = [&](int s) { return bars + 32 + 8u * s; };
+  auto kv_empty = [&](int s) { return bars + 32 + 8u * (FA_KVS + s); };
+  auto s_full = [&](int i) { return bars + 96 + 8u * i; };
+  auto s_empty = [&](int i) { return bars + 112 + 8u * i; };
+  auto p_full = [&](int i) { return bars + 128 + 8u * i; };
+  auto p_empty = [&](int i) { return bars + 144 + 8u * i; };
+  const uint32_t tmem_slot = bars + 160;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + FA_BAR + 160);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+  }
+  if (warp == 9 && lane == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 8);
+    for (int s = 0; s < FA_KVS; ++s) {
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(s_full(i), 1);
+      mbar_init(s_empty(i), 8);
+      mbar_init(p_full(i), 8);
+      mbar_init(p_empty(i), 1);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 10) {
+    tmem_alloc<512>(tmem_slot);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  // TMEM columns: S buffers at 0 / 128, O_j at 256 + 64 j
+
+  if (warp == 8) {
+    if (lane == 0) {
+      uint32_t kvc = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+        const int qt = item % p.qtiles, h = (item / p.qtiles) % p.heads, b = item / (p.qtiles * p.heads);
+        mbar_wait(q_empty, (uint32_t)(it & 1) ^ 1u);
+        mbar_expect_tx(q_full, 16384);
+        tma_load_4d(base + FA_SQ, &mapQ, q_full, 0, qt * 128, h, b);
+#pragma unroll 1
+        for (int j = 0; j < NB; ++j, ++kvc) {
+          const int s = kvc % FA_KVS;
+          mbar_wait(kv_empty(s), ((kvc / FA_KVS) & 1u) ^ 1u);
+          mbar_expect_tx(kv_full(s), 32768);
+          tma_load_4d(base + FA_SKV + s * 32768, &mapK, kv_full(s), 0, j * 128, h, b);
+          tma_load_4d(base + FA_SKV + s * 32768 + 16384, &mapV, kv_full(s), 0, j * 128, h, b);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64) | (1u << 16);   // B operand (V) is MN-major
+      uint32_t kvc = 0, sc = 0, pc = 0;
+      int it = 0;
+      auto issue_pv = [&](int jj, int stage) {
+        const int pb = pc & 1;
+        mbar_wait(p_full(pb), (pc >> 1) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint64_t dp = umma_desc_sw128(base + FA_SP + pb * 32768 + kb * 16384);
+          const uint64_t dv = fa_desc_mn(base + FA_SKV + stage * 32768 + 16384 + kb * 8192);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + 256 + 64 * jj, dp + 2u * k, dv + 128u * k, idesc_pv, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(p_empty(pb));
+        umma_commit(kv_empty(stage));
+        ++pc;
+      };
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+        mbar_wait(q_full, (uint32_t)(it & 1));
+        mbar_wait(o_empty, (uint32_t)(it & 1) ^ 1u);
+        int prev_stage = 0;
+#pragma unroll 1
+        for (int j = 0; j < NB; ++j, ++kvc, ++sc) {
+          const int s = kvc % FA_KVS, sb = sc & 1;
+          mbar_wait(kv_full(s), (kvc / FA_KVS) & 1u);
+          mbar_wait(s_empty(sb), ((sc >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint64_t dq = umma_desc_sw128(base + FA_SQ);
+          const uint64_t dk = umma_desc_sw128(base + FA_SKV + s * 32768);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem + sb * 128, dq + 2u * k, dk + 2u * k, idesc_qk, k != 0 ? 1u : 0u);
+          umma_commit(s_full(sb));
+          if (j == NB - 1) umma_commit(q_empty);
+          if (j > 0) issue_pv(j - 1, prev_stage);
+          prev_stage = s;
+        }
+        issue_pv(NB - 1, prev_stage);
+        umma_commit(o_full);
+      }
+    }
+  } else if (warp < 8) {
+    const int qd = warp & 3, hf = warp >> 2;
+    const int row = qd * 32 + lane;
+    const uint32_t trow = tmem + (static_cast<uint32_t>(qd * 32) << 16);
+    uint32_t sc = 0, pc = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+      const int qt = item % p.qtiles, h = (item / p.qtiles) % p.heads, b = item / (p.qtiles * p.heads);
+      float m_j[NB], l_j[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j, ++sc, ++pc) {
+        const int sb = sc & 1, pb = pc & 1;
+        mbar_wait(s_full(sb), (sc >> 1) & 1u);
+        tc_fence_after();
+        float sv[64];
+        {
+          float t0[32], t1[32];
+          tmem_ld_32x32(trow + sb * 128 + hf * 64, t0);
+          tmem_ld_32x32(trow + sb * 128 + hf * 64 + 32, t1);
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            sv[t] = t0[t];
+            sv[32 + t] = t1[t];
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty(sb));   // S_j is in registers: the MMA warp may overwrite the buffer
+        // Keys beyond T' (only possible in the last block) get a large negative FINITE score: exp2 then underflows to 0
+        // by itself, so the hot loops below carry no per-element compare / select.
+        const int key0 = j * 128 + hf * 64;
+        if (j == NB - 1 && key0 + 64 > p.T) {
+#pragma unroll
+          for (int t = 0; t < 64; ++t)
+            if (key0 + t >= p.T) sv[t] = -3.0e38f;
+        }
+        float mx0 = sv[0], mx1 = sv[1], mx2 = sv[2], mx3 = sv[3];
+#pragma unroll
+        for (int t = 4; t < 64; t += 4) {
+          mx0 = fmaxf(mx0, sv[t]);
+          mx1 = fmaxf(mx1, sv[t + 1]);
+          mx2 = fmaxf(mx2, sv[t + 2]);
+          mx3 = fmaxf(mx3, sv[t + 3]);
+        }
+        float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        s_m[(sb * 2 + hf) * 128 + row] = mx;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mx = fmaxf(s_m[(sb * 2 + 0) * 128 + row], s_m[(sb * 2 + 1) * 128 + row]);
+        m_j[j] = mx;
+        const float2 sc2 = make_float2(p.scale_log2e, p.scale_log2e);
+        const float2 nm2 = make_float2(-mx * p.scale_log2e, -mx * p.scale_log2e);
+        mbar_wait(p_empty(pb), ((pc >> 1) & 1u) ^ 1u);   // P V of two blocks ago has drained this P buffer
+        float2 acc2 = make_float2(0.f, 0.f);
+        const uint32_t sp_row = base + FA_SP + pb * 32768 + hf * 16384 + row * 128;
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          float2 e[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 a = __ffma2_rn(make_float2(sv[c8 * 8 + 2 * t], sv[c8 * 8 + 2 * t + 1]), sc2, nm2);
+            e[t] = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+            acc2 = __fadd2_rn(acc2, e[t]);
+          }
+          sts128(sp_row + (((uint32_t)c8 ^ ((uint32_t)row & 7u)) << 4), pack_bf16x2(e[0].x, e[0].y),
+                 pack_bf16x2(e[1].x, e[1].y), pack_bf16x2(e[2].x, e[2].y), pack_bf16x2(e[3].x, e[3].y));
+        }
+        const float sum = acc2.x + acc2.y;
+        l_j[j] = sum;
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(pb));
+      }
+      // ---- merge the blocks and store ------------------------------------------------------------------------------
+#pragma unroll
+      for (int j = 0; j < NB; ++j) s_l[(j * 2 + hf) * 128 + row] = l_j[j];
+      mbar_wait(o_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float m = m_j[0];
+#pragma unroll
+      for (int j = 1; j < NB; ++j) m = fmaxf(m, m_j[j]);
+      float a_j[NB], L = 0.f;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        a_j[j] = ex2_approx((m_j[j] - m) * p.scale_log2e);
+        L = fmaf(a_j[j], s_l[(j * 2 + 0) * 128 + row] + s_l[(j * 2 + 1) * 128 + row], L);
+      }
+      const float inv = 1.0f / L;
+      float o[32];
+#pragma unroll
+      for (int t = 0; t < 32; ++t) o[t] = 0.f;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        float v[32];
+        tmem_ld_32x32(trow + 256 + 64 * j + hf * 32, v);
+#pragma unroll
+        for (int t = 0; t < 32; ++t) o[t] = fmaf(a_j[j], v[t], o[t]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+      const int i = qt * 128 + row;
+      if (i < p.T) {
+        __nv_bfloat16* orow = p.ctx + ((long long)b * p.T + i) * p.H + h * 64 + hf * 32;
+#pragma unroll
+        for (int t = 0; t < 32; t += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(o[t] * inv, o[t + 1] * inv);
+          u.y = pack_bf16x2(o[t + 2] * inv, o[t + 3] * inv);
+          u.z = pack_bf16x2(o[t + 4] * inv, o[t + 5] * inv);
+          u.w = pack_bf16x2(o[t + 6] * inv, o[t + 7] * inv);
+          *reinterpret_cast<uint4*>(orow + t) = u;
+        }
+      }
+      // the s_l strip is rewritten only after the next item's NB block barriers, so no extra barrier is needed here
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+bool attention_fa_supported(const AttnParams& p) {
+  return p.hd == 64 && p.T <= 512 && p.pos_proj == nullptr && (p.H % 8 == 0);
+}
+
+std::string attention_fa_init() {
+  cudaError_t e = cudaFuncSetAttribute(attention_fa_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_fa_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_fa_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_fa_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FA_SMEM);
+  if (e != cudaSuccess) return std::string("cudaFuncSetAttribute(attention_fa_kernel): ") + cudaGetErrorString(e);
+  return "";
+}
+
+std::string attention_fa_prepare(const AttnParams& p, int num_sms, AttnFaPlan** out) {
+  if (!attention_fa_supported(p)) return "attention (tcgen05, pipelined): unsupported shape";
+  AttnFaPlan* pl = new AttnFaPlan();
+  pl->dev.ctx = p.ctx;
+  pl->dev.B = p.B; pl->dev.T = p.T; pl->dev.H = p.H; pl->dev.heads = p.heads;
+  pl->dev.qtiles = (p.T + 127) / 128;
+  pl->dev.num_items = pl->dev.qtiles * p.heads * p.B;
+  pl->dev.scale_log2e = p.scale * 1.4426950408889634f;
+  pl->nb = (p.T + 127) / 128;
+  pl->grid = pl->dev.num_items < num_sms ? pl->dev.num_items : num_sms;
+  const uint64_t ld = (uint64_t)p.ld;
+  uint64_t dims[4] = {64, (uint64_t)p.T, (uint64_t)p.heads, (uint64_t)p.B};
+  uint64_t str[3] = {ld * 2, 128, (uint64_t)p.T * ld * 2};
+  uint32_t box[4] = {64, 128, 1, 1};
+  std::string err = make_tensor_map_bf16(&pl->mapQ, p.qkv + p.q_off, 4, dims, str, box);
+  if (err.empty()) err = make_tensor_map_bf16(&pl->mapK, p.qkv + p.k_off, 4, dims, str, box);
+  if (err.empty()) err = make_tensor_map_bf16(&pl->mapV, p.qkv + p.v_off, 4, dims, str, box);
+  if (!err.empty()) {
+    delete pl;
+    return err;
+  }
+  *out = pl;
+  return "";
+}
+
+std::string attention_fa_launch(const AttnFaPlan* pl, cudaStream_t s) {
+  switch (pl->nb) {
+    case 1: attention_fa_kernel<1><<<pl->grid, 384, FA_SMEM, s>>>(pl->mapQ, pl->mapK, pl->mapV, pl->dev); break;
+    case 2: attention_fa_kernel<2><<<pl->grid, 384, FA_SMEM, s>>>(pl->mapQ, pl->mapK, pl->mapV, pl->dev); break;
+    case 3: attention_fa_kernel<3><<<pl->grid, 384, FA_SMEM, s>>>(pl->mapQ, pl->mapK, pl->mapV, pl->dev); break;
+    case 4: attention_fa_kernel<4><<<pl->grid, 384, FA_SMEM, s>>>(pl->mapQ, pl->mapK, pl->mapV, pl->dev); break;
+    default: return "attention (tcgen05, pipelined): more than 4 key blocks";
+  }
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+void attention_fa_free(AttnFaPlan* pl) { delete pl; }
+
+}  // namespace w2s

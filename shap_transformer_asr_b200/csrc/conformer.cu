@@ -28,7 +28,7 @@ std::string launch_bn_fold(const float* g, const float* b, const float* mean, co
 // each input row is loaded once (128 B per warp, coalesced) and scattered into the <= 16 accumulators it touches;
 // all tap indices are compile-time after unrolling, so filters and accumulators stay in registers.
 template <int K>
-__global__ void __launch_bounds__(256) depthwise_kernel(const __nv_bfloat16* __restrict__ in, int T, int H,
+__global__ void __launch_bounds__(256, 2) depthwise_kernel(const __nv_bfloat16* __restrict__ in, int T, int H,
                                                          const float* __restrict__ w, const float* __restrict__ scale,
                                                          const float* __restrict__ shift, int act,
                                                          __nv_bfloat16* __restrict__ out) {
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) depthwise_kernel(const __nv_bfloat16* __r
   const uint32_t* xw = reinterpret_cast<const uint32_t*>(xs) + warp * TT * 32 + lane;
   float2 wr[K];
 #pragma unroll
-  for (int j = 0; j < K; ++j) wr[j] = make_float2(__ldg(w + (long long)c * K + j), __ldg(w + (long long)(c + 1) * K + j));
+  for (int j = 0; j < K; ++j) wr[j] = __ldg(reinterpret_cast<const float2*>(w + (long long)j * H + c));   // taps stored [K][H]
   float2 acc[TT];
 #pragma unroll
   for (int t = 0; t < TT; ++t) acc[t] = make_float2(0.f, 0.f);
@@ -101,6 +101,20 @@ std::string launch_depthwise(const __nv_bfloat16* in, int B, int T, int H, int k
     case 3: depthwise_kernel<3><<<grid, 256, 0, s>>>(in, T, H, w, scale, shift, act, out); break;
     default: return "depthwise conv: kernel size " + std::to_string(k) + " not instantiated (31, 15, 7, 3)";
   }
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+__global__ void transpose_f32_kernel(const float* src, float* dst, int R, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < R * C) {
+    const int r = i / C, cc = i - r * C;
+    dst[(long long)cc * R + r] = src[i];
+  }
+}
+// dst[C][R] = src[R][C]^T (one-off weight re-layout)
+std::string launch_transpose_f32(const float* src, float* dst, int R, int C, cudaStream_t s) {
+  transpose_f32_kernel<<<(R * C + 255) / 256, 256, 0, s>>>(src, dst, R, C);
   W2S_CUDA_OK(cudaGetLastError());
   return "";
 }

@@ -71,6 +71,13 @@ std::string attention_tc_prepare(const AttnParams& p, AttnTcPlan** plan);
 std::string attention_tc_launch(const AttnTcPlan* plan, cudaStream_t s);
 void attention_tc_free(AttnTcPlan* plan);
 bool attention_tc_supported(const AttnParams& p);
+// persistent, warp-specialised variant with independent key blocks (attention_fa.cu); preferred when supported
+struct AttnFaPlan;
+std::string attention_fa_init();
+bool attention_fa_supported(const AttnParams& p);
+std::string attention_fa_prepare(const AttnParams& p, int num_sms, AttnFaPlan** plan);
+std::string attention_fa_launch(const AttnFaPlan* plan, cudaStream_t s);
+void attention_fa_free(AttnFaPlan* plan);
 // conformer relative-position attention on tcgen05 (T' <= 256)
 struct AttnRelPlan;
 std::string attention_rel_init();
@@ -82,8 +89,10 @@ void attention_rel_free(AttnRelPlan* plan);
 // ---- conformer-only CUDA-core kernels (conformer.cu) ---------------------------------------------------------
 std::string launch_bn_fold(const float* g, const float* b, const float* mean, const float* var, int n, float eps,
                            float* scale, float* shift, cudaStream_t s);
+// w: depthwise taps stored [k][H] (transposed from the HF [H][1][k] layout)
 std::string launch_depthwise(const __nv_bfloat16* in, int B, int T, int H, int k, const float* w, const float* scale,
                              const float* shift, int act, __nv_bfloat16* out, cudaStream_t s);
+std::string launch_transpose_f32(const float* src, float* dst, int R, int C, cudaStream_t s);
 std::string launch_rotary(const __nv_bfloat16* x, long long rows, int T, int H, int hd, int base, __nv_bfloat16* out,
                           cudaStream_t s);
 std::string launch_relpos(int T, int H, __nv_bfloat16* out, cudaStream_t s);
