@@ -135,7 +135,10 @@ class KernelShapExplainer:
     def explain(self, clip, num_segments: int, mode: str = "logprob", targets=None, baseline: float = 0.0):
         eng = self.engine
         eng.set_clip(clip, num_segments=num_segments, baseline=baseline)
-        if targets is None:
+        if mode in ("max", "mean", "logits"):
+            frames, tokens = (), ()
+            eng.set_targets(mode)
+        elif targets is None:
             frames, tokens, _ = self.select_targets(mode)
         else:
             frames, tokens = targets

