@@ -1006,7 +1006,8 @@ int64_t w2s_out_width(const w2s_handle* h, int64_t num_samples) { return out_wid
 
 int w2s_eval(w2s_handle* h, const uint32_t* z_bits_dev, int64_t K, float* out_dev, void* stream) {
   if (h->L <= 0) return fail(h, "eval: no clip set (w2s_set_clip)");
-  if (!z_bits_dev || !out_dev) return fail(h, "eval: null buffer");
+  if (K == 0) return 0;   // empty coalition matrix: nothing to evaluate
+  if (K < 0 || !z_bits_dev || !out_dev) return fail(h, "eval: null buffer");
   if ((h->mode == W2S_OUT_LOGIT || h->mode == W2S_OUT_LOGPROB) && h->max_frame >= h->T)
     return fail(h, "eval: target frame beyond the clip's " + std::to_string(h->T) + " frames");
   std::string e = ensure_workspace(h, h->L);
@@ -1016,7 +1017,8 @@ int w2s_eval(w2s_handle* h, const uint32_t* z_bits_dev, int64_t K, float* out_de
 
 int w2s_eval_waveforms(w2s_handle* h, const float* x_dev, int64_t n, int64_t L, int64_t ld, float* out_dev,
                        void* stream) {
-  if (!x_dev || !out_dev) return fail(h, "eval_waveforms: null buffer");
+  if (n == 0) return 0;
+  if (n < 0 || !x_dev || !out_dev) return fail(h, "eval_waveforms: null buffer");
   if (ld < L) return fail(h, "eval_waveforms: row stride smaller than the row length");
   std::string e = ensure_workspace(h, L);
   if (e.empty() && (h->mode == W2S_OUT_LOGIT || h->mode == W2S_OUT_LOGPROB) && h->max_frame >= h->T)
