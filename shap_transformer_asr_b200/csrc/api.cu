@@ -27,7 +27,7 @@ struct LayerW {
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
   // conformer extras
   bf16 *f2w1 = nullptr, *f2w2 = nullptr, *wpos = nullptr, *pw1 = nullptr, *pw2 = nullptr;
-  float *f2b1 = nullptr, *f2b2 = nullptr, *bias_u = nullptr, *bias_v = nullptr;
+  float *f2b1 = nullptr, *f2b2 = nullptr;
   float *lnf1_g = nullptr, *lnf1_b = nullptr, *lnf2_g = nullptr, *lnf2_b = nullptr;
   float *lnc_g = nullptr, *lnc_b = nullptr, *lnfin_g = nullptr, *lnfin_b = nullptr;
   float *dw_w = nullptr, *dw_scale = nullptr, *dw_shift = nullptr;  // depthwise taps [H][k], folded BatchNorm

@@ -1,13 +1,12 @@
 // Self-attention of the encoder (HF wav2vec2/modeling_wav2vec2.py:438-463, :500-549; conformer relative
 // positions wav2vec2_conformer/modeling_wav2vec2_conformer.py:509-565).
 //
-//  * attention_tc_kernel  : tcgen05 path.  One CTA per (128-query tile, head, coalition).  Q, K and V^T tiles
-//                           arrive by TMA (128B swizzle); S = Q K^T accumulates in TMEM (up to 512 fp32
-//                           columns = the whole key range, T' <= 512); the four warps run the softmax out of
-//                           TMEM (thread = query row), write P as bf16 into swizzled shared memory and a
-//                           second tcgen05.mma chain forms O = P V in TMEM.
+//  * attention_fa.cu       : the default tcgen05 kernel (persistent, warp-specialised, independent key blocks).
+//  * attention_tc_kernel  : first-generation tcgen05 kernel, one CTA per (128-query tile, head, coalition) with the
+//                           whole score row block in TMEM; kept selectable (W2S_ATTN_V1=1) as a cross-check.
+//  * attention_rel_kernel : conformer relative-position attention on tcgen05 (T' <= 256).
 //  * attention_simt_kernel: CUDA-core validation kernel (one warp per query row), also carries the
-//                           conformer relative-position term.
+//                           conformer relative-position term for longer clips.
 #include "kernels.cuh"
 #include "gemm.cuh"
 
@@ -461,6 +460,8 @@ attention_rel_kernel(const __grid_constant__ CUtensorMap mapQU, const __grid_con
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&s_tmem);
   const uint32_t trow = tmem + (static_cast<uint32_t>(qd * 32) << 16);
+  pdl_trigger();
+  pdl_wait();
 
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar_q, 32768);
@@ -640,7 +641,7 @@ std::string attention_rel_prepare(const AttnParams& p, AttnRelPlan** out) {
   return "";
 }
 std::string attention_rel_launch(const AttnRelPlan* pl, cudaStream_t s) {
-  attention_rel_kernel<<<pl->grid, 256, REL_SMEM, s>>>(pl->mapQU, pl->mapQV, pl->mapK, pl->mapV, pl->mapP, pl->dev);
+  W2S_CUDA_OK(launch_pdl(attention_rel_kernel, pl->grid, dim3(256), REL_SMEM, s, 1, pl->mapQU, pl->mapQV, pl->mapK, pl->mapV, pl->mapP, pl->dev));
   W2S_CUDA_OK(cudaGetLastError());
   return "";
 }

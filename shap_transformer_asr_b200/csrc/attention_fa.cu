@@ -86,6 +86,8 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
   // TMEM columns: S buffers at 0 / 128, O_j at 256 + 64 j
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 8) {
     if (lane == 0) {
@@ -316,10 +318,10 @@ std::string attention_fa_prepare(const AttnParams& p, int num_sms, AttnFaPlan** 
 
 std::string attention_fa_launch(const AttnFaPlan* pl, cudaStream_t s) {
   switch (pl->nb) {
-    case 1: attention_fa_kernel<1><<<pl->grid, 384, FA_SMEM, s>>>(pl->mapQ, pl->mapK, pl->mapV, pl->dev); break;
-    case 2: attention_fa_kernel<2><<<pl->grid, 384, FA_SMEM, s>>>(pl->mapQ, pl->mapK, pl->mapV, pl->dev); break;
-    case 3: attention_fa_kernel<3><<<pl->grid, 384, FA_SMEM, s>>>(pl->mapQ, pl->mapK, pl->mapV, pl->dev); break;
-    case 4: attention_fa_kernel<4><<<pl->grid, 384, FA_SMEM, s>>>(pl->mapQ, pl->mapK, pl->mapV, pl->dev); break;
+    case 1: W2S_CUDA_OK(launch_pdl(attention_fa_kernel<1>, dim3(pl->grid), dim3(384), FA_SMEM, s, 1, pl->mapQ, pl->mapK, pl->mapV, pl->dev)); break;
+    case 2: W2S_CUDA_OK(launch_pdl(attention_fa_kernel<2>, dim3(pl->grid), dim3(384), FA_SMEM, s, 1, pl->mapQ, pl->mapK, pl->mapV, pl->dev)); break;
+    case 3: W2S_CUDA_OK(launch_pdl(attention_fa_kernel<3>, dim3(pl->grid), dim3(384), FA_SMEM, s, 1, pl->mapQ, pl->mapK, pl->mapV, pl->dev)); break;
+    case 4: W2S_CUDA_OK(launch_pdl(attention_fa_kernel<4>, dim3(pl->grid), dim3(384), FA_SMEM, s, 1, pl->mapQ, pl->mapK, pl->mapV, pl->dev)); break;
     default: return "attention (tcgen05, pipelined): more than 4 key blocks";
   }
   W2S_CUDA_OK(cudaGetLastError());

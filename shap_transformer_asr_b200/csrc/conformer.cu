@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(256, 2) depthwise_kernel(const __nv_bfloat16* 
                                                          __nv_bfloat16* __restrict__ out) {
   constexpr int TT = 16, PAD = (K - 1) / 2, ROWS = 8 * TT + K - 1;
   __shared__ uint4 xs[ROWS * 8];   // [ROWS][64 channels] bf16, staged by the whole CTA with 16-byte loads
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z;
   const int c_blk = blockIdx.y * 64;
@@ -95,10 +97,10 @@ std::string launch_depthwise(const __nv_bfloat16* in, int B, int T, int H, int k
   if (B == 0) return "";
   dim3 grid((T + 127) / 128, (H + 63) / 64, B);
   switch (k) {
-    case 31: depthwise_kernel<31><<<grid, 256, 0, s>>>(in, T, H, w, scale, shift, act, out); break;
-    case 15: depthwise_kernel<15><<<grid, 256, 0, s>>>(in, T, H, w, scale, shift, act, out); break;
-    case 7: depthwise_kernel<7><<<grid, 256, 0, s>>>(in, T, H, w, scale, shift, act, out); break;
-    case 3: depthwise_kernel<3><<<grid, 256, 0, s>>>(in, T, H, w, scale, shift, act, out); break;
+    case 31: W2S_CUDA_OK(launch_pdl(depthwise_kernel<31>, grid, dim3(256), 0, s, 1, in, T, H, w, scale, shift, act, out)); break;
+    case 15: W2S_CUDA_OK(launch_pdl(depthwise_kernel<15>, grid, dim3(256), 0, s, 1, in, T, H, w, scale, shift, act, out)); break;
+    case 7: W2S_CUDA_OK(launch_pdl(depthwise_kernel<7>, grid, dim3(256), 0, s, 1, in, T, H, w, scale, shift, act, out)); break;
+    case 3: W2S_CUDA_OK(launch_pdl(depthwise_kernel<3>, grid, dim3(256), 0, s, 1, in, T, H, w, scale, shift, act, out)); break;
     default: return "depthwise conv: kernel size " + std::to_string(k) + " not instantiated (31, 15, 7, 3)";
   }
   W2S_CUDA_OK(cudaGetLastError());

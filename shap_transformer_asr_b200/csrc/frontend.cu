@@ -12,6 +12,8 @@ __global__ void __launch_bounds__(256) mask_kernel(const float* __restrict__ x, 
                                                     const uint32_t* __restrict__ zbits, int zwords, long long L,
                                                     float baseline, float* __restrict__ out, long long ld) {
   __shared__ uint32_t z[64];
+  pdl_trigger();
+  pdl_wait();
   const long long k = blockIdx.y;
   if (threadIdx.x < zwords) z[threadIdx.x] = zbits[k * zwords + threadIdx.x];
   __syncthreads();
@@ -40,7 +42,7 @@ std::string launch_mask(const float* x, const uint16_t* seg_id, const uint32_t* 
   if (zwords > 64) return "mask: more than 2048 segments are not supported";
   if (K == 0) return "";
   dim3 grid((unsigned)((L + 1023) / 1024), (unsigned)K);
-  mask_kernel<<<grid, 256, 0, s>>>(x, seg_id, zbits, zwords, L, baseline, out, ld);
+  W2S_CUDA_OK(launch_pdl(mask_kernel, grid, dim3(256), 0, s, 1, x, seg_id, zbits, zwords, L, baseline, out, ld));
   W2S_CUDA_OK(cudaGetLastError());
   return "";
 }
@@ -59,6 +61,8 @@ __global__ void __launch_bounds__(256) conv0_stats_kernel(const Conv0Params p) {
   constexpr int NACC = KW + NR;
   __shared__ double red[8][NACC];
   __shared__ double tot[NACC];
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x;
   const float* x = p.x + (long long)row * p.ld;
   float acc[NACC];
@@ -122,7 +126,7 @@ __global__ void __launch_bounds__(256) conv0_stats_kernel(const Conv0Params p) {
 std::string launch_conv0_stats(const Conv0Params& p, cudaStream_t s) {
   if (p.kw != 10) return "conv0: only kernel width 10 is implemented for layer 0";
   if (p.n == 0) return "";
-  conv0_stats_kernel<10><<<p.n, 256, 0, s>>>(p);
+  W2S_CUDA_OK(launch_pdl(conv0_stats_kernel<10>, dim3(p.n), dim3(256), 0, s, 1, p));
   W2S_CUDA_OK(cudaGetLastError());
   return "";
 }
@@ -141,6 +145,8 @@ __global__ void __launch_bounds__(256, 2) conv0_kernel(const Conv0Params p, int 
   float* fmean = xs + FT * p.stride + KW;  // [FT] (layer variant)
   float* frstd = fmean + FT;
   float2* xs2 = reinterpret_cast<float2*>(frstd + FT + ((FT * p.stride + KW) & 1));  // (x, x) pairs, 8-byte aligned
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.y;
   const int f0 = blockIdx.x * FT;
   const int nf = min(FT, p.T0 - f0);
@@ -230,8 +236,8 @@ std::string launch_conv0(const Conv0Params& p, bool layer_norm, cudaStream_t s) 
   const int FT = p.T0 >= 4096 ? 512 : 128;
   dim3 grid((p.T0 + FT - 1) / FT, p.n);
   const size_t smem = (size_t)(3 * (FT * p.stride + p.kw) + 2 * FT + 2) * sizeof(float);
-  if (layer_norm) conv0_kernel<10, true><<<grid, 256, smem, s>>>(p, FT);
-  else conv0_kernel<10, false><<<grid, 256, smem, s>>>(p, FT);
+  if (layer_norm) W2S_CUDA_OK(launch_pdl(conv0_kernel<10, true>, grid, dim3(256), smem, s, 1, p, FT));
+  else W2S_CUDA_OK(launch_pdl(conv0_kernel<10, false>, grid, dim3(256), smem, s, 1, p, FT));
   W2S_CUDA_OK(cudaGetLastError());
   return "";
 }
@@ -330,6 +336,8 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const void* __restri
                                                              __nv_bfloat16* __restrict__ out,
                                                              float* __restrict__ out_f32) {
   constexpr int H = 128 * NV;
+  pdl_trigger();
+  pdl_wait();
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -391,11 +399,11 @@ static bool launch_ln_vec(const void* in, const __nv_bfloat16* residual, long lo
                           const float* beta, float eps, int act, __nv_bfloat16* out, float* out_f32, cudaStream_t s) {
   const unsigned grid = (unsigned)((rows + 7) / 8);
   switch (H) {
-    case 128: layernorm_vec_kernel<IN_F32, 1><<<grid, 256, 0, s>>>(in, residual, rows, gamma, beta, eps, act, out, out_f32); return true;
-    case 256: layernorm_vec_kernel<IN_F32, 2><<<grid, 256, 0, s>>>(in, residual, rows, gamma, beta, eps, act, out, out_f32); return true;
-    case 512: layernorm_vec_kernel<IN_F32, 4><<<grid, 256, 0, s>>>(in, residual, rows, gamma, beta, eps, act, out, out_f32); return true;
-    case 768: layernorm_vec_kernel<IN_F32, 6><<<grid, 256, 0, s>>>(in, residual, rows, gamma, beta, eps, act, out, out_f32); return true;
-    case 1024: layernorm_vec_kernel<IN_F32, 8><<<grid, 256, 0, s>>>(in, residual, rows, gamma, beta, eps, act, out, out_f32); return true;
+    case 128: launch_pdl(layernorm_vec_kernel<IN_F32, 1>, dim3(grid), dim3(256), 0, s, 1, in, residual, rows, gamma, beta, eps, act, out, out_f32); return true;
+    case 256: launch_pdl(layernorm_vec_kernel<IN_F32, 2>, dim3(grid), dim3(256), 0, s, 1, in, residual, rows, gamma, beta, eps, act, out, out_f32); return true;
+    case 512: launch_pdl(layernorm_vec_kernel<IN_F32, 4>, dim3(grid), dim3(256), 0, s, 1, in, residual, rows, gamma, beta, eps, act, out, out_f32); return true;
+    case 768: launch_pdl(layernorm_vec_kernel<IN_F32, 6>, dim3(grid), dim3(256), 0, s, 1, in, residual, rows, gamma, beta, eps, act, out, out_f32); return true;
+    case 1024: launch_pdl(layernorm_vec_kernel<IN_F32, 8>, dim3(grid), dim3(256), 0, s, 1, in, residual, rows, gamma, beta, eps, act, out, out_f32); return true;
     default: return false;
   }
 }
@@ -424,6 +432,8 @@ std::string launch_layernorm(const void* in, int in_fp32, long long rows, int H,
 __global__ void __launch_bounds__(256) pos_pad_kernel(const __nv_bfloat16* __restrict__ h, int T, int H, int G,
                                                        int kpos, __nv_bfloat16* __restrict__ out) {
   // one thread = 8 consecutive channels (16 bytes) of one padded row
+  pdl_trigger();
+  pdl_wait();
   const int cpg = H / G;
   const int Tp = T + kpos;
   const int W8 = G * 8;
@@ -455,7 +465,7 @@ std::string launch_pos_pad(const __nv_bfloat16* h, int B, int T, int H, int G, i
   if (B == 0) return "";
   const long long per = (long long)(T + kpos) * G * 8;
   dim3 grid((unsigned)((per + 255) / 256 > 1024 ? 1024 : (per + 255) / 256), B);
-  pos_pad_kernel<<<grid, 256, 0, s>>>(h, T, H, G, kpos, out);
+  W2S_CUDA_OK(launch_pdl(pos_pad_kernel, grid, dim3(256), 0, s, 1, h, T, H, G, kpos, out));
   W2S_CUDA_OK(cudaGetLastError());
   return "";
 }

@@ -102,6 +102,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if constexpr (MC) cluster_sync_all();   // barrier inits visible to the peer before any multicast traffic
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 8) {
     if (lane == 0) {
@@ -382,7 +384,7 @@ std::string gemm_prepare(const GemmProblem& p, int num_sms, GemmLaunch* out) {
   // pair kernel: TMA-store epilogue (not for the GLU epilogue, whose output width differs from the tile width)
   out->tma_out = 0;
   static const bool tma_out_enabled = getenv("W2S_NO_TMA_STORE") == nullptr;
-  if (out->mc == 2 && tma_out_enabled && !p.epi.glu && p.epi.vt == nullptr) {
+  if (out->mc == 2 && tma_out_enabled && !p.epi.glu) {
     const uint64_t es = p.epi.out_fp32 ? 4 : 2;
     const uint64_t ldb = p.Bz > 1 ? (uint64_t)p.epi.ldb : (uint64_t)p.epi.ldm * p.M;
     const uint64_t ldg = p.G > 1 ? (uint64_t)p.epi.ldg : ldb * p.Bz;
@@ -399,19 +401,7 @@ std::string gemm_prepare(const GemmProblem& p, int num_sms, GemmLaunch* out) {
 
 template <int BN>
 static cudaError_t launch_mc(const GemmLaunch& l, cudaStream_t s) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(l.grid);
-  cfg.blockDim = dim3(384);
-  cfg.dynamicSmemBytes = l.smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, true>, l.mapA, l.mapW, l.dev);
+  return launch_pdl(gemm_tc_kernel<BN, true>, dim3(l.grid), dim3(384), l.smem, s, 2, l.mapA, l.mapW, l.dev);
 }
 
 std::string gemm_launch_tc(const GemmLaunch& l, cudaStream_t s) {
@@ -423,11 +413,11 @@ std::string gemm_launch_tc(const GemmLaunch& l, cudaStream_t s) {
     return "";
   }
   switch (l.bn) {
-    case 256: gemm_tc_kernel<256, false><<<l.grid, 384, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
-    case 128: gemm_tc_kernel<128, false><<<l.grid, 384, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
-    case 64: gemm_tc_kernel<64, false><<<l.grid, 384, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
-    case 48: gemm_tc_kernel<48, false><<<l.grid, 384, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
-    case 32: gemm_tc_kernel<32, false><<<l.grid, 384, l.smem, s>>>(l.mapA, l.mapW, l.dev); break;
+    case 256: W2S_CUDA_OK(launch_pdl(gemm_tc_kernel<256, false>, dim3(l.grid), dim3(384), l.smem, s, 1, l.mapA, l.mapW, l.dev)); break;
+    case 128: W2S_CUDA_OK(launch_pdl(gemm_tc_kernel<128, false>, dim3(l.grid), dim3(384), l.smem, s, 1, l.mapA, l.mapW, l.dev)); break;
+    case 64: W2S_CUDA_OK(launch_pdl(gemm_tc_kernel<64, false>, dim3(l.grid), dim3(384), l.smem, s, 1, l.mapA, l.mapW, l.dev)); break;
+    case 48: W2S_CUDA_OK(launch_pdl(gemm_tc_kernel<48, false>, dim3(l.grid), dim3(384), l.smem, s, 1, l.mapA, l.mapW, l.dev)); break;
+    case 32: W2S_CUDA_OK(launch_pdl(gemm_tc_kernel<32, false>, dim3(l.grid), dim3(384), l.smem, s, 1, l.mapA, l.mapW, l.dev)); break;
     default: return "gemm: bad BN";
   }
   W2S_CUDA_OK(cudaGetLastError());

@@ -18,9 +18,6 @@ struct EpiParams {
   void* out = nullptr;
   int out_fp32 = 0;
   long long ldg = 0, ldb = 0, ldm = 0;  // element strides of (group, batch, row); columns contiguous
-  // optional side output: columns >= vt_n0 are also written transposed as V^T[b, head, d, t] (row m = b*T + t)
-  __nv_bfloat16* vt = nullptr;
-  int vt_n0 = 0, vt_T = 1, vt_Tp = 1, vt_heads = 1, vt_hd = 64;
 };
 
 // C[g, b] (M x N) = A[g, b] (M x K) * W[g]^T (N x K).

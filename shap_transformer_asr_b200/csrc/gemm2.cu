@@ -76,6 +76,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_trigger();   // every CTA holds its smem/TMEM now: the next kernel may stage its prologue behind our tail
+  pdl_wait();      // operands and residuals of this kernel come from its predecessors
 
   if (warp == 8) {
     if (lane == 0) {
@@ -248,19 +250,8 @@ size_t gemm2_smem(int bn) { return bn == 256 ? Tc2Cfg<256>::SMEM : Tc2Cfg<128>::
 
 template <int BN>
 static cudaError_t launch2(const GemmLaunch& l, cudaStream_t s) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(l.grid);
-  cfg.blockDim = dim3(384);
-  cfg.dynamicSmemBytes = Tc2Cfg<BN>::SMEM;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<BN>, l.mapA, l.mapW, l.tma_out ? l.mapOut : l.mapA, l.dev, l.tma_out);
+  return launch_pdl(gemm_tc2_kernel<BN>, dim3(l.grid), dim3(384), Tc2Cfg<BN>::SMEM, s, 2, l.mapA, l.mapW,
+                    l.tma_out ? l.mapOut : l.mapA, l.dev, l.tma_out);
 }
 
 std::string gemm2_launch(const GemmLaunch& l, cudaStream_t s) {

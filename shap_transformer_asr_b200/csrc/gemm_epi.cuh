@@ -108,18 +108,6 @@ __device__ __forceinline__ void epi_store(const EpiParams& e, int N, int g, int 
       }
     }
   }
-  if (e.vt && !e.glu) {
-    const int bb = m / e.vt_T, t = m - bb * e.vt_T;
-#pragma unroll
-    for (int j = 0; j < CH; ++j) {
-      const int n = ncol0 + j;
-      if (n >= e.vt_n0 && n < N) {
-        const int nn = n - e.vt_n0;
-        const int hh = nn / e.vt_hd, d = nn - hh * e.vt_hd;
-        e.vt[((long long)(bb * e.vt_heads + hh) * e.vt_hd + d) * e.vt_Tp + t] = __float2bfloat16_rn(v[j]);
-      }
-    }
-  }
 }
 
 

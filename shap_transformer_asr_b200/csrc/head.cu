@@ -97,6 +97,8 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p, long long
 // second stage of the tensor-core head: logits[rows, V] (fp32, bias included) -> reduction; one warp per work item
 __global__ void __launch_bounds__(256) head_reduce_kernel(const float* __restrict__ logits, const HeadParams p,
                                                            long long items) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool targeted = (p.mode == W2S_OUT_LOGIT || p.mode == W2S_OUT_LOGPROB);
   const int per = targeted ? p.D : p.T;
@@ -152,7 +154,7 @@ std::string launch_head_reduce(const float* logits, const HeadParams& p, cudaStr
   if (p.mode == W2S_OUT_MEAN) W2S_CUDA_OK(cudaMemsetAsync(p.out, 0, sizeof(float) * p.n, s));
   long long blocks = (items + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  head_reduce_kernel<<<(unsigned)blocks, 256, 0, s>>>(logits, p, items);
+  W2S_CUDA_OK(launch_pdl(head_reduce_kernel, dim3((unsigned)blocks), dim3(256), 0, s, 1, logits, p, items));
   W2S_CUDA_OK(cudaGetLastError());
   return "";
 }

@@ -74,6 +74,8 @@ posconv_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 8) {
     if (lane == 0) {
@@ -223,9 +225,9 @@ std::string posconv_prepare(const __nv_bfloat16* x, const __nv_bfloat16* w, int 
 
 std::string posconv_launch(const PosConvPlan* pl, cudaStream_t s) {
   switch (pl->ng) {
-    case 32: posconv_kernel<32><<<pl->grid, 384, PcCfg<32>::SMEM, s>>>(pl->mapX, pl->mapW, pl->dev); break;
-    case 48: posconv_kernel<48><<<pl->grid, 384, PcCfg<48>::SMEM, s>>>(pl->mapX, pl->mapW, pl->dev); break;
-    case 64: posconv_kernel<64><<<pl->grid, 384, PcCfg<64>::SMEM, s>>>(pl->mapX, pl->mapW, pl->dev); break;
+    case 32: W2S_CUDA_OK(launch_pdl(posconv_kernel<32>, dim3(pl->grid), dim3(384), PcCfg<32>::SMEM, s, 1, pl->mapX, pl->mapW, pl->dev)); break;
+    case 48: W2S_CUDA_OK(launch_pdl(posconv_kernel<48>, dim3(pl->grid), dim3(384), PcCfg<48>::SMEM, s, 1, pl->mapX, pl->mapW, pl->dev)); break;
+    case 64: W2S_CUDA_OK(launch_pdl(posconv_kernel<64>, dim3(pl->grid), dim3(384), PcCfg<64>::SMEM, s, 1, pl->mapX, pl->mapW, pl->dev)); break;
     default: return "positional conv kernel: bad group width";
   }
   W2S_CUDA_OK(cudaGetLastError());
