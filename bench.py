@@ -192,14 +192,8 @@ def run_b200(args):
         Z, kw = Z[:args.coalitions], kw[:args.coalitions]
     model = make_hf_model(cfg)
     # batch tile: rows = B * T' should fill whole waves of 128-row tiles on 148 SMs (B = floor(148*128*k / T'))
-    T = cfg.num_frames(wl.num_samples)
-    batch = args.batch
-    if batch <= 0:
-        k = 1
-        while (148 * 128 * k) // T < 128:
-            k += 1
-        batch = min(wl.num_coalitions, (148 * 128 * k) // T)
-    eng = Engine(model, cfg, device=local, max_batch=batch)
+    # (the library picks B = floor(148*128*k / T') with B >= 128 itself when max_batch is 0)
+    eng = Engine(model, cfg, device=local, max_batch=max(0, args.batch))
     eng.set_clip(clip, num_segments=wl.num_segments)
     # targets: per-character frames of the unmasked clip (all frames if the random-init transcript is empty)
     eng.set_targets("logits")

@@ -70,6 +70,7 @@ struct w2s_handle {
   w2s_config cfg{};
   int device = 0;
   int num_sms = 148;
+  bool auto_batch = false;   // max_batch == 0 at create: pick the batch tile per clip length
   std::string err;
   std::vector<void*> allocs;      // weights: live until destroy
   std::vector<void*> ws_allocs;   // workspace: re-made when the clip length changes
@@ -388,6 +389,16 @@ std::string ensure_workspace(w2s_handle* h, long long L) {
   if (T <= 0) return "clip of " + std::to_string(L) + " samples is shorter than the conv receptive field";
   h->T = (int)T;
   h->Tp = (int)((T + 63) / 64 * 64);
+  if (h->auto_batch) {
+    // rows = tile * T' should fill whole waves of 128-row tiles on all SMs (tile = floor(SMs * 128 * k / T')), with at
+    // least 128 coalitions per tile to amortise per-launch prologues, and the conv0 output (the largest buffer) <= 8 GB
+    long long k = 1;
+    while ((long long)h->num_sms * 128 * k / T < 128) ++k;
+    long long tile = (long long)h->num_sms * 128 * k / T;
+    const long long conv0_bytes = (long long)h->Tl[0] * c.conv_dim[0] * 2;
+    while (tile > 8 && tile * conv0_bytes > (8LL << 30)) tile /= 2;
+    h->cfg.max_batch = (int)tile;
+  }
   const size_t nb = (size_t)c.max_batch;
   const int H = c.hidden_size, I = c.intermediate_size;
   const int Cl = c.conv_dim[c.num_conv_layers - 1];
@@ -904,7 +915,8 @@ int w2s_create(const w2s_config* cfg, const char* const* names, const float* con
   h->cfg = *cfg;
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
-  if (h->cfg.max_batch <= 0) h->cfg.max_batch = 64;
+  h->auto_batch = h->cfg.max_batch <= 0;
+  if (h->auto_batch) h->cfg.max_batch = 64;
   if (cfg->num_conv_layers < 1 || cfg->num_conv_layers > W2S_MAX_CONV_LAYERS) {
     g_create_error = "num_conv_layers out of range";
     return 1;
