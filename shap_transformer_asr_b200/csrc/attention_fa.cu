@@ -114,8 +114,12 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64) | (1u << 16);   // B operand (V) is MN-major
       uint32_t kvc = 0, sc = 0, pc = 0;
       int it = 0;
-      auto issue_pv = [&](int jj, int stage) {
+      auto issue_pv = [&](int jj, int stage, int it_) {
         const int pb = pc & 1;
+        // the O accumulators are overwritten from the first P V of an item on: only then must the previous item's merge
+        // have drained them (waiting here instead of before the score MMAs lets S_0 / S_1 of the next item be computed
+        // while the softmax warps still finish the previous one)
+        if (jj == 0) mbar_wait(o_empty, (uint32_t)(it_ & 1) ^ 1u);
         mbar_wait(p_full(pb), (pc >> 1) & 1u);
         tc_fence_after();
 #pragma unroll
@@ -130,10 +134,12 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         umma_commit(kv_empty(stage));
         ++pc;
       };
+      // Blocks form ONE stream across items: S_g is issued, then P V of block g-1 -- also across an item boundary, so the
+      // first score block of the next item is already in TMEM when the softmax warps finish the previous item.
+      bool pending = false;
+      int pend_j = 0, pend_stage = 0, pend_it = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
         mbar_wait(q_full, (uint32_t)(it & 1));
-        mbar_wait(o_empty, (uint32_t)(it & 1) ^ 1u);
-        int prev_stage = 0;
 #pragma unroll 1
         for (int j = 0; j < NB; ++j, ++kvc, ++sc) {
           const int s = kvc % FA_KVS, sb = sc & 1;
@@ -146,10 +152,18 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
           for (int k = 0; k < 4; ++k) umma_bf16(tmem + sb * 128, dq + 2u * k, dk + 2u * k, idesc_qk, k != 0 ? 1u : 0u);
           umma_commit(s_full(sb));
           if (j == NB - 1) umma_commit(q_empty);
-          if (j > 0) issue_pv(j - 1, prev_stage);
-          prev_stage = s;
+          if (pending) {
+            issue_pv(pend_j, pend_stage, pend_it);
+            if (pend_j == NB - 1) umma_commit(o_full);
+          }
+          pending = true;
+          pend_j = j;
+          pend_stage = s;
+          pend_it = it;
         }
-        issue_pv(NB - 1, prev_stage);
+      }
+      if (pending) {
+        issue_pv(pend_j, pend_stage, pend_it);
         umma_commit(o_full);
       }
     }
@@ -199,13 +213,13 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         }
         float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
         s_m[(sb * 2 + hf) * 128 + row] = mx;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");   // only the partner warp (same lane quadrant) shares these rows
         mx = fmaxf(s_m[(sb * 2 + 0) * 128 + row], s_m[(sb * 2 + 1) * 128 + row]);
         m_j[j] = mx;
         const float2 sc2 = make_float2(p.scale_log2e, p.scale_log2e);
         const float2 nm2 = make_float2(-mx * p.scale_log2e, -mx * p.scale_log2e);
         mbar_wait(p_empty(pb), ((pc >> 1) & 1u) ^ 1u);   // P V of two blocks ago has drained this P buffer
-        float2 acc2 = make_float2(0.f, 0.f);
+        float2 acc4[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
         const uint32_t sp_row = base + FA_SP + pb * 32768 + hf * 16384 + row * 128;
 #pragma unroll
         for (int c8 = 0; c8 < 8; ++c8) {
@@ -214,11 +228,12 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
           for (int t = 0; t < 4; ++t) {
             const float2 a = __ffma2_rn(make_float2(sv[c8 * 8 + 2 * t], sv[c8 * 8 + 2 * t + 1]), sc2, nm2);
             e[t] = make_float2(ex2_approx(a.x), ex2_approx(a.y));
-            acc2 = __fadd2_rn(acc2, e[t]);
+            acc4[t] = __fadd2_rn(acc4[t], e[t]);   // four independent chains
           }
           sts128(sp_row + (((uint32_t)c8 ^ ((uint32_t)row & 7u)) << 4), pack_bf16x2(e[0].x, e[0].y),
                  pack_bf16x2(e[1].x, e[1].y), pack_bf16x2(e[2].x, e[2].y), pack_bf16x2(e[3].x, e[3].y));
         }
+        const float2 acc2 = __fadd2_rn(__fadd2_rn(acc4[0], acc4[1]), __fadd2_rn(acc4[2], acc4[3]));
         const float sum = acc2.x + acc2.y;
         l_j[j] = sum;
         fence_proxy_async();
@@ -230,7 +245,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       for (int j = 0; j < NB; ++j) s_l[(j * 2 + hf) * 128 + row] = l_j[j];
       mbar_wait(o_full, (uint32_t)(it & 1));
       tc_fence_after();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
       float m = m_j[0];
 #pragma unroll
       for (int j = 1; j < NB; ++j) m = fmaxf(m, m_j[j]);
