@@ -111,8 +111,8 @@ def build_problem(workload_name):
 
 
 def make_hf_model(cfg):
-    from oracle import w2v2_forward as W          # model CONSTRUCTION only (random-init weights of the named arch)
-    return W.randomize_affine(W.build_hf_model(cfg.to_dict(), seed=0), seed=1)
+    from shap_transformer_asr_b200.modelzoo import build_random_init_model   # random-init weights of the named arch
+    return build_random_init_model(cfg, seed=0)
 
 
 def cpu_reference_rate(model, cfg, clip, Z, bounds, frames, tokens, n_rows, batch=32, threads=None):

@@ -11,3 +11,4 @@ from .callbacks import CoalitionCallback, ModelWrapper, make_lime_predict_fn, ma
 from .engine import Engine, debug_gemm  # noqa: F401
 from .metrics import eta_raw, greedy_ctc_decode, wer  # noqa: F401
 from .sweep import add_noise, explain_test_set, make_test_set  # noqa: F401
+from .modelzoo import build_random_init_model  # noqa: F401

@@ -59,3 +59,19 @@ def test_create_fails_loudly_without_a_gpu(lib):
     from shap_transformer_asr_b200 import Engine
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         Engine({}, MODELS["wav2vec2-tiny"])
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the product package (nor the B200 arm's helpers) may import it."""
+    import glob
+    pkg = os.path.join(ROOT, "shap_transformer_asr_b200")
+    for path in glob.glob(os.path.join(pkg, "**", "*.py"), recursive=True) + glob.glob(os.path.join(pkg, "csrc", "*")):
+        if os.path.isdir(path) or path.endswith((".o", ".so")):
+            continue
+        text = open(path, errors="ignore").read()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), path
+        assert "oracle/" not in text or path.endswith(".md"), path
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    body = bench[bench.index("def run_b200"):bench.index("def main")]
+    uses = [m.start() for m in re.finditer(r"from oracle", body)]
+    assert len(uses) == 1 and "CPU baseline" in body[uses[0] - 400:uses[0]]     # only inside the cpu_baseline leg

@@ -19,8 +19,8 @@ import torch
 import torch.distributed as td
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import w2v2_forward as W  # model construction only (random-init weights of the named architecture)
 from shap_transformer_asr_b200 import MODELS, Engine, dist as wdist, eta_raw, explain_test_set, make_test_set, wer
+from shap_transformer_asr_b200.modelzoo import build_random_init_model
 
 
 def main():
@@ -36,7 +36,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     cfg = MODELS[args.model]
-    model = W.randomize_affine(W.build_hf_model(cfg.to_dict(), seed=0), seed=1)
+    model = build_random_init_model(cfg, seed=0)
     eng = Engine(model, cfg, device=local, max_batch=128)
     test_set = make_test_set(num_clips=args.clips, num_samples=args.samples, snrs=(5, 2, 1), seed=0)
     # keep each clip's clean item with its noisy versions on one rank (the clean transcript is their WER reference)
