@@ -112,6 +112,7 @@ struct w2s_handle {
   float* xm = nullptr;
   long long xm_ld = 0;
   float *gn_a = nullptr, *gn_b = nullptr;
+  bf16* gn_wb = nullptr;
   bf16 *bufA = nullptr, *bufB = nullptr;
   bf16 *fpn = nullptr, *h0 = nullptr, *hp = nullptr, *hb = nullptr, *h1 = nullptr, *qkv = nullptr, *ctx = nullptr,
        *ffn = nullptr;
@@ -407,6 +408,7 @@ std::string ensure_workspace(w2s_handle* h, long long L) {
   W2S_TRY(dalloc(pool, &h->xm, nb * h->xm_ld));
   W2S_TRY(dalloc(pool, &h->gn_a, nb * c.conv_dim[0]));
   W2S_TRY(dalloc(pool, &h->gn_b, nb * c.conv_dim[0]));
+  W2S_TRY(dalloc(pool, &h->gn_wb, nb * c.conv_dim[0] * 32));
   size_t szA = 0, szB = 0;
   for (int l = 0; l < c.num_conv_layers; ++l) {
     const size_t s = nb * (size_t)h->Tl[l] * c.conv_dim[l];
@@ -538,7 +540,7 @@ struct PlanBuilder {
       cp.n = n; cp.L = (int)h->ws_L; cp.T0 = h->Tl[0]; cp.C = c.conv_dim[0]; cp.kw = c.conv_kernel[0];
       cp.stride = c.conv_stride[0];
       cp.w = h->conv0_w; cp.bias = h->conv0_b; cp.gamma = h->norm0_g; cp.beta = h->norm0_b;
-      cp.gn_a = h->gn_a; cp.gn_b = h->gn_b;
+      cp.gn_a = h->gn_a; cp.gn_b = h->gn_b; cp.gn_wb = h->gn_wb;
       cp.ln_wbar = h->ln0_wbar; cp.ln_gram = h->ln0_gram; cp.ln_wb = h->ln0_wb;
       cp.ln_bmean = h->ln0_bmean; cp.ln_b2mean = h->ln0_b2mean;
       cp.out = h->bufA;

@@ -89,30 +89,30 @@ __device__ __forceinline__ float erfc_pos(float z) {
   return p * ex2_approx(-1.4426950408889634f * z * z);
 }
 
-// exact-erf GELU (HF ACT2FN["gelu"]): 0.5 v (1 + erf(v / sqrt 2))
+// exact-erf GELU (HF ACT2FN["gelu"]): 0.5 v (1 + erf(v / sqrt 2)) = max(v, 0) - |v| q,  q = 0.5 erfc(|v| / sqrt 2)
+// (v >= 0: v (1 - q); v < 0: v q) -- no select on the sign, the max runs on the ALU pipe next to the FMA pipe.
 __device__ __forceinline__ float gelu_erf(float v) {
-  float q = 0.5f * erfc_pos(fabsf(v) * 0.70710678118654752f);  // 0.5 erfc(|v|/sqrt2)
-  return v >= 0.f ? fmaf(-v, q, v) : v * q;
+  const float av = fabsf(v);
+  const float q = 0.5f * erfc_pos(av * 0.70710678118654752f);
+  return fmaf(-av, q, fmaxf(v, 0.f));
 }
 
-// Two GELUs at once on Blackwell's packed fp32 pipe (FFMA2/FMUL2: fma.rn.f32x2): ~10 issue slots per element
-// instead of ~17.  Phi(v) = v >= 0 ? 1 - q : q with q = 0.5 erfc(|v|/sqrt 2); the 0.5 is folded into the
-// A&S 7.1.26 coefficients.
+// Two GELUs at once on Blackwell's packed fp32 pipe (FFMA2/FMUL2: fma.rn.f32x2): 10 packed ops + 4 MUFU + 2 FMNMX
+// per PAIR.  The -0.5 and the 1/sqrt 2 are folded into the A&S 7.1.26 constants: nq = -0.5 erfc(|v| / sqrt 2).
 __device__ __forceinline__ float2 gelu_erf2(float2 v) {
-  const float2 z = __fmul2_rn(make_float2(fabsf(v.x), fabsf(v.y)), make_float2(0.70710678118654752f, 0.70710678118654752f));
-  const float2 den = __ffma2_rn(z, make_float2(0.3275911f, 0.3275911f), make_float2(1.0f, 1.0f));
+  const float2 av = make_float2(fabsf(v.x), fabsf(v.y));
+  const float2 den = __ffma2_rn(av, make_float2(0.3275911f * 0.70710678118654752f, 0.3275911f * 0.70710678118654752f),
+                                make_float2(1.0f, 1.0f));
   const float2 t = make_float2(rcp_approx(den.x), rcp_approx(den.y));
-  float2 p = __ffma2_rn(t, make_float2(0.5f * 1.061405429f, 0.5f * 1.061405429f),
-                        make_float2(0.5f * -1.453152027f, 0.5f * -1.453152027f));
-  p = __ffma2_rn(p, t, make_float2(0.5f * 1.421413741f, 0.5f * 1.421413741f));
-  p = __ffma2_rn(p, t, make_float2(0.5f * -0.284496736f, 0.5f * -0.284496736f));
-  p = __ffma2_rn(p, t, make_float2(0.5f * 0.254829592f, 0.5f * 0.254829592f));
+  float2 p = __ffma2_rn(t, make_float2(-0.5f * 1.061405429f, -0.5f * 1.061405429f),
+                        make_float2(-0.5f * -1.453152027f, -0.5f * -1.453152027f));
+  p = __ffma2_rn(p, t, make_float2(-0.5f * 1.421413741f, -0.5f * 1.421413741f));
+  p = __ffma2_rn(p, t, make_float2(-0.5f * -0.284496736f, -0.5f * -0.284496736f));
+  p = __ffma2_rn(p, t, make_float2(-0.5f * 0.254829592f, -0.5f * 0.254829592f));
   p = __fmul2_rn(p, t);
-  const float2 a = __fmul2_rn(__fmul2_rn(z, z), make_float2(-1.4426950408889634f, -1.4426950408889634f));
-  const float2 q = __fmul2_rn(p, make_float2(ex2_approx(a.x), ex2_approx(a.y)));
-  const float2 omq = __ffma2_rn(q, make_float2(-1.0f, -1.0f), make_float2(1.0f, 1.0f));
-  const float2 phi = make_float2(v.x >= 0.f ? omq.x : q.x, v.y >= 0.f ? omq.y : q.y);
-  return __fmul2_rn(v, phi);
+  const float2 a = __fmul2_rn(__fmul2_rn(v, v), make_float2(-0.5f * 1.4426950408889634f, -0.5f * 1.4426950408889634f));
+  const float2 nq = __fmul2_rn(p, make_float2(ex2_approx(a.x), ex2_approx(a.y)));
+  return __ffma2_rn(av, nq, make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f)));
 }
 
 __device__ __forceinline__ float swish(float v) { return v * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * v)); }
@@ -146,6 +146,19 @@ __device__ __forceinline__ float warp_max(float v) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// warp-level MMA (register accumulators) for the one contraction whose K is too short for a TMEM round trip:
+// conv0 (K = 32 after the bf16 hi/lo split), where the GELU epilogue needs the accumulators in registers anyway.
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {

@@ -118,8 +118,28 @@ __global__ void __launch_bounds__(256) conv0_stats_kernel(const Conv0Params p) {
     if (var < 0.0) var = 0.0;
     const double rstd = rsqrt(var + 1e-5);
     const double a = rstd * (double)p.gamma[c];
+    const float shift = (float)((double)p.beta[c] - mean * a);
     p.gn_a[(long long)row * p.C + c] = (float)a;
-    p.gn_b[(long long)row * p.C + c] = (float)((double)p.beta[c] - mean * a);
+    p.gn_b[(long long)row * p.C + c] = shift;
+    if (p.gn_wb) {
+      // K = 32 row of the tensor-core form: y = sum_k A[f][k] B[c][k] with A[f] = [x_hi | x_lo | x_hi | 1 1] and
+      // B[c] = [w_hi | w_hi | w_lo | shift_hi shift_lo], w = filter * rstd * gamma (the lo*lo term, ~2^-18, is dropped)
+      static_assert(3 * KW + 2 == 32, "K layout of conv0_mma_kernel");
+      __align__(16) __nv_bfloat16 kb[32];
+#pragma unroll
+      for (int j = 0; j < KW; ++j) {
+        const float wf = (float)(wj[j] * a);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(wf);
+        kb[j] = hi;
+        kb[KW + j] = hi;
+        kb[2 * KW + j] = __float2bfloat16_rn(wf - __bfloat162float(hi));
+      }
+      kb[30] = __float2bfloat16_rn(shift);
+      kb[31] = __float2bfloat16_rn(shift - __bfloat162float(kb[30]));
+      uint4* dst = reinterpret_cast<uint4*>(p.gn_wb + ((long long)row * p.C + c) * 32);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dst[q] = reinterpret_cast<const uint4*>(kb)[q];
+    }
   }
 }
 
@@ -200,9 +220,11 @@ __global__ void __launch_bounds__(256, 2) conv0_kernel(const Conv0Params p, int 
     } else {
       const float* ga = p.gn_a + (long long)row * p.C + c0 + 2 * i;
       const float* gb = p.gn_b + (long long)row * p.C + c0 + 2 * i;
+      // group norm is affine per (row, channel): fold it into the filters, the accumulator starts at the shift
       ca2[i] = make_float2(ga[0], ga[1]);
-      cb2[i] = make_float2(gb[0], gb[1]);
-      bias2[i] = make_float2(0.f, 0.f);
+      bias2[i] = make_float2(gb[0], gb[1]);
+#pragma unroll
+      for (int j = 0; j < KW; ++j) w2[i][j] = __fmul2_rn(w2[i][j], ca2[i]);
     }
   }
 
@@ -219,17 +241,102 @@ __global__ void __launch_bounds__(256, 2) conv0_kernel(const Conv0Params p, int 
       for (int j = 0; j < KW; ++j) a = __ffma2_rn(w2[i][j], xv[j], a);
       if constexpr (LAYER) {
         const float m = fmean[f], r = frstd[f];
-        a = __fmul2_rn(__fadd2_rn(a, make_float2(-m, -m)), make_float2(r, r));
+        a = __ffma2_rn(__fmul2_rn(__fadd2_rn(a, make_float2(-m, -m)), make_float2(r, r)), ca2[i], cb2[i]);
       }
-      const float2 y = gelu_erf2(__ffma2_rn(a, ca2[i], cb2[i]));
+      const float2 y = gelu_erf2(a);
       packed[i] = pack_bf16x2(y.x, y.y);
     }
     *reinterpret_cast<uint4*>(out + (long long)f * p.C) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
   }
 }
 
+// Group-norm variant on the warp-level tensor cores.  After the bf16 hi/lo split the whole layer, affine included, is
+// one K = 32 contraction per (frame, channel) (layout in conv0_stats_kernel); what is left for the FP32 pipes is the
+// GELU.  CTA = (FT frames, waveform row): the im2col rows [FT][32] are built once in shared memory (80-byte pitch:
+// conflict-free ldmatrix), each warp owns 64 channels whose B fragments stay in registers, and the channel
+// permutation inside a warp is chosen so that a thread ends up with 8 consecutive channels per (frame, half):
+// one 16-byte store, 64 contiguous bytes per quad.
+template <int KW>
+__global__ void __launch_bounds__(256, 2) conv0_mma_kernel(const Conv0Params p, int FT) {
+  extern __shared__ __align__(16) uint8_t im2col[];
+  constexpr int LDA = 80;
+  static_assert(3 * KW + 2 == 32, "K layout");
+  pdl_trigger();
+  pdl_wait();
+  const int row = blockIdx.y;
+  const int f0 = blockIdx.x * FT;
+  const int nf = min(FT, p.T0 - f0);
+  const int nfp = (nf + 15) & ~15;
+  const float* x = p.x + (long long)row * p.ld + (long long)f0 * p.stride;
+  for (int i = threadIdx.x; i < nfp * KW; i += blockDim.x) {
+    const int f = i / KW, j = i - f * KW;
+    const float v = f < nf ? __ldg(x + f * p.stride + j) : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    __nv_bfloat16* ar = reinterpret_cast<__nv_bfloat16*>(im2col + f * LDA);
+    ar[j] = hi;
+    ar[KW + j] = lo;
+    ar[2 * KW + j] = hi;
+    if (j == 0) *reinterpret_cast<uint32_t*>(ar + 3 * KW) = 0x3f803f80u;  // (1, 1): picks up the shift terms
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  uint32_t bfrag[8][2][2];
+  {
+    const __nv_bfloat16* wb = p.gn_wb + (long long)row * p.C * 32;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int ch = warp * 64 + (nt >> 2) * 32 + (g >> 1) * 8 + (nt & 3) * 2 + (g & 1);
+      const uint32_t* wr = reinterpret_cast<const uint32_t*>(wb + (long long)ch * 32);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        bfrag[nt][ks][0] = wr[8 * ks + t];
+        bfrag[nt][ks][1] = wr[8 * ks + t + 4];
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t a_base = smem_u32(im2col) + (lane & 15) * LDA + (lane >> 4) * 16;
+  __nv_bfloat16* out = p.out + ((long long)row * p.T0 + f0) * p.C + warp * 64 + t * 8;
+  for (int mb = 0; mb * 16 < nf; ++mb) {
+    uint32_t a[2][4];
+    ldmatrix_x4(a[0], a_base + mb * 16 * LDA);
+    ldmatrix_x4(a[1], a_base + mb * 16 * LDA + 32);
+    float c[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
+      mma_bf16_16816(c[nt], a[0], bfrag[nt][0]);
+      mma_bf16_16816(c[nt], a[1], bfrag[nt][1]);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int f = mb * 16 + g + 8 * r;
+      if (f < nf) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 y = gelu_erf2(make_float2(c[4 * h + q][2 * r], c[4 * h + q][2 * r + 1]));
+            pk[q] = pack_bf16x2(y.x, y.y);
+          }
+          *reinterpret_cast<uint4*>(out + (long long)f * p.C + h * 32) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+    }
+  }
+}
+
 std::string launch_conv0(const Conv0Params& p, bool layer_norm, cudaStream_t s) {
   if (p.kw != 10) return "conv0: only kernel width 10 is implemented for layer 0";
+  static const bool mma_enabled = getenv("W2S_NO_CONV0_MMA") == nullptr;
+  if (!layer_norm && mma_enabled && p.gn_wb && p.C % 64 == 0 && p.C <= 512 && p.n > 0) {
+    const int FT = 512;
+    dim3 grid((p.T0 + FT - 1) / FT, p.n);
+    W2S_CUDA_OK(launch_pdl(conv0_mma_kernel<10>, grid, dim3(p.C / 2), (size_t)FT * 80, s, 1, p, FT));
+    W2S_CUDA_OK(cudaGetLastError());
+    return "";
+  }
   const int tpf = p.C / 8;
   if (p.C % 8 || tpf > 256 || (256 % tpf)) return "conv0: channel count must be 8 * (a divisor of 256)";
   if (p.n == 0) return "";

@@ -21,6 +21,8 @@ struct Conv0Params {
   // group-norm variant: per (row, channel) affine produced by the statistics kernel
   float* gn_a;           // [n, C]  rstd * gamma
   float* gn_b;           // [n, C]  beta - mean * rstd * gamma
+  __nv_bfloat16* gn_wb;  // [n, C, 32] (optional) filters with the affine folded in, split into bf16 hi/lo terms:
+                         //            the B operand of conv0_mma_kernel
   // layer-norm variant: channel statistics of the filter bank (precomputed once)
   const float* ln_wbar;  // [kw]       mean_c w[c][j]
   const float* ln_gram;  // [kw][kw]   mean_c w[c][j] w[c][j']
