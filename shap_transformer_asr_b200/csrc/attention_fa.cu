@@ -4,10 +4,11 @@
 // every block keeps its own softmax maximum m_j, partial sum l_j and its own O_j accumulator in TMEM (4 x 64
 // columns), and the epilogue merges them,  out = sum_j a_j O_j / sum_j a_j l_j,  a_j = exp(m_j - max_j m_j),
 // so nothing is ever rescaled in TMEM and the three engines run decoupled:
-//   warp 8  (TMA)     Q tile per item, {K_j, V_j} through a 3-stage ring
+//   warp 8  (TMA)     Q tile per item (double-buffered), {K_j, V_j} through a 3-stage ring
 //   warp 9  (MMA)     S_j = Q K_j^T into one of two S buffers (128 fp32 columns each), O_j = P_j V_j one block behind
-//   warps 0-7 (softmax) read S_j from TMEM (two threads per query row, 64 keys each), write P_j = exp(S_j - m_j) as bf16
-//                     into one of two swizzled smem buffers, finally merge the O_j and store the context rows
+//   warps 0-7 (softmax) two groups of four warps, group g takes the blocks with running index g (mod 2): one thread per
+//                     query row reads S_j from TMEM, writes P_j = exp(S_j - m_j) as bf16 into the group's swizzled smem
+//                     buffer; the groups share the merge of the O_j (32 of the 64 output columns each)
 // HF wav2vec2/modeling_wav2vec2.py:438-463 (softmax(Q K^T / sqrt d) V, no mask, eval mode).
 #include "kernels.cuh"
 #include "gemm.cuh"
@@ -26,8 +27,8 @@ struct AttnFaPlan {
 };
 
 constexpr int FA_KVS = 3;
-constexpr int FA_SQ = 0, FA_SKV = 16384, FA_SP = FA_SKV + FA_KVS * 32768, FA_RED = FA_SP + 2 * 32768,
-              FA_BAR = FA_RED + 2 * 2 * 128 * 4 + 4 * 2 * 128 * 4;
+constexpr int FA_SQ = 0, FA_SKV = 2 * 16384, FA_SP = FA_SKV + FA_KVS * 32768, FA_RED = FA_SP + 2 * 32768,
+              FA_BAR = FA_RED + 2 * (4 * 4 * 128 * 4);
 constexpr size_t FA_SMEM = FA_BAR + 256 + 1024;
 
 __device__ __forceinline__ uint64_t fa_desc_mn(uint32_t a) { return umma_desc_sw128(a); }
@@ -40,18 +41,25 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw);
-  float* s_m = reinterpret_cast<float*>(base_ptr + FA_RED);               // [2][2][128] block maxima exchange
-  float* s_l = s_m + 2 * 2 * 128;                                          // [4][2][128] partial sums exchange
+  float* s_m = reinterpret_cast<float*>(base_ptr + FA_RED);               // [item mod 4][4][128] block maxima
+  float* s_l = s_m + 4 * 4 * 128;                                          // [item mod 4][4][128] block sums
   const uint32_t bars = base + FA_BAR;
-  const uint32_t q_full = bars, q_empty = bars + 8, o_full = bars + 16, o_empty = bars + 24;
-  auto kv_full = [&](int s) { return bars + 32 + 8u * s; };
-  auto kv_empty = [&](int s) { return bars + 32 + 8u * (FA_KVS + s); };
-  auto s_full = [&](int i) { return bars + 96 + 8u * i; };
-  auto s_empty = [&](int i) { return bars + 112 + 8u * i; };
-  auto p_full = [&](int i) { return bars + 128 + 8u * i; };
-  auto p_empty = [&](int i) { return bars + 144 + 8u * i; };
-  const uint32_t tmem_slot = bars + 160;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + FA_BAR + 160);
+  auto kv_full = [&](int s) { return bars + 8u * s; };
+  auto kv_empty = [&](int s) { return bars + 24 + 8u * s; };
+  auto s_full = [&](int i) { return bars + 48 + 8u * i; };
+  auto s_empty = [&](int i) { return bars + 64 + 8u * i; };
+  auto p_full = [&](int i) { return bars + 80 + 8u * i; };
+  auto p_empty = [&](int i) { return bars + 96 + 8u * i; };
+  auto q_full = [&](int i) { return bars + 112 + 8u * i; };
+  auto q_empty = [&](int i) { return bars + 128 + 8u * i; };
+  auto o_full = [&](int i) { return bars + 144 + 8u * i; };
+  auto o_empty = [&](int i) { return bars + 160 + 8u * i; };
+  auto ml_full = [&](int i) { return bars + 176 + 8u * i; };
+  const uint32_t tmem_slot = bars + 208;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + FA_BAR + 208);
+  // With at most two key blocks per item the O accumulators (NB x 64 columns) fit twice next to the two S buffers:
+  // the P V MMAs of item i+1 then never wait for the merge of item i.
+  constexpr int OB = NB <= 2 ? 2 : 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 8 && lane == 0) {
@@ -60,20 +68,21 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     tma_prefetch_desc(&mapV);
   }
   if (warp == 9 && lane == 0) {
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
-    mbar_init(o_full, 1);
-    mbar_init(o_empty, 8);
     for (int s = 0; s < FA_KVS; ++s) {
       mbar_init(kv_full(s), 1);
       mbar_init(kv_empty(s), 1);
     }
     for (int i = 0; i < 2; ++i) {
+      mbar_init(q_full(i), 1);
+      mbar_init(q_empty(i), 1);
+      mbar_init(o_full(i), 1);
+      mbar_init(o_empty(i), 8);
       mbar_init(s_full(i), 1);
-      mbar_init(s_empty(i), 8);
-      mbar_init(p_full(i), 8);
+      mbar_init(s_empty(i), 4);
+      mbar_init(p_full(i), 4);
       mbar_init(p_empty(i), 1);
     }
+    for (int i = 0; i < 4; ++i) mbar_init(ml_full(i), 8);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -85,7 +94,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
-  // TMEM columns: S buffers at 0 / 128, O_j at 256 + 64 j
+  // TMEM columns: S buffers at 0 / 128, O_j of item parity ob at 256 + 128 ob + 64 j (NB <= 2), else 256 + 64 j
   pdl_trigger();
   pdl_wait();
 
@@ -95,9 +104,10 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       int it = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
         const int qt = item % p.qtiles, h = (item / p.qtiles) % p.heads, b = item / (p.qtiles * p.heads);
-        mbar_wait(q_empty, (uint32_t)(it & 1) ^ 1u);
-        mbar_expect_tx(q_full, 16384);
-        tma_load_4d(base + FA_SQ, &mapQ, q_full, 0, qt * 128, h, b);
+        // Q is double-buffered: the tile of item i+1 (and its first K/V stage) is in flight while item i computes
+        mbar_wait(q_empty(it & 1), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(q_full(it & 1), 16384);
+        tma_load_4d(base + FA_SQ + (it & 1) * 16384, &mapQ, q_full(it & 1), 0, qt * 128, h, b);
 #pragma unroll 1
         for (int j = 0; j < NB; ++j, ++kvc) {
           const int s = kvc % FA_KVS;
@@ -119,7 +129,8 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         // the O accumulators are overwritten from the first P V of an item on: only then must the previous item's merge
         // have drained them (waiting here instead of before the score MMAs lets S_0 / S_1 of the next item be computed
         // while the softmax warps still finish the previous one)
-        if (jj == 0) mbar_wait(o_empty, (uint32_t)(it_ & 1) ^ 1u);
+        const int ob = it_ % OB;
+        if (jj == 0) mbar_wait(o_empty(ob), ((uint32_t)(it_ / OB) & 1u) ^ 1u);
         mbar_wait(p_full(pb), (pc >> 1) & 1u);
         tc_fence_after();
 #pragma unroll
@@ -128,7 +139,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
           const uint64_t dv = fa_desc_mn(base + FA_SKV + stage * 32768 + 16384 + kb * 8192);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem + 256 + 64 * jj, dp + 2u * k, dv + 128u * k, idesc_pv, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16(tmem + 256 + 128 * ob + 64 * jj, dp + 2u * k, dv + 128u * k, idesc_pv, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(p_empty(pb));
         umma_commit(kv_empty(stage));
@@ -139,22 +150,22 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       bool pending = false;
       int pend_j = 0, pend_stage = 0, pend_it = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-        mbar_wait(q_full, (uint32_t)(it & 1));
+        mbar_wait(q_full(it & 1), (uint32_t)(it >> 1) & 1u);
 #pragma unroll 1
         for (int j = 0; j < NB; ++j, ++kvc, ++sc) {
           const int s = kvc % FA_KVS, sb = sc & 1;
           mbar_wait(kv_full(s), (kvc / FA_KVS) & 1u);
           mbar_wait(s_empty(sb), ((sc >> 1) & 1u) ^ 1u);
           tc_fence_after();
-          const uint64_t dq = umma_desc_sw128(base + FA_SQ);
+          const uint64_t dq = umma_desc_sw128(base + FA_SQ + (it & 1) * 16384);
           const uint64_t dk = umma_desc_sw128(base + FA_SKV + s * 32768);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(tmem + sb * 128, dq + 2u * k, dk + 2u * k, idesc_qk, k != 0 ? 1u : 0u);
           umma_commit(s_full(sb));
-          if (j == NB - 1) umma_commit(q_empty);
+          if (j == NB - 1) umma_commit(q_empty(it & 1));
           if (pending) {
             issue_pv(pend_j, pend_stage, pend_it);
-            if (pend_j == NB - 1) umma_commit(o_full);
+            if (pend_j == NB - 1) umma_commit(o_full(pend_it % OB));
           }
           pending = true;
           pend_j = j;
@@ -164,114 +175,80 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       }
       if (pending) {
         issue_pv(pend_j, pend_stage, pend_it);
-        umma_commit(o_full);
+        umma_commit(o_full(pend_it % OB));
       }
     }
   } else if (warp < 8) {
-    const int qd = warp & 3, hf = warp >> 2;
+    // Two softmax groups of four warps.  Group g owns every key block whose running index is g (mod 2) -- S buffer g,
+    // P buffer g -- and one thread owns one query row with all 128 keys of the block, so a block needs no exchange
+    // between threads and the two groups drift apart: while one waits for TMEM or the MMA warp, the other keeps the
+    // MUFU / FMA pipes of the same scheduler busy.  Scores are read from TMEM twice (maximum, then exponentials)
+    // instead of being held in 128 registers.  The merge of item i is deferred until after the group's first block
+    // of item i+1, so the P V MMAs of item i finish behind useful work.
+    const int grp = warp >> 2, qd = warp & 3;
     const int row = qd * 32 + lane;
     const uint32_t trow = tmem + (static_cast<uint32_t>(qd * 32) << 16);
-    uint32_t sc = 0, pc = 0;
-    int it = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
-      const int qt = item % p.qtiles, h = (item / p.qtiles) % p.heads, b = item / (p.qtiles * p.heads);
-      float m_j[NB], l_j[NB];
+    const uint32_t s_addr = trow + grp * 128;
+    const uint32_t sp_row = base + FA_SP + grp * 32768 + row * 128;
+    const uint32_t sw = (uint32_t)row & 7u;
+    const float2 sc2 = make_float2(p.scale_log2e, p.scale_log2e);
+
+    auto mask_tail = [&](float (&v)[32], int col0, int nvalid) {
 #pragma unroll
-      for (int j = 0; j < NB; ++j, ++sc, ++pc) {
-        const int sb = sc & 1, pb = pc & 1;
-        mbar_wait(s_full(sb), (sc >> 1) & 1u);
-        tc_fence_after();
-        float sv[64];
-        {
-          float t0[32], t1[32];
-          tmem_ld_32x32(trow + sb * 128 + hf * 64, t0);
-          tmem_ld_32x32(trow + sb * 128 + hf * 64 + 32, t1);
+      for (int g8 = 0; g8 < 4; ++g8) {
+        if (col0 + 8 * g8 + 8 > nvalid) {   // warp-uniform
 #pragma unroll
-          for (int t = 0; t < 32; ++t) {
-            sv[t] = t0[t];
-            sv[32 + t] = t1[t];
-          }
+          for (int t = 0; t < 8; ++t)
+            if (col0 + 8 * g8 + t >= nvalid) v[8 * g8 + t] = -3.0e38f;   // finite: exp2 underflows to 0 by itself
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_empty(sb));   // S_j is in registers: the MMA warp may overwrite the buffer
-        // Keys beyond T' (only possible in the last block) get a large negative FINITE score: exp2 then underflows to 0
-        // by itself, so the hot loops below carry no per-element compare / select.
-        const int key0 = j * 128 + hf * 64;
-        if (j == NB - 1 && key0 + 64 > p.T) {
-#pragma unroll
-          for (int t = 0; t < 64; ++t)
-            if (key0 + t >= p.T) sv[t] = -3.0e38f;
-        }
-        float mx0 = sv[0], mx1 = sv[1], mx2 = sv[2], mx3 = sv[3];
-#pragma unroll
-        for (int t = 4; t < 64; t += 4) {
-          mx0 = fmaxf(mx0, sv[t]);
-          mx1 = fmaxf(mx1, sv[t + 1]);
-          mx2 = fmaxf(mx2, sv[t + 2]);
-          mx3 = fmaxf(mx3, sv[t + 3]);
-        }
-        float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-        s_m[(sb * 2 + hf) * 128 + row] = mx;
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");   // only the partner warp (same lane quadrant) shares these rows
-        mx = fmaxf(s_m[(sb * 2 + 0) * 128 + row], s_m[(sb * 2 + 1) * 128 + row]);
-        m_j[j] = mx;
-        const float2 sc2 = make_float2(p.scale_log2e, p.scale_log2e);
-        const float2 nm2 = make_float2(-mx * p.scale_log2e, -mx * p.scale_log2e);
-        mbar_wait(p_empty(pb), ((pc >> 1) & 1u) ^ 1u);   // P V of two blocks ago has drained this P buffer
-        float2 acc4[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-        const uint32_t sp_row = base + FA_SP + pb * 32768 + hf * 16384 + row * 128;
-#pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {
-          float2 e[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float2 a = __ffma2_rn(make_float2(sv[c8 * 8 + 2 * t], sv[c8 * 8 + 2 * t + 1]), sc2, nm2);
-            e[t] = make_float2(ex2_approx(a.x), ex2_approx(a.y));
-            acc4[t] = __fadd2_rn(acc4[t], e[t]);   // four independent chains
-          }
-          sts128(sp_row + (((uint32_t)c8 ^ ((uint32_t)row & 7u)) << 4), pack_bf16x2(e[0].x, e[0].y),
-                 pack_bf16x2(e[1].x, e[1].y), pack_bf16x2(e[2].x, e[2].y), pack_bf16x2(e[3].x, e[3].y));
-        }
-        const float2 acc2 = __fadd2_rn(__fadd2_rn(acc4[0], acc4[1]), __fadd2_rn(acc4[2], acc4[3]));
-        const float sum = acc2.x + acc2.y;
-        l_j[j] = sum;
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_full(pb));
       }
-      // ---- merge the blocks and store ------------------------------------------------------------------------------
+    };
+    auto max32 = [&](const float (&v)[32]) {
+      float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
 #pragma unroll
-      for (int j = 0; j < NB; ++j) s_l[(j * 2 + hf) * 128 + row] = l_j[j];
-      mbar_wait(o_full, (uint32_t)(it & 1));
-      tc_fence_after();
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
-      float m = m_j[0];
+      for (int t = 4; t < 32; t += 4) {
+        m0 = fmaxf(m0, v[t]);
+        m1 = fmaxf(m1, v[t + 1]);
+        m2 = fmaxf(m2, v[t + 2]);
+        m3 = fmaxf(m3, v[t + 3]);
+      }
+      return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    };
+
+    auto merge = [&](int item, int it_) {
+      const int qt = item % p.qtiles, h = (item / p.qtiles) % p.heads, b = item / (p.qtiles * p.heads);
+      const float* pm = s_m + (it_ & 3) * (4 * 128) + row;
+      const float* pl = s_l + (it_ & 3) * (4 * 128) + row;
+      const int ob = it_ % OB;
+      mbar_wait(ml_full(it_ & 3), (uint32_t)(it_ >> 2) & 1u);
+      float m = pm[0];
 #pragma unroll
-      for (int j = 1; j < NB; ++j) m = fmaxf(m, m_j[j]);
+      for (int j = 1; j < NB; ++j) m = fmaxf(m, pm[j * 128]);
       float a_j[NB], L = 0.f;
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
-        a_j[j] = ex2_approx((m_j[j] - m) * p.scale_log2e);
-        L = fmaf(a_j[j], s_l[(j * 2 + 0) * 128 + row] + s_l[(j * 2 + 1) * 128 + row], L);
+        a_j[j] = ex2_approx((pm[j * 128] - m) * p.scale_log2e);
+        L = fmaf(a_j[j], pl[j * 128], L);
       }
       const float inv = 1.0f / L;
+      mbar_wait(o_full(ob), (uint32_t)(it_ / OB) & 1u);
+      tc_fence_after();
       float o[32];
 #pragma unroll
       for (int t = 0; t < 32; ++t) o[t] = 0.f;
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
         float v[32];
-        tmem_ld_32x32(trow + 256 + 64 * j + hf * 32, v);
+        tmem_ld_32x32(trow + 256 + 128 * ob + 64 * j + grp * 32, v);
 #pragma unroll
         for (int t = 0; t < 32; ++t) o[t] = fmaf(a_j[j], v[t], o[t]);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(o_empty);
+      if (lane == 0) mbar_arrive(o_empty(ob));
       const int i = qt * 128 + row;
       if (i < p.T) {
-        __nv_bfloat16* orow = p.ctx + ((long long)b * p.T + i) * p.H + h * 64 + hf * 32;
+        __nv_bfloat16* orow = p.ctx + ((long long)b * p.T + i) * p.H + h * 64 + grp * 32;
 #pragma unroll
         for (int t = 0; t < 32; t += 8) {
           uint4 u;
@@ -282,8 +259,92 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
           *reinterpret_cast<uint4*>(orow + t) = u;
         }
       }
-      // the s_l strip is rewritten only after the next item's NB block barriers, so no extra barrier is needed here
+    };
+
+    uint32_t cblk = 0, mine = 0;
+    int it = 0;
+    bool pend = false;
+    int pend_item = 0, pend_it = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
+      float* pm = s_m + (it & 3) * (4 * 128) + row;   // ring of four items: a group may run ahead of the other's merge
+      float* pl = s_l + (it & 3) * (4 * 128) + row;
+#pragma unroll
+      for (int j = 0; j < NB; ++j, ++cblk) {
+        if ((cblk & 1u) != (uint32_t)grp) continue;
+        const uint32_t par = mine & 1u;
+        ++mine;
+        const int nvalid = p.T - j * 128;   // columns >= nvalid of this block are padding (last block only)
+        mbar_wait(s_full(grp), par);
+        tc_fence_after();
+        float s0[32], s1[32];
+        // pass 1: block maximum; the second half stays in registers for pass 2
+        tmem_ld_32x32_issue(s_addr, s0);
+        tmem_ld_32x32_issue(s_addr + 32, s1);
+        tmem_ld_wait();
+        if (nvalid < 64) {
+          mask_tail(s0, 0, nvalid);
+          mask_tail(s1, 32, nvalid);
+        }
+        float mx = fmaxf(max32(s0), max32(s1));
+        tmem_ld_32x32_issue(s_addr + 64, s0);
+        tmem_ld_32x32_issue(s_addr + 96, s1);
+        tmem_ld_wait();
+        if (nvalid < 128) {
+          mask_tail(s0, 64, nvalid);
+          mask_tail(s1, 96, nvalid);
+        }
+        mx = fmaxf(mx, fmaxf(max32(s0), max32(s1)));
+        const float2 nm2 = make_float2(-mx * p.scale_log2e, -mx * p.scale_log2e);
+        float2 acc4[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        auto exp_store = [&](const float (&v)[32], int c) {   // 32-column chunk c of the block -> P (bf16, 128B swizzle)
+          const uint32_t dst = sp_row + (uint32_t)(c >> 1) * 16384u;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float2 e[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 a = __ffma2_rn(make_float2(v[q * 8 + 2 * t], v[q * 8 + 2 * t + 1]), sc2, nm2);
+              e[t] = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+              acc4[t] = __fadd2_rn(acc4[t], e[t]);   // four independent chains
+            }
+            sts128(dst + ((((uint32_t)(c & 1) * 4u + (uint32_t)q) ^ sw) << 4), pack_bf16x2(e[0].x, e[0].y),
+                   pack_bf16x2(e[1].x, e[1].y), pack_bf16x2(e[2].x, e[2].y), pack_bf16x2(e[3].x, e[3].y));
+          }
+        };
+        mbar_wait(p_empty(grp), par ^ 1u);   // the P V MMAs of this group's previous block have drained the P buffer
+        exp_store(s0, 2);
+        exp_store(s1, 3);
+        tmem_ld_32x32_issue(s_addr, s0);
+        tmem_ld_32x32_issue(s_addr + 32, s1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty(grp));   // the MMA warp may overwrite this S buffer
+        if (nvalid < 64) {
+          mask_tail(s0, 0, nvalid);
+          mask_tail(s1, 32, nvalid);
+        }
+        exp_store(s0, 0);
+        exp_store(s1, 1);
+        const float2 acc2 = __fadd2_rn(__fadd2_rn(acc4[0], acc4[1]), __fadd2_rn(acc4[2], acc4[3]));
+        pm[j * 128] = mx;
+        pl[j * 128] = acc2.x + acc2.y;
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(grp));
+        if (pend) {
+          merge(pend_item, pend_it);
+          pend = false;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ml_full(it & 3));   // this warp's (m_j, l_j) of the item are published
+      if (pend) merge(pend_item, pend_it);
+      pend = true;
+      pend_item = item;
+      pend_it = it;
     }
+    if (pend) merge(pend_item, pend_it);
   }
   tc_fence_before();
   __syncthreads();
