@@ -2,11 +2,17 @@
 // groups=16), last frame dropped, GELU) + residual, as a tcgen05 kernel specialised for its Toeplitz structure.
 //
 // For one (coalition, group) the 128 taps all read the SAME input window shifted by one frame per tap.  The generic
-// contraction kernel reloads a 128x64 A tile for every tap (16 KB per 96 MMA cycles -- far beyond what shared memory
-// can absorb); here the whole window (up to 256 + 127 frames x 64 channels, 48 KB, 128B swizzle) is loaded ONCE and
-// each tap's A operand is just a descriptor whose start address is advanced by one 128-byte row.  Only the 6-8 KB
-// weight slice of the tap streams through the TMA ring.  One unit = (coalition, group, 256-frame chunk): two
-// 128-row accumulators share every weight slice.
+// contraction kernel reloads a 128x64 A tile for every tap; here the window (up to 256 + 127 frames x 64 channels,
+// 48 KB, 128B swizzle) stays in shared memory and a tap's A operand is a descriptor whose start address is advanced
+// by one 128-byte row per tap (a start inside a swizzle atom costs nothing measurable).  Only the 4-8 KB weight slice
+// of a tap streams through the TMA ring, and the K steps that would multiply the zero padding of a 32/48-channel
+// group are skipped.
+//
+// Measured on B200: a 128x48x16 MMA costs ~46 cycles here (it is bound by the ~5.5 KB of operands it pulls from
+// shared memory, not by the tensor pipe), and with one coalition per unit a tap cost another ~310 cycles of
+// weight-ring latency (12 x 6 KB in flight is less than latency x consumption rate).  So one unit is now
+// (TWO coalitions, group, 256-frame chunk): every weight slice feeds 4 accumulators (2 coalitions x 2 row halves),
+// the ring is as deep as shared memory allows (120 KB in flight) and the weight traffic out of L2 halves.
 #include "gemm.cuh"
 #include "gemm_epi.cuh"
 #include "kernels.cuh"
@@ -19,33 +25,33 @@ struct PosConvDev {
 };
 
 constexpr int PC_WIN_BYTES = 3 * 16384;   // 384 rows x 128 B
-constexpr int PC_WSTAGES = 12;
 
 template <int NG>
 struct PcCfg {
   static constexpr int W_BYTES = NG * 128;
-  static constexpr size_t SMEM = 2 * PC_WIN_BYTES + (size_t)PC_WSTAGES * W_BYTES + 1024 + 512;
+  static constexpr int WSTAGES = NG == 64 ? 15 : 20;
+  static constexpr size_t SMEM = 2 * PC_WIN_BYTES + (size_t)WSTAGES * W_BYTES + 1024 + 512;
 };
 
 template <int NG>
 __global__ void __launch_bounds__(384, 1)
 posconv_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW, const PosConvDev p) {
   using C = PcCfg<NG>;
+  constexpr int WS = C::WSTAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw);
   const uint32_t sWin = base, sW = base + 2 * PC_WIN_BYTES;
-  const uint32_t bars = sW + PC_WSTAGES * C::W_BYTES;
+  const uint32_t bars = sW + WS * C::W_BYTES;
   auto wfull = [&](int s) { return bars + 8u * s; };
-  auto wempty = [&](int s) { return bars + 8u * (PC_WSTAGES + s); };
-  auto winfull = [&](int i) { return bars + 8u * (2 * PC_WSTAGES + i); };
-  auto winempty = [&](int i) { return bars + 8u * (2 * PC_WSTAGES + 2 + i); };
-  auto tfull = [&](int a) { return bars + 8u * (2 * PC_WSTAGES + 4 + a); };
-  auto tempty = [&](int a) { return bars + 8u * (2 * PC_WSTAGES + 6 + a); };
-  const uint32_t tmem_slot = bars + 8u * (2 * PC_WSTAGES + 8);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
-      base_ptr + 2 * PC_WIN_BYTES + PC_WSTAGES * C::W_BYTES + 8 * (2 * PC_WSTAGES + 8));
+  auto wempty = [&](int s) { return bars + 8u * (WS + s); };
+  const uint32_t winfull = bars + 8u * (2 * WS), winempty = bars + 8u * (2 * WS + 1);
+  auto tfull = [&](int a) { return bars + 8u * (2 * WS + 2 + a); };
+  auto tempty = [&](int a) { return bars + 8u * (2 * WS + 4 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * WS + 6);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(base_ptr + 2 * PC_WIN_BYTES + WS * C::W_BYTES + 8 * (2 * WS + 6));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 8 && lane == 0) {
@@ -53,13 +59,13 @@ posconv_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     tma_prefetch_desc(&mapW);
   }
   if (warp == 9 && lane == 0) {
-    for (int s = 0; s < PC_WSTAGES; ++s) {
+    for (int s = 0; s < WS; ++s) {
       mbar_init(wfull(s), 1);
       mbar_init(wempty(s), 1);
     }
+    mbar_init(winfull, 1);
+    mbar_init(winempty, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(winfull(i), 1);
-      mbar_init(winempty(i), 1);
       mbar_init(tfull(i), 1);
       mbar_init(tempty(i), 8);
     }
@@ -67,75 +73,80 @@ posconv_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     fence_proxy_async();
   }
   if (warp == 10) {
-    tmem_alloc<256>(tmem_slot);
+    tmem_alloc<512>(tmem_slot);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // TMEM columns: accumulator set a (alternating units) at 256 a; coalition u of the pair at + 128 u; row half at + 64 half
   pdl_trigger();
   pdl_wait();
 
   if (warp == 8) {
-    if (lane == 0) {
+    if (lane == 0) {   // weight slices: one stream across units, never blocked by the windows
       int ws = 0;
       uint32_t wphase = 0;
-      int it = 0;
-      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
-        const int ch = unit % p.chunks;
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
         const int g = (unit / p.chunks) % p.G;
-        const int b = unit / (p.chunks * p.G);
-        const int buf = it & 1;
-        const uint32_t bphase = (it >> 1) & 1;
-        mbar_wait(winempty(buf), bphase ^ 1u);
-        mbar_expect_tx(winfull(buf), PC_WIN_BYTES);
-        for (int i = 0; i < 3; ++i)
-          tma_load_3d(sWin + buf * PC_WIN_BYTES + i * 16384, &mapX, winfull(buf), g * 64, ch * 256 + i * 128, b);
         for (int j = 0; j < p.kpos; ++j) {
           mbar_wait(wempty(ws), wphase ^ 1u);
           mbar_expect_tx(wfull(ws), C::W_BYTES);
           tma_load_3d(sW + ws * C::W_BYTES, &mapW, wfull(ws), j * 64, 0, g);
-          if (++ws == PC_WSTAGES) {
+          if (++ws == WS) {
             ws = 0;
             wphase ^= 1u;
           }
         }
       }
     }
+  } else if (warp == 11) {
+    if (lane == 0) {   // the two windows of a unit
+      int it = 0;
+      for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
+        const int ch = unit % p.chunks;
+        const int g = (unit / p.chunks) % p.G;
+        const int b0 = 2 * (unit / (p.chunks * p.G));
+        mbar_wait(winempty, ((uint32_t)it & 1u) ^ 1u);
+        mbar_expect_tx(winfull, 2 * PC_WIN_BYTES);
+        for (int u = 0; u < 2; ++u)   // b0 + 1 == B (odd batch): the box is out of bounds and arrives as zeros
+          for (int i = 0; i < 3; ++i)
+            tma_load_3d(sWin + u * PC_WIN_BYTES + i * 16384, &mapX, winfull, g * 64, ch * 256 + i * 128, b0 + u);
+      }
+    }
   } else if (warp == 9) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, NG);
+      constexpr int KSTEPS = NG / 16;   // channels beyond NG are zero padding in both operands
       int ws = 0;
       uint32_t wphase = 0;
       int it = 0;
       for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const uint32_t bphase = (it >> 1) & 1;
-        mbar_wait(tempty(buf), bphase ^ 1u);
-        mbar_wait(winfull(buf), bphase);
+        const int abuf = it & 1;
+        mbar_wait(tempty(abuf), (((uint32_t)it >> 1) & 1u) ^ 1u);
+        mbar_wait(winfull, (uint32_t)it & 1u);
         tc_fence_after();
-        const uint32_t win = sWin + buf * PC_WIN_BYTES;
         for (int j = 0; j < p.kpos; ++j) {
           mbar_wait(wfull(ws), wphase);
           tc_fence_after();
           const uint64_t dw = umma_desc_sw128(sW + ws * C::W_BYTES);
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            // tap j of output rows [128 half, 128 half + 128): window rows start at 128 half + j (one row = 128 B)
-            const uint64_t da = umma_desc_sw128(win + (uint32_t)(half * 128 + j) * 128u);
+          for (int uh = 0; uh < 4; ++uh) {
+            // coalition uh / 2, output rows [128 (uh % 2), + 128): tap j reads window rows 128 (uh % 2) + j ...
+            const uint64_t da = umma_desc_sw128(sWin + (uint32_t)(uh >> 1) * PC_WIN_BYTES + (uint32_t)((uh & 1) * 128 + j) * 128u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base + buf * 128 + half * 64, da + 2u * k, dw + 2u * k, idesc, (j | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < KSTEPS; ++k)
+              umma_bf16(tmem_base + abuf * 256 + uh * 64, da + 2u * k, dw + 2u * k, idesc, (j | k) != 0 ? 1u : 0u);
           }
           umma_commit(wempty(ws));
-          if (++ws == PC_WSTAGES) {
+          if (++ws == WS) {
             ws = 0;
             wphase ^= 1u;
           }
         }
-        umma_commit(winempty(buf));
-        umma_commit(tfull(buf));
+        umma_commit(winempty);
+        umma_commit(tfull(abuf));
       }
     }
   } else if (warp < 8) {
@@ -144,30 +155,33 @@ posconv_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
       const int ch = unit % p.chunks;
       const int g = (unit / p.chunks) % p.G;
-      const int b = unit / (p.chunks * p.G);
-      const int buf = it & 1;
-      const uint32_t bphase = (it >> 1) & 1;
-      mbar_wait(tfull(buf), bphase);
+      const int b0 = 2 * (unit / (p.chunks * p.G));
+      const int abuf = it & 1;
+      mbar_wait(tfull(abuf), ((uint32_t)it >> 1) & 1u);
       tc_fence_after();
       const int t = ch * 256 + half * 128 + q * 32 + lane;
       const bool row_ok = t < p.T;
-      const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 128 + half * 64;
 #pragma unroll 1
-      for (int c = 0; c < NG; c += 16) {
-        float v[16];
-        tmem_ld_32x16(t0 + c, v);
-        if (row_ok) epi_store<16>(p.epi, p.cpg, g, b, t, c, v);
+      for (int u = 0; u < 2; ++u) {
+        if (b0 + u >= p.B) break;   // warp-uniform
+        const uint32_t t0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + abuf * 256 + u * 128 + half * 64;
+#pragma unroll 1
+        for (int c = 0; c < NG; c += 16) {
+          float v[16];
+          tmem_ld_32x16(t0 + c, v);
+          if (row_ok) epi_store<16>(p.epi, p.cpg, g, b0 + u, t, c, v);
+        }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty(buf));
+      if (lane == 0) mbar_arrive(tempty(abuf));
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 10) {
     tc_fence_after();
-    tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -199,7 +213,7 @@ std::string posconv_prepare(const __nv_bfloat16* x, const __nv_bfloat16* w, int 
   pl->ng = cpg;
   pl->dev.T = T; pl->dev.cpg = cpg; pl->dev.G = G; pl->dev.B = B; pl->dev.kpos = kpos;
   pl->dev.chunks = (T + 255) / 256;
-  pl->dev.num_units = pl->dev.chunks * G * B;
+  pl->dev.num_units = pl->dev.chunks * G * ((B + 1) / 2);   // a unit covers two coalitions
   pl->dev.epi = epi;
   pl->grid = pl->dev.num_units < num_sms ? pl->dev.num_units : num_sms;
   std::string err;
