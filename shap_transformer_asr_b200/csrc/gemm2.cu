@@ -173,37 +173,50 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         __syncwarp();
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
+        // 32-column sub-blocks of this warp, software-pipelined: the TMEM load of sub-block s+1 is in flight while the
+        // values of s are written to the staging strip, and the wait for the TMA engine to have read the strip (previous
+        // store) comes after the math of the sub-block instead of before its load.
+        const int nsub = f32 ? nblk : 2 * nblk;
+        auto sub_col = [&](int sidx) { return f32 ? (2 * sidx + hsel) * 32 : (2 * (sidx >> 1) + hsel) * 64 + (sidx & 1) * 32; };
+        float v[32];
+        tmem_ld_32x32_issue(t0 + sub_col(0), v);
 #pragma unroll 1
-        for (int ib = 0; ib < nblk; ++ib) {
-          const int cblk = (2 * ib + hsel) * bw;
-          if (lane == 0) tma_store_wait_read();   // the previous store of this warp has drained the strip
-          __syncwarp();
-#pragma unroll 1
-          for (int sub = 0; sub < (f32 ? 1 : 2); ++sub) {
-            const int c = cblk + sub * 32;
-            float v[32];
-            tmem_ld_32x32(t0 + c, v);
-            epi_math32(p.epi, p.epi.bias ? sbias + ib * bw + sub * 32 : nullptr, p.N, g, b, m, n0 + c, row_ok, v,
-                       reduce_add);
-            if (f32) {
+        for (int sidx = 0; sidx < nsub; ++sidx) {
+          const int c = sub_col(sidx);
+          const int sub = f32 ? 0 : (sidx & 1);
+          tmem_ld_wait();
+          epi_math32(p.epi, p.epi.bias ? sbias + sidx * 32 : nullptr, p.N, g, b, m, n0 + c, row_ok, v, reduce_add);
+          if (f32) {
+            if (lane == 0) tma_store_wait_read();   // the previous store of this warp has drained the strip
+            __syncwarp();
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                sts128(stg_row + (((uint32_t)j ^ ((uint32_t)lane & 7u)) << 4), __float_as_uint(v[4 * j]),
-                       __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
-            } else {
+            for (int j = 0; j < 8; ++j)
+              sts128(stg_row + (((uint32_t)j ^ ((uint32_t)lane & 7u)) << 4), __float_as_uint(v[4 * j]),
+                     __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+            if (sidx + 1 < nsub) tmem_ld_32x32_issue(t0 + sub_col(sidx + 1), v);
+          } else {
+            uint32_t pk[16];
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                sts128(stg_row + (((uint32_t)(sub * 4 + j) ^ ((uint32_t)lane & 7u)) << 4),
-                       pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                       pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+            for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            if (sidx + 1 < nsub) tmem_ld_32x32_issue(t0 + sub_col(sidx + 1), v);
+            if (sub == 0) {
+              if (lane == 0) tma_store_wait_read();
+              __syncwarp();
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              sts128(stg_row + (((uint32_t)(sub * 4 + j) ^ ((uint32_t)lane & 7u)) << 4), pk[4 * j], pk[4 * j + 1],
+                     pk[4 * j + 2], pk[4 * j + 3]);
           }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            if (reduce_add) tma_reduce_add_4d(&mapOut, stg, n0 + cblk, m0 + q * 32, b, g);
-            else tma_store_4d(&mapOut, stg, n0 + cblk, m0 + q * 32, b, g);   // rows >= M are clipped by the tensor map
-            tma_store_commit();
+          if (f32 || sub == 1) {
+            const int cblk = f32 ? c : c - 32;
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              if (reduce_add) tma_reduce_add_4d(&mapOut, stg, n0 + cblk, m0 + q * 32, b, g);
+              else tma_store_4d(&mapOut, stg, n0 + cblk, m0 + q * 32, b, g);   // rows >= M are clipped by the tensor map
+              tma_store_commit();
+            }
           }
         }
       } else {

@@ -13,6 +13,8 @@
 // weight-ring latency (12 x 6 KB in flight is less than latency x consumption rate).  So one unit is now
 // (TWO coalitions, group, 256-frame chunk): every weight slice feeds 4 accumulators (2 coalitions x 2 row halves),
 // the ring is as deep as shared memory allows (120 KB in flight) and the weight traffic out of L2 halves.
+// A ring stage holds up to 8 taps (one full/empty barrier round trip per stage: ~300 cycles that the MMA queue does
+// not hide when it is paid per tap; measured 10.3 / 8.7 / 7.9 / 7.5 ms per C2 step for 1 / 2 / 4 / 8 taps per stage).
 #include "gemm.cuh"
 #include "gemm_epi.cuh"
 #include "kernels.cuh"
@@ -21,6 +23,7 @@ namespace w2s {
 
 struct PosConvDev {
   int T, cpg, G, B, kpos, chunks, num_units;
+  int tps;   // taps per ring stage (divides kpos): one barrier round trip per tps weight slices
   EpiParams epi;
 };
 
@@ -86,15 +89,17 @@ posconv_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
 
   if (warp == 8) {
     if (lane == 0) {   // weight slices: one stream across units, never blocked by the windows
+      const int nws = WS / p.tps * p.tps;
       int ws = 0;
       uint32_t wphase = 0;
       for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
         const int g = (unit / p.chunks) % p.G;
-        for (int j = 0; j < p.kpos; ++j) {
+        for (int j = 0; j < p.kpos; j += p.tps) {
           mbar_wait(wempty(ws), wphase ^ 1u);
-          mbar_expect_tx(wfull(ws), C::W_BYTES);
-          tma_load_3d(sW + ws * C::W_BYTES, &mapW, wfull(ws), j * 64, 0, g);
-          if (++ws == WS) {
+          mbar_expect_tx(wfull(ws), C::W_BYTES * p.tps);
+          for (int tt = 0; tt < p.tps; ++tt)
+            tma_load_3d(sW + (ws + tt) * C::W_BYTES, &mapW, wfull(ws), (j + tt) * 64, 0, g);
+          if ((ws += p.tps) >= nws) {
             ws = 0;
             wphase ^= 1u;
           }
@@ -119,6 +124,7 @@ posconv_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, NG);
       constexpr int KSTEPS = NG / 16;   // channels beyond NG are zero padding in both operands
+      const int nws = WS / p.tps * p.tps;
       int ws = 0;
       uint32_t wphase = 0;
       int it = 0;
@@ -127,20 +133,24 @@ posconv_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
         mbar_wait(tempty(abuf), (((uint32_t)it >> 1) & 1u) ^ 1u);
         mbar_wait(winfull, (uint32_t)it & 1u);
         tc_fence_after();
-        for (int j = 0; j < p.kpos; ++j) {
+        for (int j0 = 0; j0 < p.kpos; j0 += p.tps) {
           mbar_wait(wfull(ws), wphase);
           tc_fence_after();
-          const uint64_t dw = umma_desc_sw128(sW + ws * C::W_BYTES);
+          for (int tt = 0; tt < p.tps; ++tt) {
+            const int j = j0 + tt;
+            const uint64_t dw = umma_desc_sw128(sW + (ws + tt) * C::W_BYTES);
 #pragma unroll
-          for (int uh = 0; uh < 4; ++uh) {
-            // coalition uh / 2, output rows [128 (uh % 2), + 128): tap j reads window rows 128 (uh % 2) + j ...
-            const uint64_t da = umma_desc_sw128(sWin + (uint32_t)(uh >> 1) * PC_WIN_BYTES + (uint32_t)((uh & 1) * 128 + j) * 128u);
+            for (int uh = 0; uh < 4; ++uh) {
+              // coalition uh / 2, output rows [128 (uh % 2), + 128): tap j reads window rows 128 (uh % 2) + j ...
+              const uint64_t da =
+                  umma_desc_sw128(sWin + (uint32_t)(uh >> 1) * PC_WIN_BYTES + (uint32_t)((uh & 1) * 128 + j) * 128u);
 #pragma unroll
-            for (int k = 0; k < KSTEPS; ++k)
-              umma_bf16(tmem_base + abuf * 256 + uh * 64, da + 2u * k, dw + 2u * k, idesc, (j | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < KSTEPS; ++k)
+                umma_bf16(tmem_base + abuf * 256 + uh * 64, da + 2u * k, dw + 2u * k, idesc, (j | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(wempty(ws));
-          if (++ws == WS) {
+          if ((ws += p.tps) >= nws) {
             ws = 0;
             wphase ^= 1u;
           }
@@ -212,6 +222,14 @@ std::string posconv_prepare(const __nv_bfloat16* x, const __nv_bfloat16* w, int 
   const int cpg = H / G;
   pl->ng = cpg;
   pl->dev.T = T; pl->dev.cpg = cpg; pl->dev.G = G; pl->dev.B = B; pl->dev.kpos = kpos;
+  {
+    const char* e = getenv("W2S_PC_TPS");
+    int tps = e ? atoi(e) : 8;
+    if (tps < 1 || tps > 8) tps = 8;
+    const int slots = cpg == 64 ? PcCfg<64>::WSTAGES : PcCfg<48>::WSTAGES;
+    while (tps > 1 && (kpos % tps || slots / tps < 2)) --tps;
+    pl->dev.tps = tps;
+  }
   pl->dev.chunks = (T + 255) / 256;
   pl->dev.num_units = pl->dev.chunks * G * ((B + 1) / 2);   // a unit covers two coalitions
   pl->dev.epi = epi;
