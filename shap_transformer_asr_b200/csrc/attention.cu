@@ -159,7 +159,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int row = qd * 32 + lane;  // query row inside the tile == TMEM lane
 
-  if (threadIdx.x == 0) {
+  if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&mapQ);
     tma_prefetch_desc(&mapK);
     tma_prefetch_desc(&mapV);
@@ -180,7 +180,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   const uint32_t sV = base + p.sv_off;
 
   // ---- loads ---------------------------------------------------------------------------------------
-  if (threadIdx.x == 0) {
+  if (warp == 0 && elect_one()) {
     // Q and K gate the score MMAs; V is only needed for P V, so it lands behind the softmax on its own barrier
     mbar_expect_tx(bar_load, 16384u + (p.n1 > 0 ? 65536u : 32768u));
     tma_load_4d(base + ATT_SQ, &mapQ, bar_load, 0, qt * 128, h, b);
@@ -283,7 +283,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (warp == 0 && elect_one()) {
       if (r0 == 0) mbar_wait(bar_v, 0);
       tc_fence_after();
       constexpr uint32_t idesc = umma_idesc_bf16_bmn(128, 64);
@@ -442,7 +442,7 @@ attention_rel_kernel(const __grid_constant__ CUtensorMap mapQU, const __grid_con
   const int row = qd * 32 + lane;
   float* stg = reinterpret_cast<float*>(base_ptr + REL_STG) + warp * 32 * REL_STG_STRIDE + lane * REL_STG_STRIDE;
 
-  if (threadIdx.x == 0) {
+  if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&mapQU);
     tma_prefetch_desc(&mapK);
     tma_prefetch_desc(&mapV);
@@ -463,7 +463,7 @@ attention_rel_kernel(const __grid_constant__ CUtensorMap mapQU, const __grid_con
   pdl_trigger();
   pdl_wait();
 
-  if (threadIdx.x == 0) {
+  if (warp == 0 && elect_one()) {
     mbar_expect_tx(bar_q, 32768);
     tma_load_4d(base + REL_QU, &mapQU, bar_q, 0, qt * 128, h, b);
     tma_load_4d(base + REL_QV, &mapQV, bar_q, 0, qt * 128, h, b);
@@ -473,7 +473,7 @@ attention_rel_kernel(const __grid_constant__ CUtensorMap mapQU, const __grid_con
   float l_h[2] = {0.f, 0.f};
   for (int hk = 0; hk < p.nh; ++hk) {
     const int j0 = hk * 128;
-    if (threadIdx.x == 0) {
+    if (warp == 0 && elect_one()) {
       if (hk > 0) mbar_wait(bar_pv, (hk - 1) & 1);  // previous P V has finished reading V and P
       mbar_expect_tx(bar_load, 16384 + 16384 + 32768);
       tma_load_4d(base + REL_K, &mapK, bar_load, 0, j0, h, b);
@@ -544,7 +544,7 @@ attention_rel_kernel(const __grid_constant__ CUtensorMap mapQU, const __grid_con
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();   // also orders the s_red reads above before the next half overwrites it
-    if (threadIdx.x == 0) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
       constexpr uint32_t idesc = umma_idesc_bf16_bmn(128, 64);
       for (int kb = 0; kb < 2; ++kb) {

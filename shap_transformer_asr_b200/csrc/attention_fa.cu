@@ -4,7 +4,7 @@
 // every block keeps its own softmax maximum m_j, partial sum l_j and its own O_j accumulator in TMEM (4 x 64
 // columns), and the epilogue merges them,  out = sum_j a_j O_j / sum_j a_j l_j,  a_j = exp(m_j - max_j m_j),
 // so nothing is ever rescaled in TMEM and the three engines run decoupled:
-//   warp 8  (TMA)     Q tile per item (double-buffered), {K_j, V_j} through a 3-stage ring
+//   warp 8  (TMA)     Q tile per item (double-buffered), K_j through a 3-stage and V_j through a 4-stage ring
 //   warp 9  (MMA)     S_j = Q K_j^T into one of two S buffers (128 fp32 columns each), O_j = P_j V_j one block behind
 //   warps 0-7 (softmax) two groups of four warps, group g takes the blocks with running index g (mod 2): one thread per
 //                     query row reads S_j from TMEM, writes P_j = exp(S_j - m_j) as bf16 into the group's swizzled smem
@@ -26,10 +26,14 @@ struct AttnFaPlan {
   int nb, grid;
 };
 
-constexpr int FA_KVS = 3;
-constexpr int FA_SQ = 0, FA_SKV = 2 * 16384, FA_SP = FA_SKV + FA_KVS * 32768, FA_RED = FA_SP + 2 * 32768,
-              FA_BAR = FA_RED + 2 * (4 * 4 * 128 * 4);
-constexpr size_t FA_SMEM = FA_BAR + 256 + 1024;
+// K and V travel through separate rings.  A K block is dead as soon as its score MMAs have run, a V block lives until
+// the softmax of its block is done; with one {K, V} ring a stage was recycled only after P V, and the ~3000-cycle
+// TMA round trip of the next load then sat on the critical path (measured with clock64 stamps: the MMA thread waited
+// for K/V about a third of every item).
+constexpr int FA_KS = 3, FA_VS = 4;
+constexpr int FA_SQ = 0, FA_SK = 2 * 16384, FA_SV = FA_SK + FA_KS * 16384, FA_SP = FA_SV + FA_VS * 16384,
+              FA_RED = FA_SP + 2 * 32768, FA_BAR = FA_RED + 2 * (4 * 4 * 128 * 4);
+constexpr size_t FA_SMEM = FA_BAR + 512 + 1024;
 
 __device__ __forceinline__ uint64_t fa_desc_mn(uint32_t a) { return umma_desc_sw128(a); }
 
@@ -44,19 +48,21 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   float* s_m = reinterpret_cast<float*>(base_ptr + FA_RED);               // [item mod 4][4][128] block maxima
   float* s_l = s_m + 4 * 4 * 128;                                          // [item mod 4][4][128] block sums
   const uint32_t bars = base + FA_BAR;
-  auto kv_full = [&](int s) { return bars + 8u * s; };
-  auto kv_empty = [&](int s) { return bars + 24 + 8u * s; };
-  auto s_full = [&](int i) { return bars + 48 + 8u * i; };
-  auto s_empty = [&](int i) { return bars + 64 + 8u * i; };
-  auto p_full = [&](int i) { return bars + 80 + 8u * i; };
-  auto p_empty = [&](int i) { return bars + 96 + 8u * i; };
-  auto q_full = [&](int i) { return bars + 112 + 8u * i; };
-  auto q_empty = [&](int i) { return bars + 128 + 8u * i; };
-  auto o_full = [&](int i) { return bars + 144 + 8u * i; };
-  auto o_empty = [&](int i) { return bars + 160 + 8u * i; };
-  auto ml_full = [&](int i) { return bars + 176 + 8u * i; };
-  const uint32_t tmem_slot = bars + 208;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + FA_BAR + 208);
+  auto k_full = [&](int s) { return bars + 8u * s; };
+  auto k_empty = [&](int s) { return bars + 24 + 8u * s; };
+  auto v_full = [&](int s) { return bars + 48 + 8u * s; };
+  auto v_empty = [&](int s) { return bars + 80 + 8u * s; };
+  auto s_full = [&](int i) { return bars + 112 + 8u * i; };
+  auto s_empty = [&](int i) { return bars + 128 + 8u * i; };
+  auto p_full = [&](int i) { return bars + 144 + 8u * i; };
+  auto p_empty = [&](int i) { return bars + 160 + 8u * i; };
+  auto q_full = [&](int i) { return bars + 176 + 8u * i; };
+  auto q_empty = [&](int i) { return bars + 192 + 8u * i; };
+  auto o_full = [&](int i) { return bars + 208 + 8u * i; };
+  auto o_empty = [&](int i) { return bars + 224 + 8u * i; };
+  auto ml_full = [&](int i) { return bars + 240 + 8u * i; };
+  const uint32_t tmem_slot = bars + 272;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + FA_BAR + 272);
   // With at most two key blocks per item the O accumulators (NB x 64 columns) fit twice next to the two S buffers:
   // the P V MMAs of item i+1 then never wait for the merge of item i.
   constexpr int OB = NB <= 2 ? 2 : 1;
@@ -68,9 +74,13 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     tma_prefetch_desc(&mapV);
   }
   if (warp == 9 && lane == 0) {
-    for (int s = 0; s < FA_KVS; ++s) {
-      mbar_init(kv_full(s), 1);
-      mbar_init(kv_empty(s), 1);
+    for (int s = 0; s < FA_KS; ++s) {
+      mbar_init(k_full(s), 1);
+      mbar_init(k_empty(s), 1);
+    }
+    for (int s = 0; s < FA_VS; ++s) {
+      mbar_init(v_full(s), 1);
+      mbar_init(v_empty(s), 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(q_full(i), 1);
@@ -99,7 +109,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   pdl_wait();
 
   if (warp == 8) {
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t kvc = 0;
       int it = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
@@ -110,71 +120,77 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         tma_load_4d(base + FA_SQ + (it & 1) * 16384, &mapQ, q_full(it & 1), 0, qt * 128, h, b);
 #pragma unroll 1
         for (int j = 0; j < NB; ++j, ++kvc) {
-          const int s = kvc % FA_KVS;
-          mbar_wait(kv_empty(s), ((kvc / FA_KVS) & 1u) ^ 1u);
-          mbar_expect_tx(kv_full(s), 32768);
-          tma_load_4d(base + FA_SKV + s * 32768, &mapK, kv_full(s), 0, j * 128, h, b);
-          tma_load_4d(base + FA_SKV + s * 32768 + 16384, &mapV, kv_full(s), 0, j * 128, h, b);
+          const int ks = kvc % FA_KS, vs = kvc % FA_VS;
+          mbar_wait(k_empty(ks), ((kvc / FA_KS) & 1u) ^ 1u);
+          mbar_expect_tx(k_full(ks), 16384);
+          tma_load_4d(base + FA_SK + ks * 16384, &mapK, k_full(ks), 0, j * 128, h, b);
+          mbar_wait(v_empty(vs), ((kvc / FA_VS) & 1u) ^ 1u);
+          mbar_expect_tx(v_full(vs), 16384);
+          tma_load_4d(base + FA_SV + vs * 16384, &mapV, v_full(vs), 0, j * 128, h, b);
         }
       }
     }
   } else if (warp == 9) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(128, 128);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64) | (1u << 16);   // B operand (V) is MN-major
       uint32_t kvc = 0, sc = 0, pc = 0;
       int it = 0;
-      auto issue_pv = [&](int jj, int stage, int it_) {
+      auto issue_pv = [&](int jj, uint32_t blk, int it_) {
+        const int vs = blk % FA_VS;
         const int pb = pc & 1;
         // the O accumulators are overwritten from the first P V of an item on: only then must the previous item's merge
         // have drained them (waiting here instead of before the score MMAs lets S_0 / S_1 of the next item be computed
         // while the softmax warps still finish the previous one)
         const int ob = it_ % OB;
         if (jj == 0) mbar_wait(o_empty(ob), ((uint32_t)(it_ / OB) & 1u) ^ 1u);
+        mbar_wait(v_full(vs), (blk / FA_VS) & 1u);
         mbar_wait(p_full(pb), (pc >> 1) & 1u);
         tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
           const uint64_t dp = umma_desc_sw128(base + FA_SP + pb * 32768 + kb * 16384);
-          const uint64_t dv = fa_desc_mn(base + FA_SKV + stage * 32768 + 16384 + kb * 8192);
+          const uint64_t dv = fa_desc_mn(base + FA_SV + vs * 16384 + kb * 8192);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16(tmem + 256 + 128 * ob + 64 * jj, dp + 2u * k, dv + 128u * k, idesc_pv, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(p_empty(pb));
-        umma_commit(kv_empty(stage));
+        umma_commit(v_empty(vs));
         ++pc;
       };
       // Blocks form ONE stream across items: S_g is issued, then P V of block g-1 -- also across an item boundary, so the
       // first score block of the next item is already in TMEM when the softmax warps finish the previous item.
       bool pending = false;
-      int pend_j = 0, pend_stage = 0, pend_it = 0;
+      int pend_j = 0, pend_it = 0;
+      uint32_t pend_blk = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++it) {
         mbar_wait(q_full(it & 1), (uint32_t)(it >> 1) & 1u);
 #pragma unroll 1
         for (int j = 0; j < NB; ++j, ++kvc, ++sc) {
-          const int s = kvc % FA_KVS, sb = sc & 1;
-          mbar_wait(kv_full(s), (kvc / FA_KVS) & 1u);
+          const int ks = kvc % FA_KS, sb = sc & 1;
+          mbar_wait(k_full(ks), (kvc / FA_KS) & 1u);
           mbar_wait(s_empty(sb), ((sc >> 1) & 1u) ^ 1u);
           tc_fence_after();
           const uint64_t dq = umma_desc_sw128(base + FA_SQ + (it & 1) * 16384);
-          const uint64_t dk = umma_desc_sw128(base + FA_SKV + s * 32768);
+          const uint64_t dk = umma_desc_sw128(base + FA_SK + ks * 16384);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(tmem + sb * 128, dq + 2u * k, dk + 2u * k, idesc_qk, k != 0 ? 1u : 0u);
           umma_commit(s_full(sb));
+          umma_commit(k_empty(ks));
           if (j == NB - 1) umma_commit(q_empty(it & 1));
           if (pending) {
-            issue_pv(pend_j, pend_stage, pend_it);
+            issue_pv(pend_j, pend_blk, pend_it);
             if (pend_j == NB - 1) umma_commit(o_full(pend_it % OB));
           }
           pending = true;
           pend_j = j;
-          pend_stage = s;
+          pend_blk = kvc;
           pend_it = it;
         }
       }
       if (pending) {
-        issue_pv(pend_j, pend_stage, pend_it);
+        issue_pv(pend_j, pend_blk, pend_it);
         umma_commit(o_full(pend_it % OB));
       }
     }

@@ -343,6 +343,19 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One lane of a CONVERGED warp (all 32 lanes must execute this).  Code that issues tcgen05.mma / tcgen05.commit has to
+// sit under this predicate and not under `lane == 0`: for a lane-id branch ptxas cannot prove that a single thread is
+// active and wraps every UTCHMMA / UTCBAR in an ELECT + BRA.U.ANY loop (~50-80 cycles of issue time per instruction,
+// which made the MMA-issuing thread the bottleneck of the attention and positional-conv kernels).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // mbarrier arrives once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)

@@ -106,7 +106,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   pdl_wait();
 
   if (warp == 8) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int unit = unit0; unit < p.num_units; unit += unit_step) {
@@ -133,7 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
   } else if (warp == 9) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
       int stage = 0;
       uint32_t phase = 0;

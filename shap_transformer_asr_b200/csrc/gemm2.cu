@@ -80,7 +80,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   pdl_wait();      // operands and residuals of this kernel come from its predecessors
 
   if (warp == 8) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int unit = unit0; unit < p.num_units; unit += unit_step) {
@@ -109,7 +109,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       }
     }
   } else if (warp == 9) {
-    if (lane == 0 && leader) {
+    if (leader && elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -140,6 +140,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
   } else if (warp < 8) {
     const int q = warp & 3, hsel = warp >> 2;
+    const bool lead = elect_one();   // the lane that owns this warp's TMA-store bulk groups
     const uint32_t stg = epi_smem + warp * 4096;              // this warp's 32 rows x 128 B staging strip
     const uint32_t stg_row = stg + lane * 128;
     float* sbias = reinterpret_cast<float*>(tiles_ptr + C::STAGES * C::STAGE_BYTES + 8 * 4096 + warp * 512);
@@ -187,7 +188,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           tmem_ld_wait();
           epi_math32(p.epi, p.epi.bias ? sbias + sidx * 32 : nullptr, p.N, g, b, m, n0 + c, row_ok, v, reduce_add);
           if (f32) {
-            if (lane == 0) tma_store_wait_read();   // the previous store of this warp has drained the strip
+            if (lead) tma_store_wait_read();   // the previous store of this warp has drained the strip
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -200,7 +201,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
             if (sidx + 1 < nsub) tmem_ld_32x32_issue(t0 + sub_col(sidx + 1), v);
             if (sub == 0) {
-              if (lane == 0) tma_store_wait_read();
+              if (lead) tma_store_wait_read();
               __syncwarp();
             }
 #pragma unroll
@@ -212,7 +213,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             const int cblk = f32 ? c : c - 32;
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
+            if (lead) {
               if (reduce_add) tma_reduce_add_4d(&mapOut, stg, n0 + cblk, m0 + q * 32, b, g);
               else tma_store_4d(&mapOut, stg, n0 + cblk, m0 + q * 32, b, g);   // rows >= M are clipped by the tensor map
               tma_store_commit();
@@ -238,7 +239,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
-    if (tma_out && lane == 0) tma_store_wait_all();   // global writes complete before the CTA retires
+    if (tma_out && lead) tma_store_wait_all();   // global writes complete before the CTA retires
   }
 
   tc_fence_before();

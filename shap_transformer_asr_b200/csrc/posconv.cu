@@ -88,7 +88,7 @@ posconv_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
   pdl_wait();
 
   if (warp == 8) {
-    if (lane == 0) {   // weight slices: one stream across units, never blocked by the windows
+    if (elect_one()) {   // weight slices: one stream across units, never blocked by the windows
       const int nws = WS / p.tps * p.tps;
       int ws = 0;
       uint32_t wphase = 0;
@@ -107,7 +107,7 @@ posconv_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
       }
     }
   } else if (warp == 11) {
-    if (lane == 0) {   // the two windows of a unit
+    if (elect_one()) {   // the two windows of a unit
       int it = 0;
       for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
         const int ch = unit % p.chunks;
@@ -121,7 +121,7 @@ posconv_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
       }
     }
   } else if (warp == 9) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, NG);
       constexpr int KSTEPS = NG / 16;   // channels beyond NG are zero padding in both operands
       const int nws = WS / p.tps * p.tps;
