@@ -246,7 +246,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         a_j[j] = ex2_approx((pm[j * 128] - m) * p.scale_log2e);
         L = fmaf(a_j[j], pl[j * 128], L);
       }
-      const float inv = 1.0f / L;
+      const float inv = rcp_approx(L);
       mbar_wait(o_full(ob), (uint32_t)(it_ / OB) & 1u);
       tc_fence_after();
       float o[32];
@@ -347,14 +347,22 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         pl[j * 128] = acc2.x + acc2.y;
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_full(grp));
+        if (lane == 0) {
+          mbar_arrive(p_full(grp));
+          // last block of this group in the item: its (m_j, l_j) are published -- before the deferred merge below, so the
+          // other group's merge of this item never waits for ours of the previous one
+          if (j + 2 >= NB) mbar_arrive(ml_full(it & 3));
+        }
         if (pend) {
           merge(pend_item, pend_it);
           pend = false;
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(ml_full(it & 3));   // this warp's (m_j, l_j) of the item are published
+      // (a group without a block in this item -- NB == 1 -- still has to arrive)
+      if (NB == 1 && (((cblk - 1u) & 1u) != (uint32_t)grp)) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ml_full(it & 3));
+      }
       if (pend) merge(pend_item, pend_it);
       pend = true;
       pend_item = item;
