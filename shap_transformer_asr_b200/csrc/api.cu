@@ -168,7 +168,6 @@ struct WeightTable {
     *out = it->second.first;
     return "";
   }
-  bool has(const std::string& name) const { return t.count(name) != 0; }
 };
 
 std::string copy_f32(w2s_handle* h, const WeightTable& wt, const std::string& name, int64_t n, float** dst) {

@@ -75,3 +75,17 @@ def test_product_package_never_imports_the_oracle():
     body = bench[bench.index("def run_b200"):bench.index("def main")]
     uses = [m.start() for m in re.finditer(r"from oracle", body)]
     assert len(uses) == 1 and "CPU baseline" in body[uses[0] - 400:uses[0]]     # only inside the cpu_baseline leg
+
+
+def test_hot_kernels_are_tcgen05_tma_code_issued_without_elect_loops(lib):
+    """The shipped SASS is sm_100a tensor-core / TMA code (not a CUDA-core fallback), and no tcgen05 / TMA instruction
+    sits in the ELECT + BRA.U.ANY loop ptxas emits when such code is guarded by `lane == 0` instead of elect.sync."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass or "SM100a" in sass or "sm_100" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "UTMAREDG", "LDTM", "HMMA"):
+        assert mnemonic in sass, f"{mnemonic} missing from libw2s.so"
+    assert sass.count("BRA.U.ANY") == 0
