@@ -47,6 +47,14 @@ def ncu_traffic(workload):
     if workload != "C2" or not os.path.exists(p):
         return None
     d = json.load(open(p))
+    return d["mean_traffic_bytes_per_launch"]
+
+
+def ncu_traffic_detail(workload):
+    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if workload != "C2" or not os.path.exists(p):
+        return None
+    d = json.load(open(p))
     return {"dram_bytes_per_launch": d["mean_traffic_bytes_per_launch"],
             "algorithmic_bytes_per_launch": d["mean_algorithmic_bytes_per_launch"], "source": "profiles/r01_ncu_traffic.json"}
 
@@ -326,7 +334,8 @@ def run_b200(args):
         "gpu_launches": int(args.steps * (n_batches * launches_per_batch + 1)),
         "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (all contraction launches)", "achieved": achieved,
                      "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
-                     "traffic": ncu_traffic(wl.name), "peak_source": peaks["source"] + " bf16_tflops_sustained",
+                     "traffic": ncu_traffic(wl.name), "traffic_detail": ncu_traffic_detail(wl.name),
+                     "peak_source": peaks["source"] + " bf16_tflops_sustained",
                      "launches": int(gemm_n), "share_of_step": gemm_ms / total_prof_ms,
                      "profiled_ms_per_step": prof_ms / args.steps,
                      "whole_step_tflops": value * flops_fwd / 1e12 / world},
