@@ -638,6 +638,11 @@ struct PlanBuilder {
     }
     const int act = c.hidden_act == 1 ? ACT_SWISH : ACT_GELU;
     const bool ln_res = !stable && (H == 128 || H == 256 || H == 512 || H == 768 || H == 1024);
+    // Opt-in experiment (not measured yet, default off): post-LN models write the pre-LayerNorm tensor of out_proj / ffn2
+    // as bf16 instead of fp32 -- halves the traffic of the one HBM-bound contraction and of both LayerNorms at the price
+    // of one more bf16 rounding per sub-layer.
+    static const bool bf16_preln = getenv("W2S_BF16_PRELN") != nullptr;
+    const int pre32 = (bf16_preln && ln_res) ? 0 : 1;
     for (int l = 0; l < c.num_hidden_layers; ++l) {
       const LayerW& w = h->layers[l];
       const std::string ls = "L" + std::to_string(l) + ".";
@@ -659,11 +664,11 @@ struct PlanBuilder {
           p.epi.residual = stable ? (const void*)h->pre : (const void*)h->hb;
           p.epi.res_fp32 = stable ? 1 : 0;
         }
-        p.epi.out = h->pre; p.epi.out_fp32 = 1;
+        p.epi.out = h->pre; p.epi.out_fp32 = pre32;
         W2S_TRY(add_gemm(ls + "out_proj", p));
       }
       if (stable) add_ln(ls + "ln2", h->pre, 1, rows, H, w.ln2_g, w.ln2_b, c.layer_norm_eps, ACT_NONE, h->h1, nullptr);
-      else add_ln(ls + "ln1", h->pre, 1, rows, H, w.ln1_g, w.ln1_b, c.layer_norm_eps, ACT_NONE, h->h1, nullptr,
+      else add_ln(ls + "ln1", h->pre, pre32, rows, H, w.ln1_g, w.ln1_b, c.layer_norm_eps, ACT_NONE, h->h1, nullptr,
                   ln_res ? h->hb : nullptr);
       {
         GemmProblem p = plain(h->h1, rows, H, w.w1, I);
@@ -678,10 +683,10 @@ struct PlanBuilder {
           p.epi.residual = stable ? (const void*)h->pre : (const void*)h->h1;
           p.epi.res_fp32 = stable ? 1 : 0;
         }
-        p.epi.out = h->pre; p.epi.out_fp32 = 1;
+        p.epi.out = h->pre; p.epi.out_fp32 = pre32;
         W2S_TRY(add_gemm(ls + "ffn2", p));
       }
-      if (!stable) add_ln(ls + "ln2", h->pre, 1, rows, H, w.ln2_g, w.ln2_b, c.layer_norm_eps, ACT_NONE, h->hb, nullptr,
+      if (!stable) add_ln(ls + "ln2", h->pre, pre32, rows, H, w.ln2_g, w.ln2_b, c.layer_norm_eps, ACT_NONE, h->hb, nullptr,
                           ln_res ? h->h1 : nullptr);
     }
     if (stable)
