@@ -80,7 +80,10 @@ def sample_coalitions(M: int, nsamples="auto", seed: Optional[int] = None):
         ind_set = np.random.choice(len(rem), 4 * samples_left, p=rem)
         pos = 0
         seen = {}
+        # rows are collected as (index in Z, permutation prefix, complement flag) and written in one vectorised pass at
+        # the end; the RNG call sequence (one permutation per draw) is exactly shap's
         row = np.zeros(M, dtype=np.uint8)
+        new_at, new_rows, comp_at = [], [], []
         while samples_left > 0 and pos < len(ind_set):
             size = int(ind_set[pos]) + n_full + 1
             pos += 1
@@ -92,7 +95,8 @@ def sample_coalitions(M: int, nsamples="auto", seed: Optional[int] = None):
             if fresh:
                 seen[key] = added
                 samples_left -= 1
-                Z[added] = row
+                new_at.append(added)
+                new_rows.append(key)
                 kw[added] = 1.0
                 added += 1
             else:
@@ -100,11 +104,17 @@ def sample_coalitions(M: int, nsamples="auto", seed: Optional[int] = None):
             if samples_left > 0 and size <= n_paired:
                 if fresh:
                     samples_left -= 1
-                    Z[added] = 1 - row
+                    comp_at.append((added, len(new_rows) - 1))
                     kw[added] = 1.0
                     added += 1
                 else:
                     kw[at + 1] += 1.0
+        if new_rows:
+            R = np.frombuffer(b"".join(new_rows), dtype=np.uint8).reshape(len(new_rows), M)
+            Z[np.asarray(new_at)] = R
+            if comp_at:
+                ca = np.asarray(comp_at)
+                Z[ca[:, 0]] = 1 - R[ca[:, 1]]
         weight_left = np.sum(wv[n_full:])
         kw[n_fixed:] *= weight_left / kw[n_fixed:].sum()
     info = dict(nsamples=nsamples, n_fixed=n_fixed, n_full_sizes=n_full, max_samples=max_samples)
