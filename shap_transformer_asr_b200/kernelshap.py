@@ -148,13 +148,25 @@ class KernelShapExplainer:
         if mode in ("max", "mean", "logits"):
             frames, tokens = (), ()
             eng.set_targets(mode)
+        M = eng.num_segments
+        Z = None
+        if mode in ("max", "mean", "logits"):
+            pass
         elif targets is None:
-            frames, tokens, _ = self.select_targets(mode)
+            # the one-row target-selection forward is asynchronous on the engine's stream: draw the coalitions on the
+            # host while it runs, read the logits back afterwards
+            eng.set_targets("logits")
+            ones = eng.bits_to_device(np.ones((1, M), dtype=np.uint8))
+            logits_dev = eng.eval_bits(ones)
+            Z, kw, info = sample_coalitions(M, self.nsamples, seed=self.seed)
+            logits = logits_dev.view(-1, eng.config.vocab_size).cpu().numpy()
+            frames, tokens = char_targets(logits)
+            eng.set_targets(mode, frames, tokens)
         else:
             frames, tokens = targets
             eng.set_targets(mode, frames, tokens)
-        M = eng.num_segments
-        Z, kw, info = sample_coalitions(M, self.nsamples, seed=self.seed)
+        if Z is None:
+            Z, kw, info = sample_coalitions(M, self.nsamples, seed=self.seed)
         K = Z.shape[0]
         # rows 0/1 of the evaluated matrix are the empty and the full coalition (fnull, fx)
         Zall = np.concatenate([np.zeros((1, M), np.uint8), np.ones((1, M), np.uint8), Z])

@@ -5,6 +5,7 @@ import os
 
 import numpy as np
 import pytest
+import torch
 
 from oracle.kernelshap_ref import KernelExplainerRef, brute_force_shapley
 from shap_transformer_asr_b200.kernelshap import expand_to_samples, sample_coalitions
@@ -98,3 +99,69 @@ def test_expand_to_samples_layout():
     assert out.shape == (1, 6, 2) and out[0, :, 0].tolist() == [0, 0, 2, 4, 4, 4]
     per = expand_to_samples(phi, b, per_sample=True)
     assert np.allclose(per[0].sum(0), phi.sum(0))
+
+
+class _MockEngine:
+    """CPU stand-in with the Engine surface KernelShapExplainer.explain uses: an additive game over M segments
+    (output d of a coalition = bias_d + sum of the kept segments' weights), so the Shapley values are the weights."""
+
+    def __init__(self, M, D, vocab=8, frames=6):
+        import types
+        rng = np.random.default_rng(7)
+        self.num_segments = M
+        self.device = torch.device("cpu")
+        self.config = types.SimpleNamespace(vocab_size=vocab)
+        self.W = rng.standard_normal((M, D))
+        self.bias = rng.standard_normal(D)
+        self.logit_table = rng.standard_normal((frames, vocab))
+        self.mode, self.sel = None, None
+        self.calls = []
+
+    def set_clip(self, clip, num_segments, baseline=0.0):
+        assert num_segments == self.num_segments
+        self.calls.append("set_clip")
+
+    def set_targets(self, mode, frames=None, tokens=None):
+        self.mode = mode
+        self.sel = None if frames is None else (np.asarray(frames), np.asarray(tokens))
+        self.calls.append(f"set_targets:{mode}")
+
+    def out_width(self):
+        return self.logit_table.size if self.mode == "logits" else self.W.shape[1]
+
+    def bits_to_device(self, Z):
+        from shap_transformer_asr_b200.preprocess import pack_coalitions
+        return torch.from_numpy(pack_coalitions(Z).view(np.int32))
+
+    def _unpack(self, bits):
+        w = bits.numpy().view(np.uint32)
+        return np.stack([(w[:, m // 32] >> (m % 32)) & 1 for m in range(self.num_segments)], 1).astype(np.float64)
+
+    def eval_bits(self, bits):
+        self.calls.append(f"eval:{self.mode}:{bits.shape[0]}")
+        if self.mode == "logits":
+            return torch.from_numpy(np.tile(self.logit_table.reshape(1, -1), (bits.shape[0], 1)).astype(np.float32))
+        return torch.from_numpy((self._unpack(bits) @ self.W + self.bias).astype(np.float32))
+
+    def wls(self, bits, w, y, fx, fnull, M):
+        ks = KernelExplainerRef(None, M)
+        ks.maskMatrix, ks.kernelWeights, ks.nsamplesAdded = self._unpack(bits), w.numpy(), bits.shape[0]
+        return torch.from_numpy(ks.solve(y.numpy(), fx.numpy(), fnull.numpy())), torch.zeros(1, dtype=torch.int32)
+
+
+@pytest.mark.parametrize("targets_given", [False, True])
+def test_explain_orchestration_on_a_mock_engine(targets_given):
+    """explain(): target selection (overlapped with the host sampler), evaluation of [empty, full, Z], device-solve call:
+    on an additive game the attributions are the segment weights, and the sampled rows are the seeded sampler's."""
+    from shap_transformer_asr_b200.kernelshap import KernelShapExplainer, sample_coalitions
+    M, D = 12, 5
+    eng = _MockEngine(M, D)
+    tg = (np.arange(D, dtype=np.int32), np.zeros(D, dtype=np.int32)) if targets_given else None
+    res = KernelShapExplainer(eng, nsamples=300, seed=3).explain(np.zeros(1000, np.float32), num_segments=M, targets=tg)
+    Z, kw, _ = sample_coalitions(M, 300, seed=3)
+    assert np.array_equal(res["Z"], Z) and np.array_equal(res["weights"], kw)
+    assert np.abs(res["phi"].numpy() - eng.W).max() < 1e-5
+    assert np.abs(res["fx"].numpy() - (eng.W.sum(0) + eng.bias)).max() < 1e-5
+    assert eng.calls[0] == "set_clip" and eng.calls[-1] == f"eval:logprob:{Z.shape[0] + 2}"
+    if not targets_given:
+        assert "eval:logits:1" in eng.calls and len(res["frames"]) > 0
