@@ -332,7 +332,7 @@ def run_b200(args):
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(cb.h2d_bytes), "d2h_bytes_per_step": int(cb.d2h_bytes)},
         "gpu_launches": int(args.steps * (n_batches * launches_per_batch + 1)),
-        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (all contraction launches)", "achieved": achieved,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc2_kernel<256> and the other contraction launches (gemm_tc_kernel, posconv_kernel)", "achieved": achieved,
                      "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
                      "traffic": ncu_traffic(wl.name), "traffic_detail": ncu_traffic_detail(wl.name),
                      "peak_source": peaks["source"] + " bf16_tflops_sustained",
