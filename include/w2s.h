@@ -38,8 +38,11 @@ enum {
 
 /* w2s_config.flags */
 enum {
-  W2S_FLAG_VALIDATE_GEMM = 1, /* run every contraction on the CUDA-core validation kernels (same bf16 data) */
-  W2S_FLAG_VALIDATE_ATTN = 2  /* run attention on the CUDA-core validation kernel                            */
+  W2S_FLAG_VALIDATE_GEMM = 1,  /* run every contraction on the CUDA-core validation kernels (same bf16 data) */
+  W2S_FLAG_VALIDATE_ATTN = 2,  /* run attention on the CUDA-core validation kernel                            */
+  W2S_FLAG_BF16_PRELN    = 4,  /* post-LN models: bf16 (instead of fp32) pre-LayerNorm tensors -- A/B measurement */
+  W2S_FLAG_PDL           = 8,  /* programmatic dependent launch between the kernels of a tile -- A/B measurement  */
+  W2S_FLAG_NO_GRAPH      = 16  /* launch the kernels of a tile one by one instead of replaying a CUDA graph        */
 };
 
 /* Mirrors transformers.Wav2Vec2Config / Wav2Vec2ConformerConfig (the objects the reference
@@ -93,9 +96,10 @@ int w2s_set_clip(w2s_handle* h, const float* x_dev, int64_t L, const int32_t* se
                  float baseline, void* stream);
 
 /* Replaces timestep_to_explain / token_id_to_explain (w2v2conformer.py:93-110) and the character-frame
- * list of visualization.py:319-327: D (frame, token) pairs (host arrays; ignored for MAX/MEAN/LOGITS). */
+ * list of visualization.py:319-327: D (frame, token) pairs (host arrays, copied before the call returns; ignored
+ * for MAX/MEAN/LOGITS).  The upload is ordered on `stream` behind evaluations already queued there. */
 int w2s_set_targets(w2s_handle* h, const int32_t* frame_idx_host, const int32_t* token_idx_host, int D,
-                    int mode);
+                    int mode, void* stream);
 
 /* Number of fp32 values one evaluated row produces under the current mode for clips of L samples. */
 int64_t w2s_out_width(const w2s_handle* h, int64_t num_samples);
@@ -116,15 +120,32 @@ int w2s_mask(w2s_handle* h, const uint32_t* z_bits_dev, int64_t K, float* out_de
 
 /* KernelSHAP constrained weighted least squares (shap KernelExplainer.solve with l1_reg=False; SURVEY.md
  * Appendix A step 6): z_bits[K, ceil(M/32)], kernel weights w[K] (fp64), y[K, D] fp32, fx[D], fnull[D]
- * (fp64) -> phi[M, D] fp64, all device pointers.  `status_dev` (int32, device, may be NULL) receives 0,
- * or 1 when the normal matrix is not positive definite. */
+ * (fp64) -> phi[M, D] fp64, all device pointers.  `status_dev` (int32, device, required) receives 0 when the
+ * normal matrix was factored by Cholesky; 2 when the design is rank deficient (fewer distinct coalitions than
+ * features, or a feature that never varies) and the minimum-norm least-squares solution was computed instead
+ * -- what shap's `solve` returns through its numpy.linalg.lstsq fallback -- by conjugate gradients on the device;
+ * 1 if that iteration did not converge (phi is then not to be used). */
 int w2s_wls(w2s_handle* h, const uint32_t* z_bits_dev, const double* w_dev, const float* y_dev, int64_t K,
             int M, int D, const double* fx_dev, const double* fnull_dev, double* phi_dev, int32_t* status_dev,
             void* stream);
 
+/* The random half of shap.KernelExplainer's coalition sampler (third-party, never called by the reference: SURVEY.md
+ * Appendix A step 4), on the HOST: for every entry of `ind_set` (the subset sizes drawn by np.random.choice) one
+ * legacy np.random.permutation(M) on the MT19937 state `mt_key[624]` / `*mt_pos` taken from np.random.get_state()
+ * (updated in place, to be handed back with np.random.set_state), de-duplicated rows appended to the bit-packed
+ * matrix z_words[cap_rows, ceil(M/32)] from row `added` on, with their hit counts in weights[] and the paired
+ * complement rows where shap adds them.  Returns the new row count, or -1 on a bad argument / overflow.
+ * No device is touched. */
+int64_t w2s_sample_rows(int M, int n_full, int n_paired, const int64_t* ind_set, int64_t n_ind,
+                        int64_t samples_left, int64_t added, uint32_t* mt_key, int32_t* mt_pos,
+                        uint32_t* z_words, double* weights, int64_t cap_rows, int64_t* ind_used);
+
 /* Test / profiling hooks for the individual kernels (used by tests/ and bench.py only). */
-int w2s_debug_gemm(int use_tcgen05, const void* a_bf16, const void* w_bf16, const float* bias, void* out,
-                   int M, int N, int K, int act, int out_fp32, void* stream);
+/* out[M, N] = act(a[M, K] w[N, K]^T + bias) * alpha + residual (residual == out with fp32 data: in-place
+ * accumulation, which the CTA-pair kernel performs with TMA reduce-add). */
+int w2s_debug_gemm(int use_tcgen05, const void* a_bf16, const void* w_bf16, const float* bias,
+                   const void* residual, int res_fp32, float alpha, void* out, int M, int N, int K, int act,
+                   int out_fp32, void* stream);
 /* Per-launch CUDA-event profile on the launching stream (bench.py roofline leg): enable, run evaluations,
  * then read per launch class (newline-separated names) total milliseconds, algorithmic FLOPs / bytes and
  * launch counts.  Returns the number of classes, or -1 if `names_cap` is too small. */
@@ -132,6 +153,9 @@ int w2s_profile_enable(w2s_handle* h, int on);
 int64_t w2s_profile_read(w2s_handle* h, char* names, int64_t names_cap, double* ms, double* flops, double* bytes,
                          int64_t* counts, int64_t max_entries);
 int w2s_kernel_count(const w2s_handle* h, int64_t* launches_per_batch, int64_t* batch_tile);
+/* kernel launches issued by w2s_eval / w2s_eval_waveforms on this handle since w2s_create (counted at launch,
+ * graph-replayed kernels included) */
+int64_t w2s_launch_count(const w2s_handle* h);
 /* algorithmic FLOPs (2*MAC) of one coalition forward for clips of L samples */
 double w2s_flops_per_forward(const w2s_handle* h, int64_t num_samples);
 

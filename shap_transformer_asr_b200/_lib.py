@@ -16,7 +16,7 @@ MAX_CONV_LAYERS = 8
 
 OUT_MAX, OUT_LOGIT, OUT_LOGPROB, OUT_MEAN, OUT_LOGITS = 0, 1, 2, 3, 4
 MODE_IDS = {"max": OUT_MAX, "logit": OUT_LOGIT, "logprob": OUT_LOGPROB, "mean": OUT_MEAN, "logits": OUT_LOGITS}
-FLAG_VALIDATE_GEMM, FLAG_VALIDATE_ATTN = 1, 2
+FLAG_VALIDATE_GEMM, FLAG_VALIDATE_ATTN, FLAG_BF16_PRELN, FLAG_PDL, FLAG_NO_GRAPH = 1, 2, 4, 8, 16
 
 
 class W2SConfig(C.Structure):
@@ -55,7 +55,8 @@ SIGNATURES = {
     "w2s_num_frames": (C.c_int64, [C.c_void_p, C.c_int64]),
     "w2s_set_clip": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.c_int, C.c_float,
                                C.c_void_p]),
-    "w2s_set_targets": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, C.c_int]),
+    "w2s_set_targets": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, C.c_int,
+                                  C.c_void_p]),
     "w2s_out_width": (C.c_int64, [C.c_void_p, C.c_int64]),
     "w2s_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "w2s_eval_waveforms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
@@ -63,12 +64,15 @@ SIGNATURES = {
     "w2s_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "w2s_wls": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p,
                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "w2s_debug_gemm": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
-                                 C.c_int, C.c_int, C.c_void_p]),
+    "w2s_sample_rows": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "w2s_debug_gemm": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
+                                 C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "w2s_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "w2s_profile_read": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                      C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int64]),
     "w2s_kernel_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "w2s_launch_count": (C.c_int64, [C.c_void_p]),
     "w2s_flops_per_forward": (C.c_double, [C.c_void_p, C.c_int64]),
 }
 

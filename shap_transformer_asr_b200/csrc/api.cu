@@ -51,18 +51,22 @@ struct Plan {
   int n = 0;
   std::vector<Step> steps;
   std::vector<GemmLaunch*> gemms;
-  std::vector<AttnTcPlan*> attn;
   std::vector<AttnRelPlan*> attn_rel;
   std::vector<PosConvPlan*> posconv;
   std::vector<AttnFaPlan*> attn_fa;
+  // the whole tile forward as one CUDA graph (captured on first use; per-call arguments travel through DynArgs)
+  cudaGraphExec_t exec = nullptr;
+  bool graph_failed = false;
   ~Plan() {
+    if (exec) cudaGraphExecDestroy(exec);
     for (auto* f : attn_fa) attention_fa_free(f);
     for (auto* pc : posconv) posconv_free(pc);
     for (auto* g : gemms) delete g;
-    for (auto* a : attn) attention_tc_free(a);
     for (auto* a : attn_rel) attention_rel_free(a);
   }
 };
+
+__global__ void set_dyn_kernel(DynArgs* dst, const DynArgs v) { *dst = v; }
 
 }  // namespace
 
@@ -104,13 +108,12 @@ struct w2s_handle {
   int mode = W2S_OUT_MAX, D = 0, max_frame = 0;
   int *frames = nullptr, *tokens = nullptr;
   int targets_cap = 0;
+  std::vector<int32_t> targets_host;   // staging of the last w2s_set_targets arrays (source of the async upload)
 
   // workspace (sized for max_batch rows of the current clip length)
   long long ws_L = -1;
   int T = 0, Tp = 0;
   std::vector<int> Tl;  // conv output lengths
-  float* xm = nullptr;
-  long long xm_ld = 0;
   float *gn_a = nullptr, *gn_b = nullptr;
   bf16* gn_wb = nullptr;
   bf16 *bufA = nullptr, *bufB = nullptr;
@@ -127,10 +130,12 @@ struct w2s_handle {
   bool profiling = false;
   std::vector<ProfRec> prof;
 
-  // per-call dynamic arguments read by the plan steps at launch time
-  const float* cur_x = nullptr;
-  long long cur_ld = 0;
-  float* cur_out = nullptr;
+  // per-call arguments of the plan's kernels (kernels.cuh: DynArgs), rewritten before every tile
+  DynArgs* dyn_dev = nullptr;
+  int head_ldl = 0;             // logits row stride: vocab rounded up to a multiple of 32
+  cudaStream_t cap_stream = nullptr;   // graphs are captured here (the caller's stream may be the legacy stream)
+  bool use_graphs = true;
+  long long launches = 0;       // kernel launches issued by w2s_eval / w2s_eval_waveforms since create
 
   ~w2s_handle() {
     for (auto& r : prof) {
@@ -138,6 +143,13 @@ struct w2s_handle {
       cudaEventDestroy(r.e1);
     }
     plans.clear();
+    if (cap_stream) cudaStreamDestroy(cap_stream);
+    if (dyn_dev) cudaFree(dyn_dev);
+    if (clip) cudaFree(clip);
+    if (seg_id) cudaFree(seg_id);
+    if (frames) cudaFree(frames);
+    if (tokens) cudaFree(tokens);
+    if (wls_work) cudaFree(wls_work);
     for (void* p : ws_allocs) cudaFree(p);
     for (void* p : allocs) cudaFree(p);
   }
@@ -346,9 +358,18 @@ std::string load_weights(w2s_handle* h, const WeightTable& wt) {
       W2S_TRY(copy_f32(h, wt, lp + "final_layer_norm.bias", H, &w.lnfin_b));
     }
   }
-  W2S_TRY(dalloc(h->allocs, &h->head_w, (size_t)V * H));
-  W2S_TRY(copy_bf16(h, wt, "lm_head.weight", (int64_t)V * H, h->head_w));
-  W2S_TRY(copy_f32(h, wt, "lm_head.bias", V, &h->head_b));
+  // lm_head rows are padded with zeros to a multiple of 32 so that any vocabulary size runs on the contraction kernel
+  // (the reduction kernel only reads the first V entries of a logits row)
+  {
+    const int Vp = (V + 31) / 32 * 32;
+    h->head_ldl = Vp;
+    W2S_TRY(dalloc(h->allocs, &h->head_w, (size_t)Vp * H, true));
+    W2S_TRY(copy_bf16(h, wt, "lm_head.weight", (int64_t)V * H, h->head_w));
+    const float* b = nullptr;
+    W2S_TRY(wt.get("lm_head.bias", V, &b));
+    W2S_TRY(dalloc(h->allocs, &h->head_b, (size_t)Vp, true));
+    W2S_CUDA_OK(cudaMemcpy(h->head_b, b, sizeof(float) * V, cudaMemcpyDeviceToDevice));
+  }
   W2S_CUDA_OK(cudaDeviceSynchronize());
   return "";
 }
@@ -403,8 +424,6 @@ std::string ensure_workspace(w2s_handle* h, long long L) {
   const int H = c.hidden_size, I = c.intermediate_size;
   const int Cl = c.conv_dim[c.num_conv_layers - 1];
   auto& pool = h->ws_allocs;
-  h->xm_ld = (L + 3) / 4 * 4;
-  W2S_TRY(dalloc(pool, &h->xm, nb * h->xm_ld));
   W2S_TRY(dalloc(pool, &h->gn_a, nb * c.conv_dim[0]));
   W2S_TRY(dalloc(pool, &h->gn_b, nb * c.conv_dim[0]));
   W2S_TRY(dalloc(pool, &h->gn_wb, nb * c.conv_dim[0] * 32));
@@ -425,7 +444,7 @@ std::string ensure_workspace(w2s_handle* h, long long L) {
   W2S_TRY(dalloc(pool, &h->qkv, rows * 4 * H));
   W2S_TRY(dalloc(pool, &h->ctx, rows * H));
   W2S_TRY(dalloc(pool, &h->ffn, rows * I));
-  W2S_TRY(dalloc(pool, &h->logits, rows * (size_t)c.vocab_size));
+  W2S_TRY(dalloc(pool, &h->logits, rows * (size_t)h->head_ldl));
   if (c.kind == 0) {
     W2S_TRY(dalloc(pool, &h->hp,
                    nb * (size_t)(T + c.num_conv_pos_embeddings) * c.num_conv_pos_embedding_groups * 64));
@@ -481,7 +500,10 @@ struct PlanBuilder {
   }
   std::string add_ln(const std::string& name, const void* in, int in_fp32, long long rows, int H, const float* g,
                      const float* b, float eps, int act, bf16* out, float* out_f32, const bf16* residual = nullptr) {
-    add(name, [=](cudaStream_t s) { return launch_layernorm(in, in_fp32, rows, H, g, b, eps, act, out, out_f32, s, residual); });
+    // algorithmic HBM bytes: the row read once (+ the bf16 residual) and every output written once
+    const double bytes = (double)rows * H * ((in_fp32 ? 4 : 2) + (residual ? 2 : 0) + (out ? 2 : 0) + (out_f32 ? 4 : 0));
+    add(name, [=](cudaStream_t s) { return launch_layernorm(in, in_fp32, rows, H, g, b, eps, act, out, out_f32, s, residual); },
+        0.0, bytes);
     return "";
   }
   static GemmProblem plain(const bf16* a, long long rows, int K, const bf16* w, int N) {
@@ -490,38 +512,27 @@ struct PlanBuilder {
 
   std::string build_conformer();
 
-  // K9: lm_head on the contraction kernel (N = vocab) into an fp32 logits buffer, then the warp-level reduction.
-  // LOGITS mode writes straight into the caller's buffer; vocabularies that are not a multiple of 32 use the
-  // fused CUDA-core head kernel.
+  // K9: lm_head on the contraction kernel (N = vocab padded to a multiple of 32) into an fp32 logits buffer, then the
+  // warp-level reduction, which reads mode / targets / destination from the per-call argument block.  The fused
+  // CUDA-core head kernel exists for W2S_FLAG_VALIDATE_GEMM only.
   std::string add_head() {
     const w2s_config& c = h->cfg;
     const int T = h->T, H = c.hidden_size, V = c.vocab_size;
-    w2s_handle* hh = h;
-    const int nn = n;
-    auto params = [=]() {
-      HeadParams hp{};
-      hp.h = hh->hb; hp.w = hh->head_w; hp.bias = hh->head_b;
-      hp.n = nn; hp.T = T; hp.H = H; hp.V = V; hp.mode = hh->mode; hp.D = hh->D;
-      hp.frames = hh->frames; hp.tokens = hh->tokens; hp.out = hh->cur_out;
-      return hp;
-    };
-    if (V % 32 != 0 || simt_gemm) {
-      add("head", [=](cudaStream_t s) { return launch_head(params(), s); });
+    HeadParams hp{};
+    hp.h = h->hb; hp.w = h->head_w; hp.bias = h->head_b;
+    hp.n = n; hp.T = T; hp.H = H; hp.V = V; hp.ldl = h->head_ldl; hp.dyn = h->dyn_dev;
+    if (simt_gemm) {
+      add("head", [=](cudaStream_t s) { return launch_head(hp, s); });
       return "";
     }
-    GemmProblem p = plain(h->hb, (long long)n * T, H, h->head_w, V);
+    GemmProblem p = plain(h->hb, (long long)n * T, H, h->head_w, h->head_ldl);
     p.epi.bias = h->head_b;
     p.epi.out = h->logits;
     p.epi.out_fp32 = 1;
     W2S_TRY(add_gemm("lm_head", p));
-    add("head_reduce", [=](cudaStream_t s) -> std::string {
-      HeadParams hp = params();
-      if (hp.mode == W2S_OUT_LOGITS) {
-        W2S_CUDA_OK(cudaMemcpyAsync(hp.out, hh->logits, sizeof(float) * (size_t)nn * T * V, cudaMemcpyDeviceToDevice, s));
-        return "";
-      }
-      return launch_head_reduce(hh->logits, hp, s);
-    });
+    const float* logits = h->logits;
+    add("head_reduce", [=](cudaStream_t s) { return launch_head_reduce(logits, hp, s); }, 0.0,
+        (double)n * T * V * 4.0);
     return "";
   }
 
@@ -536,6 +547,7 @@ struct PlanBuilder {
     // ---- K1: conv0 + norm + GELU -------------------------------------------------------------------
     {
       Conv0Params cp{};
+      cp.dyn = h->dyn_dev;
       cp.n = n; cp.L = (int)h->ws_L; cp.T0 = h->Tl[0]; cp.C = c.conv_dim[0]; cp.kw = c.conv_kernel[0];
       cp.stride = c.conv_stride[0];
       cp.w = h->conv0_w; cp.bias = h->conv0_b; cp.gamma = h->norm0_g; cp.beta = h->norm0_b;
@@ -544,16 +556,10 @@ struct PlanBuilder {
       cp.ln_bmean = h->ln0_bmean; cp.ln_b2mean = h->ln0_b2mean;
       cp.out = h->bufA;
       if (!layer)
-        add("conv0_stats", [=](cudaStream_t s) {
-          Conv0Params q = cp;
-          q.x = hh->cur_x; q.ld = hh->cur_ld;
-          return launch_conv0_stats(q, s);
-        });
-      add("conv0", [=](cudaStream_t s) {
-        Conv0Params q = cp;
-        q.x = hh->cur_x; q.ld = hh->cur_ld;
-        return launch_conv0(q, layer, s);
-      }, 2.0 * cp.T0 * (double)cp.C * cp.kw * n, ((double)cp.T0 * cp.C * 2.0 + 4.0 * (double)h->ws_L) * n);
+        add("conv0_stats", [=](cudaStream_t s) { return launch_conv0_stats(cp, s); }, 0.0,
+            (4.0 * (double)h->ws_L + (double)cp.C * (8.0 + 64.0)) * n);
+      add("conv0", [=](cudaStream_t s) { return launch_conv0(cp, layer, s); },
+          2.0 * cp.T0 * (double)cp.C * cp.kw * n, ((double)cp.T0 * cp.C * 2.0 + 4.0 * (double)h->ws_L) * n);
     }
     // ---- K2: conv1..6 as implicit GEMM over the stride-row view of the previous layer ---------------------
     bf16* cur = h->bufA;
@@ -595,7 +601,8 @@ struct PlanBuilder {
     // ---- K4: positional conv (grouped, k=128) + GELU + residual (+ LayerNorm) ----------------------------
     {
       const int G = c.num_conv_pos_embedding_groups, kp = c.num_conv_pos_embeddings, cpg = H / G;
-      add("pos_pad", [=](cudaStream_t s) { return launch_pos_pad(hh->h0, nn, T, H, G, kp, hh->hp, s); });
+      add("pos_pad", [=](cudaStream_t s) { return launch_pos_pad(hh->h0, nn, T, H, G, kp, hh->hp, s); }, 0.0,
+          ((double)T * H + (double)(T + kp) * G * 64) * 2.0 * n);
       GemmProblem p;
       p.a = h->hp; p.a_cols = (long long)G * 64; p.a_rows = T + kp; p.a_batches = n;
       p.a_row_stride = (long long)G * 64; p.a_batch_stride = (long long)(T + kp) * G * 64;
@@ -605,8 +612,7 @@ struct PlanBuilder {
       p.epi.residual = h->h0; p.epi.res_fp32 = 0;
       p.epi.out = h->pre; p.epi.out_fp32 = 1;
       p.epi.ldg = cpg; p.epi.ldb = (long long)T * H; p.epi.ldm = H;
-      static const bool pc_enabled = getenv("W2S_NO_POSCONV_KERNEL") == nullptr;
-      if (pc_enabled && !simt_gemm && posconv_supported(H, G, kp)) {
+      if (!simt_gemm && posconv_supported(H, G, kp)) {
         PosConvPlan* pc = nullptr;
         W2S_TRY(posconv_prepare(h->hp, h->pos_w, n, T, H, G, kp, p.epi, h->num_sms, &pc));
         plan->posconv.push_back(pc);
@@ -623,25 +629,22 @@ struct PlanBuilder {
     ap.heads = c.num_attention_heads; ap.hd = H / c.num_attention_heads;
     ap.ld = 3 * H; ap.q_off = 0; ap.qv_off = 0; ap.k_off = H; ap.v_off = 2 * H;
     ap.scale = 1.0f / sqrtf((float)ap.hd);
-    static const bool fa_enabled = getenv("W2S_ATTN_V1") == nullptr;
-    const bool fa_attn = fa_enabled && !simt_attn && attention_fa_supported(ap);
-    const bool tc_attn = !fa_attn && !simt_attn && attention_tc_supported(ap);
-    AttnTcPlan* apl = nullptr;
+    // attention: the persistent tcgen05 kernel, or -- W2S_FLAG_VALIDATE_ATTN only -- the CUDA-core cross-check.
+    // A shape the tensor-core kernel cannot take is an error, never a silent change of code path.
     AttnFaPlan* afl = nullptr;
-    if (fa_attn) {
+    if (!simt_attn) {
+      if (!attention_fa_supported(ap))
+        return "attention: head_dim " + std::to_string(ap.hd) + " is not supported (the tcgen05 kernel needs head_dim 64)";
       W2S_TRY(attention_fa_prepare(ap, h->num_sms, &afl));
       plan->attn_fa.push_back(afl);
     }
-    if (tc_attn) {
-      W2S_TRY(attention_tc_prepare(ap, &apl));
-      plan->attn.push_back(apl);
-    }
+    const double attn_flops = 4.0 * T * (double)T * H * n;
     const int act = c.hidden_act == 1 ? ACT_SWISH : ACT_GELU;
     const bool ln_res = !stable && (H == 128 || H == 256 || H == 512 || H == 768 || H == 1024);
-    // Opt-in experiment (not measured yet, default off): post-LN models write the pre-LayerNorm tensor of out_proj / ffn2
-    // as bf16 instead of fp32 -- halves the traffic of the one HBM-bound contraction and of both LayerNorms at the price
-    // of one more bf16 rounding per sub-layer.
-    static const bool bf16_preln = getenv("W2S_BF16_PRELN") != nullptr;
+    // A/B switch for one measurement (bench.py --preln-bf16 sets it): post-LN models write the pre-LayerNorm tensor of
+    // out_proj / ffn2 as bf16 instead of fp32 -- halves the traffic of the one HBM-bound contraction and of both
+    // LayerNorms at the price of one more bf16 rounding per sub-layer.  Default: fp32.
+    const bool bf16_preln = (c.flags & W2S_FLAG_BF16_PRELN) != 0;
     const int pre32 = (bf16_preln && ln_res) ? 0 : 1;
     for (int l = 0; l < c.num_hidden_layers; ++l) {
       const LayerW& w = h->layers[l];
@@ -653,9 +656,8 @@ struct PlanBuilder {
         p.epi.out = h->qkv;
         W2S_TRY(add_gemm(ls + "qkv", p));
       }
-      if (fa_attn) add(ls + "attention", [=](cudaStream_t s) { return attention_fa_launch(afl, s); });
-      else if (tc_attn) add(ls + "attention", [=](cudaStream_t s) { return attention_tc_launch(apl, s); });
-      else add(ls + "attention", [=](cudaStream_t s) { return launch_attention_simt(ap, s); });
+      if (afl) add(ls + "attention", [=](cudaStream_t s) { return attention_fa_launch(afl, s); }, attn_flops);
+      else add(ls + "attention", [=](cudaStream_t s) { return launch_attention_simt(ap, s); }, attn_flops);
       {
         GemmProblem p = plain(h->ctx, rows, H, w.wo, H);
         p.epi.bias = w.bo;
@@ -714,19 +716,15 @@ std::string PlanBuilder::build_conformer() {
   ap.scale = 1.0f / sqrtf((float)ap.hd);
   const int nq = rel ? 2 : 1;
   ap.ld = (nq + 2) * H; ap.q_off = 0; ap.qv_off = rel ? H : 0; ap.k_off = nq * H; ap.v_off = (nq + 1) * H;
-  AttnTcPlan* apl = nullptr;
   AttnFaPlan* afl = nullptr;
-  static const bool fa_enabled = getenv("W2S_ATTN_V1") == nullptr;
-  const bool fa_attn = fa_enabled && !rel && !simt_attn && attention_fa_supported(ap);
-  const bool tc_attn = !fa_attn && !rel && !simt_attn && attention_tc_supported(ap);
-  if (fa_attn) {
+  if (!simt_attn && !rel) {
+    if (!attention_fa_supported(ap))
+      return "attention: head_dim " + std::to_string(ap.hd) + " is not supported (the tcgen05 kernel needs head_dim 64)";
     W2S_TRY(attention_fa_prepare(ap, h->num_sms, &afl));
     plan->attn_fa.push_back(afl);
   }
-  if (tc_attn) {
-    W2S_TRY(attention_tc_prepare(ap, &apl));
-    plan->attn.push_back(apl);
-  }
+  double attn_flops = 4.0 * T * (double)T * H * n;
+  if (rel) attn_flops += 2.0 * T * (2.0 * T - 1) * H * n;   // (q + v) . linear_pos(pe) over the 2T'-1 relative positions
   auto ffn = [&](const std::string& ls, const float* lg, const float* lb, const bf16* w1, const float* b1,
                  const bf16* w2, const float* b2) -> std::string {
     add_ln(ls + "ln", h->pre, 1, rows, H, lg, lb, 1e-5f, ACT_NONE, h->hb, nullptr);
@@ -747,7 +745,8 @@ std::string PlanBuilder::build_conformer() {
     add_ln(ls + "attn_ln", h->pre, 1, rows, H, w.ln1_g, w.ln1_b, 1e-5f, ACT_NONE, h->hb, nullptr);
     if (rotary) {
       const int base = c.rotary_embedding_base, hd = ap.hd;
-      add(ls + "rotary", [=](cudaStream_t s) { return launch_rotary(hh->hb, rows, T, H, hd, base, hh->hrot, s); });
+      add(ls + "rotary", [=](cudaStream_t s) { return launch_rotary(hh->hb, rows, T, H, hd, base, hh->hrot, s); }, 0.0,
+          (double)rows * H * 4.0);
       GemmProblem p = plain(h->hrot, rows, H, w.wqkv, 2 * H);
       p.epi.bias = w.bqkv; p.epi.out = h->qkv; p.epi.ldm = 3 * H;
       W2S_TRY(add_gemm(ls + "qk", p));
@@ -759,20 +758,20 @@ std::string PlanBuilder::build_conformer() {
       p.epi.bias = w.bqkv; p.epi.out = h->qkv;
       W2S_TRY(add_gemm(ls + "qkv", p));
     }
-    if (fa_attn) {
-      add(ls + "attention", [=](cudaStream_t s) { return attention_fa_launch(afl, s); });
-    } else if (tc_attn) {
-      add(ls + "attention", [=](cudaStream_t s) { return attention_tc_launch(apl, s); });
+    if (afl) {
+      add(ls + "attention", [=](cudaStream_t s) { return attention_fa_launch(afl, s); }, attn_flops);
     } else {
       AttnParams lp = ap;
       if (rel) lp.pos_proj = w.pos_proj;
-      if (rel && !simt_attn && attention_rel_supported(lp)) {
+      if (rel && !simt_attn) {
+        if (!attention_rel_supported(lp))
+          return "attention (relative positions): head_dim " + std::to_string(lp.hd) + " is not supported (needs 64)";
         AttnRelPlan* rp = nullptr;
         W2S_TRY(attention_rel_prepare(lp, &rp));
         plan->attn_rel.push_back(rp);
-        add(ls + "attention", [=](cudaStream_t s) { return attention_rel_launch(rp, s); });
+        add(ls + "attention", [=](cudaStream_t s) { return attention_rel_launch(rp, s); }, attn_flops);
       } else {
-        add(ls + "attention", [=](cudaStream_t s) { return launch_attention_simt(lp, s); });
+        add(ls + "attention", [=](cudaStream_t s) { return launch_attention_simt(lp, s); }, attn_flops);
       }
     }
     {
@@ -790,7 +789,8 @@ std::string PlanBuilder::build_conformer() {
     {
       const int kd = c.conv_depthwise_kernel_size;
       const float *dw = w.dw_w, *sc = w.dw_scale, *sh = w.dw_shift;
-      add(ls + "depthwise", [=](cudaStream_t s) { return launch_depthwise(hh->h1, nn, T, H, kd, dw, sc, sh, act, hh->ctx, s); });
+      add(ls + "depthwise", [=](cudaStream_t s) { return launch_depthwise(hh->h1, nn, T, H, kd, dw, sc, sh, act, hh->ctx, s); },
+          2.0 * rows * (double)H * kd, (double)rows * H * 4.0);
     }
     {
       GemmProblem p = plain(h->ctx, rows, H, w.pw2, H);
@@ -830,37 +830,58 @@ int64_t out_width(const w2s_handle* h, int64_t L) {
   }
 }
 
+// Capture every launch of a tile plan into one CUDA graph (on the handle's own stream: the caller's may be the legacy
+// default stream, which cannot be captured).  A capture that fails for any reason leaves the plan on the eager path.
+void capture_plan(w2s_handle* h, Plan* pl) {
+  pl->graph_failed = true;
+  if (cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  bool ok = true;
+  for (const Step& st : pl->steps)
+    if (!st.run(h->cap_stream).empty()) {
+      ok = false;
+      break;
+    }
+  cudaGraph_t g = nullptr;
+  if (cudaStreamEndCapture(h->cap_stream, &g) != cudaSuccess || !g) ok = false;
+  if (ok && cudaGraphInstantiate(&pl->exec, g, 0) != cudaSuccess) {
+    pl->exec = nullptr;
+    ok = false;
+  }
+  if (g) cudaGraphDestroy(g);
+  cudaGetLastError();
+  pl->graph_failed = !ok;
+}
+
+// One evaluation call: rows in tiles of max_batch (the last tile ragged), each tile = one DynArgs update + the plan.
 std::string run_batches(w2s_handle* h, const uint32_t* zbits, const float* x, long long ld, int64_t K, float* out,
                         cudaStream_t s) {
   const int64_t width = out_width(h, h->ws_L);
   if (width <= 0) return "no outputs selected (w2s_set_targets)";
+  const bool graphs = h->use_graphs && !h->profiling;
   for (int64_t k0 = 0; k0 < K; k0 += h->cfg.max_batch) {
     const int n = (int)((K - k0) < h->cfg.max_batch ? (K - k0) : h->cfg.max_batch);
     Plan* pl = nullptr;
     W2S_TRY(get_plan(h, n, &pl));
+    DynArgs d{};
     if (zbits) {
-      ProfRec rec;
-      if (h->profiling) {
-        rec.name = "mask";
-        rec.flops = 0.0;
-        rec.bytes = 4.0 * (double)h->L * n;
-        cudaEventCreate(&rec.e0);
-        cudaEventCreate(&rec.e1);
-        cudaEventRecord(rec.e0, s);
-      }
-      W2S_TRY(launch_mask(h->clip, h->seg_id, zbits + k0 * h->zwords, h->zwords, n, h->L, h->baseline, h->xm,
-                          h->xm_ld, s));
-      if (h->profiling) {
-        cudaEventRecord(rec.e1, s);
-        h->prof.push_back(rec);
-      }
-      h->cur_x = h->xm;
-      h->cur_ld = h->xm_ld;
+      d.clip = h->clip; d.seg_id = h->seg_id; d.zbits = zbits + k0 * h->zwords; d.zwords = h->zwords;
+      d.baseline = h->baseline;
     } else {
-      h->cur_x = x + k0 * ld;
-      h->cur_ld = ld;
+      d.x = x + k0 * ld; d.ld = ld;
     }
-    h->cur_out = out + k0 * width;
+    d.out = out + k0 * width;
+    d.mode = h->mode; d.D = h->D; d.frames = h->frames; d.tokens = h->tokens;
+    set_dyn_kernel<<<1, 1, 0, s>>>(h->dyn_dev, d);
+    W2S_CUDA_OK(cudaGetLastError());
+    h->launches += 1 + (long long)pl->steps.size();
+    if (graphs && !pl->exec && !pl->graph_failed) capture_plan(h, pl);
+    if (graphs && pl->exec) {
+      W2S_CUDA_OK(cudaGraphLaunch(pl->exec, s));
+      continue;
+    }
     for (const Step& st : pl->steps) {
       ProfRec rec;
       if (h->profiling) {
@@ -878,6 +899,15 @@ std::string run_batches(w2s_handle* h, const uint32_t* zbits, const float* x, lo
       }
       if (!e.empty()) return st.name + ": " + e;
     }
+  }
+  return "";
+}
+
+std::string check_targets(const w2s_handle* h) {
+  if (h->mode == W2S_OUT_LOGIT || h->mode == W2S_OUT_LOGPROB) {
+    if (h->D <= 0 || !h->frames || !h->tokens) return "targets not set (w2s_set_targets)";
+    if (h->max_frame >= h->T)
+      return "target frame " + std::to_string(h->max_frame) + " beyond the clip's " + std::to_string(h->T) + " frames";
   }
   return "";
 }
@@ -923,6 +953,14 @@ int w2s_create(const w2s_config* cfg, const char* const* names, const float* con
   h->num_sms = prop.multiProcessorCount;
   h->auto_batch = h->cfg.max_batch <= 0;
   if (h->auto_batch) h->cfg.max_batch = 64;
+  // graph replay needs fixed kernel arguments; the validation and PDL modes launch eagerly
+  h->use_graphs = (cfg->flags & (W2S_FLAG_NO_GRAPH | W2S_FLAG_VALIDATE_GEMM | W2S_FLAG_VALIDATE_ATTN | W2S_FLAG_PDL)) == 0;
+  pdl_flag() = (cfg->flags & W2S_FLAG_PDL) != 0;
+  if (cudaMalloc((void**)&h->dyn_dev, sizeof(DynArgs)) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_create_error = "out of device memory";
+    return 1;
+  }
   if (cfg->num_conv_layers < 1 || cfg->num_conv_layers > W2S_MAX_CONV_LAYERS) {
     g_create_error = "num_conv_layers out of range";
     return 1;
@@ -932,7 +970,6 @@ int w2s_create(const w2s_config* cfg, const char* const* names, const float* con
     return 1;
   }
   std::string e = gemm_init();
-  if (e.empty()) e = attention_tc_init();
   if (e.empty()) e = attention_rel_init();
   if (e.empty()) e = posconv_init();
   if (e.empty()) e = attention_fa_init();
@@ -992,24 +1029,34 @@ int w2s_set_clip(w2s_handle* h, const float* x_dev, int64_t L, const int32_t* se
   return 0;
 }
 
-int w2s_set_targets(w2s_handle* h, const int32_t* frame_idx_host, const int32_t* token_idx_host, int D, int mode) {
+int w2s_set_targets(w2s_handle* h, const int32_t* frame_idx_host, const int32_t* token_idx_host, int D, int mode,
+                    void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
   if (mode < W2S_OUT_MAX || mode > W2S_OUT_LOGITS) return fail(h, "set_targets: unknown mode");
-  h->mode = mode;
   if (mode == W2S_OUT_LOGIT || mode == W2S_OUT_LOGPROB) {
     if (D <= 0 || !frame_idx_host || !token_idx_host) return fail(h, "set_targets: need D > 0 (frame, token) pairs");
     for (int d = 0; d < D; ++d)
       if (token_idx_host[d] < 0 || token_idx_host[d] >= h->cfg.vocab_size || frame_idx_host[d] < 0)
         return fail(h, "set_targets: target out of range");
     if (h->targets_cap < D) {
+      // evaluations in flight on the stream still read the old arrays
+      if (cudaStreamSynchronize(s) != cudaSuccess) return fail(h, "set_targets: stream error");
       if (h->frames) cudaFree(h->frames);
       if (h->tokens) cudaFree(h->tokens);
-      if (cudaMalloc((void**)&h->frames, sizeof(int) * D) != cudaSuccess ||
-          cudaMalloc((void**)&h->tokens, sizeof(int) * D) != cudaSuccess)
+      h->frames = h->tokens = nullptr;
+      h->targets_cap = 0;
+      const int cap = D < 1024 ? 1024 : D;
+      if (cudaMalloc((void**)&h->frames, sizeof(int) * cap) != cudaSuccess ||
+          cudaMalloc((void**)&h->tokens, sizeof(int) * cap) != cudaSuccess)
         return fail(h, "set_targets: out of device memory");
-      h->targets_cap = D;
+      h->targets_cap = cap;
     }
-    if (cudaMemcpy(h->frames, frame_idx_host, sizeof(int) * D, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(h->tokens, token_idx_host, sizeof(int) * D, cudaMemcpyHostToDevice) != cudaSuccess)
+    // ordered on the caller's stream behind any evaluation still running with the previous targets; the host arrays
+    // are staged in the handle so the caller's buffers may be released when this returns
+    h->targets_host.assign(frame_idx_host, frame_idx_host + D);
+    h->targets_host.insert(h->targets_host.end(), token_idx_host, token_idx_host + D);
+    if (cudaMemcpyAsync(h->frames, h->targets_host.data(), sizeof(int) * D, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemcpyAsync(h->tokens, h->targets_host.data() + D, sizeof(int) * D, cudaMemcpyHostToDevice, s) != cudaSuccess)
       return fail(h, "set_targets: copy failed");
     h->D = D;
     h->max_frame = 0;
@@ -1017,6 +1064,7 @@ int w2s_set_targets(w2s_handle* h, const int32_t* frame_idx_host, const int32_t*
   } else {
     h->D = 0;
   }
+  h->mode = mode;
   return 0;
 }
 
@@ -1026,11 +1074,11 @@ int w2s_eval(w2s_handle* h, const uint32_t* z_bits_dev, int64_t K, float* out_de
   if (h->L <= 0) return fail(h, "eval: no clip set (w2s_set_clip)");
   if (K == 0) return 0;   // empty coalition matrix: nothing to evaluate
   if (K < 0 || !z_bits_dev || !out_dev) return fail(h, "eval: null buffer");
-  if ((h->mode == W2S_OUT_LOGIT || h->mode == W2S_OUT_LOGPROB) && h->max_frame >= h->T)
-    return fail(h, "eval: target frame beyond the clip's " + std::to_string(h->T) + " frames");
+  // the workspace (and with it T') follows the clip of THIS call: w2s_eval_waveforms may have left it at another length
   std::string e = ensure_workspace(h, h->L);
+  if (e.empty()) e = check_targets(h);
   if (e.empty()) e = run_batches(h, z_bits_dev, nullptr, 0, K, out_dev, (cudaStream_t)stream);
-  return e.empty() ? 0 : fail(h, e);
+  return e.empty() ? 0 : fail(h, "eval: " + e);
 }
 
 int w2s_eval_waveforms(w2s_handle* h, const float* x_dev, int64_t n, int64_t L, int64_t ld, float* out_dev,
@@ -1039,10 +1087,9 @@ int w2s_eval_waveforms(w2s_handle* h, const float* x_dev, int64_t n, int64_t L, 
   if (n < 0 || !x_dev || !out_dev) return fail(h, "eval_waveforms: null buffer");
   if (ld < L) return fail(h, "eval_waveforms: row stride smaller than the row length");
   std::string e = ensure_workspace(h, L);
-  if (e.empty() && (h->mode == W2S_OUT_LOGIT || h->mode == W2S_OUT_LOGPROB) && h->max_frame >= h->T)
-    e = "target frame beyond the clip's " + std::to_string(h->T) + " frames";
+  if (e.empty()) e = check_targets(h);
   if (e.empty()) e = run_batches(h, nullptr, x_dev, ld, n, out_dev, (cudaStream_t)stream);
-  return e.empty() ? 0 : fail(h, e);
+  return e.empty() ? 0 : fail(h, "eval_waveforms: " + e);
 }
 
 int w2s_mask(w2s_handle* h, const uint32_t* z_bits_dev, int64_t K, float* out_dev, void* stream) {
@@ -1054,7 +1101,7 @@ int w2s_mask(w2s_handle* h, const uint32_t* z_bits_dev, int64_t K, float* out_de
 
 int w2s_wls(w2s_handle* h, const uint32_t* z_bits_dev, const double* w_dev, const float* y_dev, int64_t K, int M,
             int D, const double* fx_dev, const double* fnull_dev, double* phi_dev, int32_t* status_dev, void* stream) {
-  const long long need = (long long)(M - 1) * (M - 1) + (long long)(M - 1) * D;
+  const long long need = 2 * ((long long)(M - 1) * (M - 1) + (long long)(M - 1) * D);
   if (h->wls_cap < need) {
     cudaStreamSynchronize((cudaStream_t)stream);
     if (h->wls_work) cudaFree(h->wls_work);
@@ -1066,13 +1113,14 @@ int w2s_wls(w2s_handle* h, const uint32_t* z_bits_dev, const double* w_dev, cons
   return e.empty() ? 0 : fail(h, e);
 }
 
-int w2s_debug_gemm(int use_tcgen05, const void* a_bf16, const void* w_bf16, const float* bias, void* out, int M, int N,
-                   int K, int act, int out_fp32, void* stream) {
+int w2s_debug_gemm(int use_tcgen05, const void* a_bf16, const void* w_bf16, const float* bias, const void* residual,
+                   int res_fp32, float alpha, void* out, int M, int N, int K, int act, int out_fp32, void* stream) {
   g_create_error.clear();
   std::string e = gemm_init();
   if (e.empty()) {
     GemmProblem p = PlanBuilder::plain((const bf16*)a_bf16, M, K, (const bf16*)w_bf16, N);
     p.epi.bias = bias; p.epi.act = act; p.epi.out = out; p.epi.out_fp32 = out_fp32;
+    p.epi.residual = residual; p.epi.res_fp32 = res_fp32; p.epi.alpha = alpha;
     GemmLaunch gl;
     static int sms = 0;
     if (sms == 0) {
@@ -1138,9 +1186,11 @@ int w2s_kernel_count(const w2s_handle* h, int64_t* launches_per_batch, int64_t* 
   int64_t n = 0;
   for (auto& kv : h->plans)
     if ((int64_t)kv.second->steps.size() > n) n = (int64_t)kv.second->steps.size();
-  if (launches_per_batch) *launches_per_batch = n + 1;  // + mask kernel
+  if (launches_per_batch) *launches_per_batch = n + 1;  // + the per-call argument kernel
   return 0;
 }
+
+int64_t w2s_launch_count(const w2s_handle* h) { return h->launches; }
 
 double w2s_flops_per_forward(const w2s_handle* h, int64_t L) {
   const w2s_config& c = h->cfg;

@@ -1,12 +1,11 @@
 // Self-attention of the encoder (HF wav2vec2/modeling_wav2vec2.py:438-463, :500-549; conformer relative
 // positions wav2vec2_conformer/modeling_wav2vec2_conformer.py:509-565).
 //
-//  * attention_fa.cu       : the default tcgen05 kernel (persistent, warp-specialised, independent key blocks).
-//  * attention_tc_kernel  : first-generation tcgen05 kernel, one CTA per (128-query tile, head, coalition) with the
-//                           whole score row block in TMEM; kept selectable (W2S_ATTN_V1=1) as a cross-check.
-//  * attention_rel_kernel : conformer relative-position attention on tcgen05 (T' <= 256).
-//  * attention_simt_kernel: CUDA-core validation kernel (one warp per query row), also carries the
-//                           conformer relative-position term for longer clips.
+//  * attention_fa.cu       : the tcgen05 kernel of the plain / rotary models (persistent, warp-specialised, key blocks
+//                            streamed through independent accumulators; any clip length).
+//  * attention_rel_kernel  : conformer relative-position attention on tcgen05 (any clip length).
+//  * attention_simt_kernel : CUDA-core cross-check (one warp per query row), reachable through W2S_FLAG_VALIDATE_ATTN
+//                            only -- never a fallback of the product path.
 #include "kernels.cuh"
 #include "gemm.cuh"
 
@@ -106,33 +105,6 @@ std::string launch_attention_simt(const AttnParams& p, cudaStream_t s) {
   return "";
 }
 
-// =================================================================================================
-// tcgen05 kernel
-// =================================================================================================
-struct AttnTcDev {
-  __nv_bfloat16* ctx;
-  int B, T, Tp, H, heads;
-  int nblk;       // 64-key blocks = Tp / 64
-  int n0, n1;     // keys in the first / second S half (multiples of 64, <= 256 each)
-  int sv_off;     // smem offset of the V tiles
-  float scale_log2e;
-};
-struct AttnTcPlan {
-  CUtensorMap mapQ, mapK, mapV;
-  AttnTcDev dev;
-  dim3 grid;
-  size_t smem;
-  int tmem_cols;
-};
-
-// shared memory map (bytes from the 1024-aligned base):
-//   [0, 16K)          Q   [128 x 64]            \  dead once S = Q K^T has completed;
-//   [16K, 16K + Ksz)  K   1 or 2 x [256 x 64]   /  P (4 x [128 x 64 keys] = 64 KB) is written over them
-//   [sv_off, ...)     V   nblk x [64 keys x 64] straight from the qkv buffer (MN-major B operand)
-constexpr int ATT_SQ = 0;
-constexpr int ATT_SK = 16384;
-constexpr int ATT_SP = 0;
-
 __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
   // MN-major operand (rows = K index, 128 contiguous bytes = 64 MN elements, 128B swizzle):
   // 8-row (K) groups are 1024 B apart (SBO); LBO (next 64-wide MN block) unused for N = 64.
@@ -141,261 +113,6 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(int M, int N) {
   return umma_idesc_bf16(M, N) | (1u << 16);  // b_major = MN
 }
-
-template <int TMEM_COLS>
-__global__ void __launch_bounds__(256, (TMEM_COLS <= 256) ? 2 : 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
-                    const __grid_constant__ CUtensorMap mapV, const AttnTcDev p) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ float s_red[2][128];
-  __shared__ uint64_t s_bar[3];
-  __shared__ uint32_t s_tmem;
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t bar_load = smem_u32(&s_bar[0]), bar_mma = smem_u32(&s_bar[1]), bar_v = smem_u32(&s_bar[2]);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qd = warp & 3, hf = warp >> 2;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int row = qd * 32 + lane;  // query row inside the tile == TMEM lane
-
-  if (warp == 0 && elect_one()) {
-    tma_prefetch_desc(&mapQ);
-    tma_prefetch_desc(&mapK);
-    tma_prefetch_desc(&mapV);
-    mbar_init(bar_load, 1);
-    mbar_init(bar_mma, 1);
-    mbar_init(bar_v, 1);
-    fence_barrier_init();
-    fence_proxy_async();
-  }
-  if (warp == 0) {
-    tmem_alloc<TMEM_COLS>(smem_u32(&s_tmem));
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&s_tmem);
-  const uint32_t sV = base + p.sv_off;
-
-  // ---- loads ---------------------------------------------------------------------------------------
-  if (warp == 0 && elect_one()) {
-    // Q and K gate the score MMAs; V is only needed for P V, so it lands behind the softmax on its own barrier
-    mbar_expect_tx(bar_load, 16384u + (p.n1 > 0 ? 65536u : 32768u));
-    tma_load_4d(base + ATT_SQ, &mapQ, bar_load, 0, qt * 128, h, b);
-    tma_load_4d(base + ATT_SK, &mapK, bar_load, 0, 0, h, b);
-    if (p.n1 > 0) tma_load_4d(base + ATT_SK + 32768, &mapK, bar_load, 0, 256, h, b);
-    mbar_expect_tx(bar_v, 8192u * p.nblk);
-    for (int kb = 0; kb < p.nblk; ++kb) tma_load_4d(sV + kb * 8192, &mapV, bar_v, 0, kb * 64, h, b);
-    {
-      // warm L2 for the CTA that will follow on this SM slot (CTAs are dispatched in linear block order, two per SM)
-      const long long nx = (long long)gridDim.x * gridDim.y;
-      const long long lin = ((long long)b * gridDim.y + h) * gridDim.x + qt + 2LL * 148;
-      if (lin < nx * gridDim.z) {
-        const int nb = (int)(lin / nx), nh2 = (int)((lin / gridDim.x) % gridDim.y), nq = (int)(lin % gridDim.x);
-        tma_prefetch_l2_4d(&mapQ, 0, nq * 128, nh2, nb);
-        tma_prefetch_l2_4d(&mapK, 0, 0, nh2, nb);
-        if (p.n1 > 0) tma_prefetch_l2_4d(&mapK, 0, 256, nh2, nb);
-        for (int kb = 0; kb < p.nblk; ++kb) tma_prefetch_l2_4d(&mapV, 0, kb * 64, nh2, nb);
-      }
-    }
-    mbar_wait(bar_load, 0);
-    // ---- S = Q K^T ---------------------------------------------------------------------------------
-    tc_fence_after();
-    const uint64_t dq = umma_desc_sw128(base + ATT_SQ);
-    {
-      const uint64_t dk = umma_desc_sw128(base + ATT_SK);
-      const uint32_t idesc = umma_idesc_bf16(128, p.n0);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(tmem, dq + 2u * k, dk + 2u * k, idesc, k != 0);
-    }
-    if (p.n1 > 0) {
-      const uint64_t dk = umma_desc_sw128(base + ATT_SK + 32768);
-      const uint32_t idesc = umma_idesc_bf16(128, p.n1);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16(tmem + 256, dq + 2u * k, dk + 2u * k, idesc, k != 0);
-    }
-    umma_commit(bar_mma);
-  }
-  mbar_wait(bar_mma, 0);
-  tc_fence_after();
-
-  const uint32_t trow = tmem + (static_cast<uint32_t>(qd * 32) << 16);
-
-  // ---- pass 1: row maximum over the valid keys (each half-warp-group scans its key blocks) -----------------
-  float mx = -INFINITY;
-  for (int r0 = 0; r0 < p.nblk; r0 += 4) {
-    const int cnt = min(4, p.nblk - r0);
-    const int per = (cnt + 1) >> 1;
-    const int b0 = r0 + hf * per, b1 = min(r0 + cnt, b0 + per);
-    for (int c = b0 * 64; c < b1 * 64; c += 32) {
-      float v[32];
-      tmem_ld_32x32(trow + c, v);
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (c + j < p.T) mx = fmaxf(mx, v[j]);
-    }
-  }
-  s_red[hf][row] = mx;
-  __syncthreads();
-  mx = fmaxf(s_red[0][row], s_red[1][row]);
-  const float mscaled = mx * p.scale_log2e;
-
-  // ---- pass 2: P = exp2(S*scale - max) as bf16 into swizzled smem (over Q/K), then O (+)= P V -----------------
-  float sum = 0.f;
-  uint32_t mma_parity = 1;
-  for (int r0 = 0; r0 < p.nblk; r0 += 4) {
-    const int cnt = min(4, p.nblk - r0);
-    const int per = (cnt + 1) >> 1;
-    const int b0 = r0 + hf * per, b1 = min(r0 + cnt, b0 + per);
-    if (r0 > 0) {
-      mbar_wait(bar_mma, mma_parity);  // previous P V chain has finished reading sP
-      mma_parity ^= 1u;
-      tc_fence_after();
-    }
-    for (int kb = b0; kb < b1; ++kb) {
-      const uint32_t sp_row = base + ATT_SP + (kb - r0) * 16384 + row * 128;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float v[32];
-        const int c = kb * 64 + half * 32;
-        tmem_ld_32x32(trow + c, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float e = (c + j < p.T) ? ex2_approx(fmaf(v[j], p.scale_log2e, -mscaled)) : 0.f;
-          v[j] = e;
-          sum += e;
-        }
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int chunk = half * 4 + q4;  // 16-byte chunk index inside the 128-byte row
-          const uint32_t addr = sp_row + (((uint32_t)chunk ^ ((uint32_t)row & 7u)) << 4);
-          const uint32_t u0 = pack_bf16x2(v[q4 * 8 + 0], v[q4 * 8 + 1]);
-          const uint32_t u1 = pack_bf16x2(v[q4 * 8 + 2], v[q4 * 8 + 3]);
-          const uint32_t u2 = pack_bf16x2(v[q4 * 8 + 4], v[q4 * 8 + 5]);
-          const uint32_t u3 = pack_bf16x2(v[q4 * 8 + 6], v[q4 * 8 + 7]);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u0), "r"(u1), "r"(u2), "r"(u3)
-                       : "memory");
-        }
-      }
-    }
-    fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0 && elect_one()) {
-      if (r0 == 0) mbar_wait(bar_v, 0);
-      tc_fence_after();
-      constexpr uint32_t idesc = umma_idesc_bf16_bmn(128, 64);
-      for (int kb = r0; kb < r0 + cnt; ++kb) {
-        const uint64_t dp = umma_desc_sw128(base + ATT_SP + (kb - r0) * 16384);
-        const uint64_t dv = umma_desc_sw128_mn(sV + kb * 8192);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)  // 16 keys per MMA: +32 B along P's rows, +16 rows (2048 B) down V
-          umma_bf16(tmem, dp + 2u * k, dv + 128u * k, idesc, (kb | k) != 0);
-      }
-      umma_commit(bar_mma);
-    }
-  }
-  s_red[hf][row] = sum;   // safe: every thread passed the barrier above after reading the maxima
-  mbar_wait(bar_mma, mma_parity);
-  tc_fence_after();
-  __syncthreads();
-  sum = s_red[0][row] + s_red[1][row];
-
-  // ---- epilogue: O / rowsum -> ctx (each half takes 32 of the 64 output columns) ----------------------------------
-  const int i = qt * 128 + row;
-  const float inv = 1.0f / sum;
-  __nv_bfloat16* orow = p.ctx + ((long long)b * p.T + i) * p.H + h * 64 + hf * 32;
-  {
-    float v[32];
-    tmem_ld_32x32(trow + hf * 32, v);
-    if (i < p.T) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint4 u;
-        u.x = pack_bf16x2(v[j] * inv, v[j + 1] * inv);
-        u.y = pack_bf16x2(v[j + 2] * inv, v[j + 3] * inv);
-        u.z = pack_bf16x2(v[j + 4] * inv, v[j + 5] * inv);
-        u.w = pack_bf16x2(v[j + 6] * inv, v[j + 7] * inv);
-        *reinterpret_cast<uint4*>(orow + j) = u;
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem);
-  }
-}
-
-bool attention_tc_supported(const AttnParams& p) {
-  return p.hd == 64 && p.T <= 512 && p.pos_proj == nullptr && (p.H % 8 == 0);
-}
-
-static size_t att_smem(int Tp) { return (Tp <= 256 ? 65536 : 81920) + (size_t)(Tp / 64) * 8192 + 1024; }
-
-std::string attention_tc_init() {
-  const int mx = (int)att_smem(512);
-  cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-  if (e != cudaSuccess) return std::string("cudaFuncSetAttribute(attention_tc_kernel): ") + cudaGetErrorString(e);
-  return "";
-}
-
-std::string attention_tc_prepare(const AttnParams& p, AttnTcPlan** out) {
-  if (!attention_tc_supported(p)) return "attention (tcgen05): unsupported shape";
-  AttnTcPlan* pl = new AttnTcPlan();
-  const int Tp = p.Tp;
-  if (Tp % 64 || Tp < p.T || Tp > 512) {
-    delete pl;
-    return "attention (tcgen05): Tp must be a multiple of 64 covering T";
-  }
-  pl->dev.ctx = p.ctx;
-  pl->dev.B = p.B; pl->dev.T = p.T; pl->dev.Tp = Tp; pl->dev.H = p.H; pl->dev.heads = p.heads;
-  pl->dev.nblk = Tp / 64;
-  pl->dev.n0 = Tp < 256 ? Tp : 256;
-  pl->dev.n1 = Tp > 256 ? Tp - 256 : 0;
-  pl->dev.sv_off = Tp <= 256 ? 65536 : 81920;
-  pl->dev.scale_log2e = p.scale * 1.4426950408889634f;
-  pl->grid = dim3((p.T + 127) / 128, p.heads, p.B);
-  pl->smem = att_smem(Tp);
-  pl->tmem_cols = Tp <= 64 ? 64 : (Tp <= 128 ? 128 : (Tp <= 256 ? 256 : 512));
-  const uint64_t H3 = (uint64_t)p.ld;
-  std::string err;
-  {
-    uint64_t dims[4] = {64, (uint64_t)p.T, (uint64_t)p.heads, (uint64_t)p.B};
-    uint64_t str[3] = {H3 * 2, 128, (uint64_t)p.T * H3 * 2};
-    uint32_t boxq[4] = {64, 128, 1, 1};
-    uint32_t boxk[4] = {64, 256, 1, 1};
-    uint32_t boxv[4] = {64, 64, 1, 1};
-    err = make_tensor_map_bf16(&pl->mapQ, p.qkv + p.q_off, 4, dims, str, boxq);
-    if (err.empty()) err = make_tensor_map_bf16(&pl->mapK, p.qkv + p.k_off, 4, dims, str, boxk);
-    if (err.empty()) err = make_tensor_map_bf16(&pl->mapV, p.qkv + p.v_off, 4, dims, str, boxv);
-  }
-  if (!err.empty()) {
-    delete pl;
-    return err;
-  }
-  *out = pl;
-  return "";
-}
-
-std::string attention_tc_launch(const AttnTcPlan* pl, cudaStream_t s) {
-  switch (pl->tmem_cols) {
-    case 64: attention_tc_kernel<64><<<pl->grid, 256, pl->smem, s>>>(pl->mapQ, pl->mapK, pl->mapV, pl->dev); break;
-    case 128: attention_tc_kernel<128><<<pl->grid, 256, pl->smem, s>>>(pl->mapQ, pl->mapK, pl->mapV, pl->dev); break;
-    case 256: attention_tc_kernel<256><<<pl->grid, 256, pl->smem, s>>>(pl->mapQ, pl->mapK, pl->mapV, pl->dev); break;
-    default: attention_tc_kernel<512><<<pl->grid, 256, pl->smem, s>>>(pl->mapQ, pl->mapK, pl->mapV, pl->dev); break;
-  }
-  W2S_CUDA_OK(cudaGetLastError());
-  return "";
-}
-
-void attention_tc_free(AttnTcPlan* plan) { delete plan; }
 
 // =================================================================================================
 // conformer relative-position attention on tcgen05 (HF wav2vec2_conformer/modeling_wav2vec2_conformer.py:509-565)

@@ -25,10 +25,12 @@ namespace w2s {
 #include <utility>
 namespace w2s {
 // Launch with the programmatic-stream-serialization attribute (and an optional cluster width).
-inline bool pdl_enabled() {
-  static const bool on = getenv("W2S_PDL") != nullptr;   // opt-in: measured neutral at the 1 kW power cap (193.5 vs 195.2 ms/step on C2)
+// (W2S_FLAG_PDL at w2s_create; off by default: measured neutral at the 1 kW power cap in round 1)
+inline bool& pdl_flag() {
+  static bool on = false;
   return on;
 }
+inline bool pdl_enabled() { return pdl_flag(); }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_x,
                               Args&&... args) {
@@ -196,11 +198,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a pipeline bug must surface as a trapped kernel, never as a hung GPU.
+// Bounded wait: a pipeline bug must surface as a trapped kernel, never as a hung GPU.  The bound is wall-clock time
+// (%globaltimer, 10 s), not a poll count: a wait that is merely slow -- time-slicing with another process, a profiler
+// replaying the kernel, heavy throttling -- must not trap and poison the context.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) __trap();
+    if ((++spins & 0xfffu) == 0) {   // look at the clock every 4096 failed polls
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 10000000000ull) __trap();
+    }
   }
 }
 

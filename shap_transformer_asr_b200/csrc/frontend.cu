@@ -47,39 +47,76 @@ std::string launch_mask(const float* x, const uint16_t* seg_id, const uint32_t* 
   return "";
 }
 
+// The same selection folded into a consumer's load: `zs` is the coalition's bit row staged in shared memory.
+struct WaveRow {
+  const float* x;
+  const uint16_t* seg;   // null: plain waveform row
+  const uint32_t* zs;
+  float baseline;
+  __device__ __forceinline__ float at(long long i) const {
+    const float v = __ldg(x + i);
+    if (!seg) return v;
+    const uint32_t sgm = __ldg(seg + i);
+    return (zs[sgm >> 5] >> (sgm & 31)) & 1u ? v : baseline;
+  }
+};
+// Row `row` of the tile described by the per-call argument block; ends with a CTA-wide barrier.
+__device__ __forceinline__ WaveRow wave_row(const DynArgs* __restrict__ dyn, int row, uint32_t* zs) {
+  WaveRow w;
+  w.zs = zs;
+  if (dyn->clip) {
+    const int zw = dyn->zwords;
+    for (int i = threadIdx.x; i < zw; i += blockDim.x) zs[i] = dyn->zbits[(long long)row * zw + i];
+    w.x = dyn->clip; w.seg = dyn->seg_id; w.baseline = dyn->baseline;
+  } else {
+    w.x = dyn->x + (long long)row * dyn->ld; w.seg = nullptr; w.baseline = 0.f;
+  }
+  __syncthreads();
+  return w;
+}
+
 // =================================================================================================
 // K1a  GroupNorm statistics of conv0 output without materialising it.
 // conv0 is linear and bias-free under GroupNorm (a conv bias cancels in y - mean), so per waveform row
 //   sum_t y[t,c]   = sum_j w[c,j] S[j],        S[j]    = sum_t x[s t + j]
 //   sum_t y[t,c]^2 = sum_jj' w[c,j] w[c,j'] R[j,j'],  R[j,j'] = sum_t x[s t + j] x[s t + j']
 // (HF wav2vec2/modeling_wav2vec2.py:302-323: GroupNorm(num_groups=C) normalises each channel over time).
-// One CTA per waveform row: 65 fp32 accumulators per thread, fp64 from the block reduction onwards.
+// One CTA per waveform row.  The 65 sums are accumulated in fp64 from the first product on (the product of two fp32
+// samples is exact in fp64): for low-pass input under a high-pass / band-pass filter the quadratic form w^T R w cancels
+// by many orders of magnitude, and fp32 partial sums lose percent-level accuracy in the variance there.
 // =================================================================================================
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 template <int KW>
-__global__ void __launch_bounds__(256) conv0_stats_kernel(const Conv0Params p) {
+__global__ void __launch_bounds__(256, 1) conv0_stats_kernel(const Conv0Params p) {
   constexpr int NR = KW * (KW + 1) / 2;
   constexpr int NACC = KW + NR;
   __shared__ double red[8][NACC];
   __shared__ double tot[NACC];
+  __shared__ uint32_t zs[64];
   pdl_trigger();
   pdl_wait();
   const int row = blockIdx.x;
-  const float* x = p.x + (long long)row * p.ld;
-  float acc[NACC];
+  const WaveRow x = wave_row(p.dyn, row, zs);
+  double acc[NACC];
 #pragma unroll
-  for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+  for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
   for (int t = threadIdx.x; t < p.T0; t += blockDim.x) {
-    float xv[KW];
-    const float* xp = x + (long long)t * p.stride;
+    double xv[KW];
+    const long long i0 = (long long)t * p.stride;
 #pragma unroll
-    for (int j = 0; j < KW; ++j) xv[j] = __ldg(xp + j);
+    for (int j = 0; j < KW; ++j) xv[j] = (double)x.at(i0 + j);
     int r = KW;
 #pragma unroll
     for (int j = 0; j < KW; ++j) {
       acc[j] += xv[j];
 #pragma unroll
       for (int jj = j; jj < KW; ++jj) {
-        acc[r] = fmaf(xv[j], xv[jj], acc[r]);
+        acc[r] = fma(xv[j], xv[jj], acc[r]);
         ++r;
       }
     }
@@ -87,8 +124,8 @@ __global__ void __launch_bounds__(256) conv0_stats_kernel(const Conv0Params p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int i = 0; i < NACC; ++i) {
-    float v = warp_sum(acc[i]);
-    if (lane == 0) red[warp][i] = (double)v;
+    const double v = warp_sum_f64(acc[i]);
+    if (lane == 0) red[warp][i] = v;
   }
   __syncthreads();
   if (threadIdx.x < NACC) {
@@ -165,15 +202,17 @@ __global__ void __launch_bounds__(256, 2) conv0_kernel(const Conv0Params p, int 
   float* fmean = xs + FT * p.stride + KW;  // [FT] (layer variant)
   float* frstd = fmean + FT;
   float2* xs2 = reinterpret_cast<float2*>(frstd + FT + ((FT * p.stride + KW) & 1));  // (x, x) pairs, 8-byte aligned
+  __shared__ uint32_t zs[64];
   pdl_trigger();
   pdl_wait();
   const int row = blockIdx.y;
   const int f0 = blockIdx.x * FT;
   const int nf = min(FT, p.T0 - f0);
-  const float* x = p.x + (long long)row * p.ld + (long long)f0 * p.stride;
+  const WaveRow x = wave_row(p.dyn, row, zs);
+  const long long x0 = (long long)f0 * p.stride;
   const int nwin = (nf - 1) * p.stride + KW;
   for (int i = threadIdx.x; i < nwin; i += blockDim.x) {
-    const float t = __ldg(x + i);
+    const float t = x.at(x0 + i);
     xs[i] = t;
     xs2[i] = make_float2(t, t);
   }
@@ -261,16 +300,18 @@ __global__ void __launch_bounds__(256, 2) conv0_mma_kernel(const Conv0Params p, 
   extern __shared__ __align__(16) uint8_t im2col[];
   constexpr int LDA = 80;
   static_assert(3 * KW + 2 == 32, "K layout");
+  __shared__ uint32_t zs[64];
   pdl_trigger();
   pdl_wait();
   const int row = blockIdx.y;
   const int f0 = blockIdx.x * FT;
   const int nf = min(FT, p.T0 - f0);
   const int nfp = (nf + 15) & ~15;
-  const float* x = p.x + (long long)row * p.ld + (long long)f0 * p.stride;
+  const WaveRow x = wave_row(p.dyn, row, zs);
+  const long long x0 = (long long)f0 * p.stride;
   for (int i = threadIdx.x; i < nfp * KW; i += blockDim.x) {
     const int f = i / KW, j = i - f * KW;
-    const float v = f < nf ? __ldg(x + f * p.stride + j) : 0.f;
+    const float v = f < nf ? x.at(x0 + f * p.stride + j) : 0.f;
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
     __nv_bfloat16* ar = reinterpret_cast<__nv_bfloat16*>(im2col + f * LDA);
@@ -329,8 +370,7 @@ __global__ void __launch_bounds__(256, 2) conv0_mma_kernel(const Conv0Params p, 
 
 std::string launch_conv0(const Conv0Params& p, bool layer_norm, cudaStream_t s) {
   if (p.kw != 10) return "conv0: only kernel width 10 is implemented for layer 0";
-  static const bool mma_enabled = getenv("W2S_NO_CONV0_MMA") == nullptr;
-  if (!layer_norm && mma_enabled && p.gn_wb && p.C % 64 == 0 && p.C <= 512 && p.n > 0) {
+  if (!layer_norm && p.gn_wb && p.C % 64 == 0 && p.C <= 512 && p.n > 0) {
     const int FT = 512;
     dim3 grid((p.T0 + FT - 1) / FT, p.n);
     W2S_CUDA_OK(launch_pdl(conv0_mma_kernel<10>, grid, dim3(p.C / 2), (size_t)FT * 80, s, 1, p, FT));

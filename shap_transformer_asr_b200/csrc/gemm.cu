@@ -40,8 +40,7 @@ struct TcCfg {
 struct TileCoord {
   int g, b, m0, n0;
 };
-template <bool MC>
-__device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int unit, int rank, int BN) {
+__device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int unit, int BN) {
   TileCoord c;
   int nt = unit % p.tiles_n;
   int r = unit / p.tiles_n;
@@ -49,19 +48,18 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmDev& p, int unit, int
   r /= p.units_m;
   c.b = r % p.Bz;
   c.g = r / p.Bz;
-  c.m0 = (MC ? 2 * mu + rank : mu) * 128;   // an odd tile count leaves the last pair's second tile empty (all rows masked)
+  c.m0 = mu * 128;
   c.n0 = nt * BN;
   return c;
 }
 
-template <int BN, bool MC>
+template <int BN>
 __global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                const GemmDev p) {
   using C = TcCfg<BN>;
-  const int rank = MC ? (int)cluster_ctarank() : 0;
-  const int unit0 = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int unit_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int unit0 = (int)blockIdx.x;
+  const int unit_step = (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t tiles = (raw + 1023u) & ~1023u;
@@ -84,7 +82,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 9 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), MC ? 2 : 1);   // multicast: the peer's W half also lands in this stage
+      mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -99,7 +97,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (MC) cluster_sync_all();   // barrier inits visible to the peer before any multicast traffic
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_trigger();
@@ -110,7 +107,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       for (int unit = unit0; unit < p.num_units; unit += unit_step) {
-        const TileCoord tc = decode_tile<MC>(p, unit, rank, BN);
+        const TileCoord tc = decode_tile(p, unit, BN);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
@@ -118,13 +115,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const int kcol = kb - krow * p.a_kb_per_row;
           const uint32_t sa = tiles + stage * C::STAGE_BYTES;
           tma_load_3d(sa, &mapA, full_bar(stage), tc.g * p.a_g_col + kcol * 64, tc.m0 + krow, tc.b);
-          if constexpr (MC) {
-            // this CTA fetches half of the W tile and multicasts it to both CTAs of the pair
-            tma_load_3d_mc(sa + C::A_BYTES + rank * (C::B_BYTES / 2), &mapW, full_bar(stage), kb * 64,
-                           tc.n0 + rank * (BN / 2), tc.g, (uint16_t)0x3);
-          } else {
-            tma_load_3d(sa + C::A_BYTES, &mapW, full_bar(stage), kb * 64, tc.n0, tc.g);
-          }
+          tma_load_3d(sa + C::A_BYTES, &mapW, full_bar(stage), kb * 64, tc.n0, tc.g);
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -154,8 +145,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             // +32 bytes per K=16 step inside the 128-byte swizzle row: +2 in the (addr >> 4) field
             umma_bf16(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          if constexpr (MC) umma_commit_mc(empty_bar(stage), (uint16_t)0x3);
-          else umma_commit(empty_bar(stage));
+          umma_commit(empty_bar(stage));
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -171,7 +161,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int unit = unit0; unit < p.num_units; unit += unit_step) {
-      const TileCoord tc = decode_tile<MC>(p, unit, rank, BN);
+      const TileCoord tc = decode_tile(p, unit, BN);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int m = tc.m0 + q * 32 + lane;
@@ -195,7 +185,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
-  if constexpr (MC) cluster_sync_all();   // the peer may still be multicasting into / signalling this CTA
   if (warp == 10) {
     tc_fence_after();
     tmem_dealloc<C::TMEM_COLS>(tmem_base);
@@ -267,11 +256,7 @@ static std::string g_init_err;
 
 template <int BN>
 static cudaError_t set_attr() {
-  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)TcCfg<BN>::SMEM);
-  if (e == cudaSuccess && BN >= 128)
-    e = cudaFuncSetAttribute(gemm_tc_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<BN>::SMEM);
-  return e;
+  return cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<BN>::SMEM);
 }
 
 std::string gemm_init() {
@@ -347,10 +332,8 @@ std::string gemm_prepare(const GemmProblem& p, int num_sms, GemmLaunch* out) {
   d.tiles_n = p.N / bn;
   d.num_tiles = d.tiles_m * d.tiles_n * p.Bz * p.G;
   d.num_kb = p.K / 64;
-  // W-tile multicast over CTA pairs: worth it when there are enough tiles to keep all pairs busy
-  static const bool mc_enabled = getenv("W2S_NO_MULTICAST") == nullptr;
-  static const bool pair_enabled = getenv("W2S_NO_PAIR") == nullptr;  // tcgen05 cta_group::2 pairs by default
-  out->mc = (mc_enabled && bn >= 128 && d.tiles_m >= 2 && d.num_tiles >= 2 * num_sms) ? (pair_enabled ? 2 : 1) : 0;
+  // CTA pairs (tcgen05 cta_group::2, 256-row tiles) when there are enough tiles to keep all pairs busy
+  out->mc = (bn >= 128 && d.tiles_m >= 2 && d.num_tiles >= 2 * num_sms) ? 2 : 0;
   d.units_m = out->mc ? (d.tiles_m + 1) / 2 : d.tiles_m;
   d.num_units = d.units_m * d.tiles_n * p.Bz * p.G;
   d.a_kb_per_row = p.a_kb_per_row;
@@ -383,8 +366,7 @@ std::string gemm_prepare(const GemmProblem& p, int num_sms, GemmLaunch* out) {
   }
   // pair kernel: TMA-store epilogue (not for the GLU epilogue, whose output width differs from the tile width)
   out->tma_out = 0;
-  static const bool tma_out_enabled = getenv("W2S_NO_TMA_STORE") == nullptr;
-  if (out->mc == 2 && tma_out_enabled && !p.epi.glu) {
+  if (out->mc == 2 && !p.epi.glu) {
     const uint64_t es = p.epi.out_fp32 ? 4 : 2;
     const uint64_t ldb = p.Bz > 1 ? (uint64_t)p.epi.ldb : (uint64_t)p.epi.ldm * p.M;
     const uint64_t ldg = p.G > 1 ? (uint64_t)p.epi.ldg : ldb * p.Bz;
@@ -399,25 +381,14 @@ std::string gemm_prepare(const GemmProblem& p, int num_sms, GemmLaunch* out) {
   return "";
 }
 
-template <int BN>
-static cudaError_t launch_mc(const GemmLaunch& l, cudaStream_t s) {
-  return launch_pdl(gemm_tc_kernel<BN, true>, dim3(l.grid), dim3(384), l.smem, s, 2, l.mapA, l.mapW, l.dev);
-}
-
 std::string gemm_launch_tc(const GemmLaunch& l, cudaStream_t s) {
   if (l.mc == 2) return gemm2_launch(l, s);
-  if (l.mc) {
-    if (l.bn == 256) W2S_CUDA_OK(launch_mc<256>(l, s));
-    else if (l.bn == 128) W2S_CUDA_OK(launch_mc<128>(l, s));
-    else return "gemm: multicast needs BN >= 128";
-    return "";
-  }
   switch (l.bn) {
-    case 256: W2S_CUDA_OK(launch_pdl(gemm_tc_kernel<256, false>, dim3(l.grid), dim3(384), l.smem, s, 1, l.mapA, l.mapW, l.dev)); break;
-    case 128: W2S_CUDA_OK(launch_pdl(gemm_tc_kernel<128, false>, dim3(l.grid), dim3(384), l.smem, s, 1, l.mapA, l.mapW, l.dev)); break;
-    case 64: W2S_CUDA_OK(launch_pdl(gemm_tc_kernel<64, false>, dim3(l.grid), dim3(384), l.smem, s, 1, l.mapA, l.mapW, l.dev)); break;
-    case 48: W2S_CUDA_OK(launch_pdl(gemm_tc_kernel<48, false>, dim3(l.grid), dim3(384), l.smem, s, 1, l.mapA, l.mapW, l.dev)); break;
-    case 32: W2S_CUDA_OK(launch_pdl(gemm_tc_kernel<32, false>, dim3(l.grid), dim3(384), l.smem, s, 1, l.mapA, l.mapW, l.dev)); break;
+    case 256: W2S_CUDA_OK(launch_pdl(gemm_tc_kernel<256>, dim3(l.grid), dim3(384), l.smem, s, 1, l.mapA, l.mapW, l.dev)); break;
+    case 128: W2S_CUDA_OK(launch_pdl(gemm_tc_kernel<128>, dim3(l.grid), dim3(384), l.smem, s, 1, l.mapA, l.mapW, l.dev)); break;
+    case 64: W2S_CUDA_OK(launch_pdl(gemm_tc_kernel<64>, dim3(l.grid), dim3(384), l.smem, s, 1, l.mapA, l.mapW, l.dev)); break;
+    case 48: W2S_CUDA_OK(launch_pdl(gemm_tc_kernel<48>, dim3(l.grid), dim3(384), l.smem, s, 1, l.mapA, l.mapW, l.dev)); break;
+    case 32: W2S_CUDA_OK(launch_pdl(gemm_tc_kernel<32>, dim3(l.grid), dim3(384), l.smem, s, 1, l.mapA, l.mapW, l.dev)); break;
     default: return "gemm: bad BN";
   }
   W2S_CUDA_OK(cudaGetLastError());

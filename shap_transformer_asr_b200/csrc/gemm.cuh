@@ -39,7 +39,7 @@ struct GemmProblem {
 struct GemmDev {
   int M, N, K, Bz, G;
   int tiles_m, tiles_n, num_tiles, num_kb;
-  int units_m, num_units;  // scheduling units: tiles, or M-pairs of tiles when the W tile is multicast over a CTA pair
+  int units_m, num_units;  // scheduling units: tiles, or M-pairs of tiles for the CTA-pair kernel
   int a_kb_per_row, a_g_col;
   // validation-kernel addressing
   const __nv_bfloat16* a;
@@ -54,8 +54,7 @@ struct GemmLaunch {
   int tma_out = 0;
   GemmDev dev;
   int bn = 0;
-  int mc = 0;   // 1: clusters of 2 CTAs (adjacent M tiles) share every W tile through TMA multicast
-                // 2: CTA pairs form one tcgen05.mma cta_group::2 unit (256-row tile, W split across the pair)
+  int mc = 0;   // 2: CTA pairs form one tcgen05.mma cta_group::2 unit (256-row tile, W split across the pair); 0: one CTA per tile
   int grid = 0;
   size_t smem = 0;
 };

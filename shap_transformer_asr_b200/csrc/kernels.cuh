@@ -9,10 +9,31 @@ namespace w2s {
 std::string launch_mask(const float* x, const uint16_t* seg_id, const uint32_t* zbits, int zwords, long long K,
                         long long L, float baseline, float* out, long long ld, cudaStream_t s);
 
+// ---- per-call arguments, read by the kernels from device memory ---------------------------------------------
+// Everything that may change between two evaluations of the same batch-tile plan lives here instead of in kernel
+// parameters, so a plan can be captured once into a CUDA graph and replayed: one tiny kernel writes this block
+// before each tile (api.cu: set_dyn_kernel), the first and the last kernels of the plan read it.
+struct DynArgs {
+  // input rows of this tile: explicit waveforms x[n, ld] (w2s_eval_waveforms) ...
+  const float* x;
+  long long ld;
+  // ... or the masker folded into the consumer's load (w2s_eval): row r = keep-bit(zbits[r], seg_id[i]) ? clip[i] :
+  // baseline, so the [n, L] masked waveforms are never materialised (conformer_test.ipynb:138-141 semantics)
+  const float* clip;        // [L]; null selects `x`
+  const uint16_t* seg_id;   // [L]
+  const uint32_t* zbits;    // [n, zwords]
+  int zwords;
+  float baseline;
+  // output reduction (w2s_set_targets) and destination of this tile
+  float* out;               // [n, width]
+  int mode, D;
+  const int* frames;        // [D] device
+  const int* tokens;        // [D] device
+};
+
 // ---- K1: conv0 (Cin = 1) + GroupNorm-over-time / LayerNorm-over-channels + GELU ------------------------
 struct Conv0Params {
-  const float* x;        // [n, ld] waveforms
-  long long ld;
+  const DynArgs* dyn;    // input rows (device)
   int n, L, T0, C, kw, stride;
   const float* w;        // [C][kw] fp32
   const float* bias;     // [C] or null
@@ -67,20 +88,14 @@ struct AttnParams {
   const __nv_bfloat16* pos_proj;  // [2T-1, H] linear_pos(rel_pos_emb), row r <-> relative position T-1-r
 };
 std::string launch_attention_simt(const AttnParams& p, cudaStream_t s);
-struct AttnTcPlan;  // opaque: tensor maps + launch geometry
-std::string attention_tc_init();
-std::string attention_tc_prepare(const AttnParams& p, AttnTcPlan** plan);
-std::string attention_tc_launch(const AttnTcPlan* plan, cudaStream_t s);
-void attention_tc_free(AttnTcPlan* plan);
-bool attention_tc_supported(const AttnParams& p);
-// persistent, warp-specialised variant with independent key blocks (attention_fa.cu); preferred when supported
+// persistent, warp-specialised tcgen05 kernel with independent key blocks (attention_fa.cu)
 struct AttnFaPlan;
 std::string attention_fa_init();
 bool attention_fa_supported(const AttnParams& p);
 std::string attention_fa_prepare(const AttnParams& p, int num_sms, AttnFaPlan** plan);
 std::string attention_fa_launch(const AttnFaPlan* plan, cudaStream_t s);
 void attention_fa_free(AttnFaPlan* plan);
-// conformer relative-position attention on tcgen05 (T' <= 256)
+// conformer relative-position attention on tcgen05
 struct AttnRelPlan;
 std::string attention_rel_init();
 bool attention_rel_supported(const AttnParams& p);
@@ -104,19 +119,19 @@ struct HeadParams {
   const __nv_bfloat16* h;     // [n*T, H]
   const __nv_bfloat16* w;     // [V, H]
   const float* bias;          // [V]
-  int n, T, H, V, mode, D;
-  const int* frames;          // [D] device
-  const int* tokens;          // [D] device
-  float* out;                 // [n, width]
+  int n, T, H, V;
+  int ldl;                    // row stride of the logits buffer (V rounded up to a multiple of 32)
+  const DynArgs* dyn;         // mode, targets and output pointer of this call (device)
 };
+// CUDA-core validation variant (W2S_FLAG_VALIDATE_GEMM): lm_head + reduction in one kernel
 std::string launch_head(const HeadParams& p, cudaStream_t s);
-// tensor-core variant: the contraction kernel writes logits[n*T, V] (fp32, bias added), this reduces them
+// tensor-core variant: the contraction kernel writes logits[n*T, ldl] (fp32, bias added), this reduces them
 std::string launch_head_reduce(const float* logits, const HeadParams& p, cudaStream_t s);
 
 // ---- K12: KernelSHAP constrained WLS -----------------------------------------------------------------------
 std::string launch_wls(const uint32_t* zbits, int zwords, const double* w, const float* y, long long K, int M,
                        int D, const double* fx, const double* fnull, double* phi, int32_t* status,
-                       double* work /* (M-1)*(M-1) + (M-1)*D doubles */, cudaStream_t s);
+                       double* work /* 2 * ((M-1)*(M-1) + (M-1)*D) doubles */, cudaStream_t s);
 
 // ---- weight re-layout (run once at create) -------------------------------------------------------------------
 // y[i] += x[i]

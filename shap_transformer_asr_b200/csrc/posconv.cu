@@ -223,9 +223,7 @@ std::string posconv_prepare(const __nv_bfloat16* x, const __nv_bfloat16* w, int 
   pl->ng = cpg;
   pl->dev.T = T; pl->dev.cpg = cpg; pl->dev.G = G; pl->dev.B = B; pl->dev.kpos = kpos;
   {
-    const char* e = getenv("W2S_PC_TPS");
-    int tps = e ? atoi(e) : 8;
-    if (tps < 1 || tps > 8) tps = 8;
+    int tps = 8;   // taps per weight-ring stage (one barrier round trip per stage)
     const int slots = cpg == 64 ? PcCfg<64>::WSTAGES : PcCfg<48>::WSTAGES;
     while (tps > 1 && (kpos % tps || slots / tps < 2)) --tps;
     pl->dev.tps = tps;

@@ -36,7 +36,8 @@ class Engine:
     plain ``state_dict`` with HF parameter names plus an explicit :class:`ModelConfig`."""
 
     def __init__(self, model, config: Optional[ModelConfig] = None, device: int = 0, max_batch: int = 0,
-                 validate_gemm: bool = False, validate_attn: bool = False):
+                 validate_gemm: bool = False, validate_attn: bool = False, preln_bf16: bool = False,
+                 pdl: bool = False, graphs: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("no CUDA device: the masked-coalition path has no CPU fallback")
         self.lib = _lib.load()
@@ -86,7 +87,9 @@ class Engine:
         cfg.hidden_act = {"gelu": 0, "swish": 1, "silu": 1}[config.hidden_act]
         cfg.rotary_embedding_base = config.rotary_embedding_base
         cfg.max_batch = int(max_batch)
-        cfg.flags = (_lib.FLAG_VALIDATE_GEMM if validate_gemm else 0) | (_lib.FLAG_VALIDATE_ATTN if validate_attn else 0)
+        cfg.flags = ((_lib.FLAG_VALIDATE_GEMM if validate_gemm else 0) | (_lib.FLAG_VALIDATE_ATTN if validate_attn else 0)
+                     | (_lib.FLAG_BF16_PRELN if preln_bf16 else 0) | (_lib.FLAG_PDL if pdl else 0)
+                     | (0 if graphs else _lib.FLAG_NO_GRAPH))
         names = list(keep.keys())
         n = len(names)
         c_names = (C.c_char_p * n)(*[s.encode() for s in names])
@@ -98,6 +101,8 @@ class Engine:
             raise RuntimeError("w2s_create: " + self.lib.w2s_last_error(None).decode())
         self._h = handle
         self._cfg_struct = cfg
+        self._pin_bits = None
+        self._pin_event = torch.cuda.Event()
         self.max_batch = max_batch
         self.num_samples = 0
         self.num_segments = 0
@@ -149,9 +154,9 @@ class Engine:
             if f.shape != t.shape:
                 raise ValueError("frames and tokens must have the same length")
             rc = self.lib.w2s_set_targets(self._h, f.ctypes.data_as(C.POINTER(C.c_int32)),
-                                          t.ctypes.data_as(C.POINTER(C.c_int32)), int(f.size), mid)
+                                          t.ctypes.data_as(C.POINTER(C.c_int32)), int(f.size), mid, self._stream())
         else:
-            rc = self.lib.w2s_set_targets(self._h, None, None, 0, mid)
+            rc = self.lib.w2s_set_targets(self._h, None, None, 0, mid, self._stream())
         self._check(rc, "w2s_set_targets")
         self.mode = mode
 
@@ -199,8 +204,26 @@ class Engine:
 
     # -- convenience (host buffers) ---------------------------------------------------------------------
     def bits_to_device(self, Z) -> torch.Tensor:
-        words = pack_coalitions(Z).view(np.int32)
-        return torch.from_numpy(words).pin_memory().to(self.device, non_blocking=True)
+        """Host {0,1} matrix [K, M] (or already packed uint32 words [K, ceil(M/32)]) -> device int32 words.  The
+        pinned staging buffer is owned by the engine and re-used (grown geometrically) across calls."""
+        Z = np.asarray(Z)
+        words = (Z if Z.dtype == np.uint32 else pack_coalitions(Z)).view(np.int32)
+        n = words.size
+        if self._pin_bits is None or self._pin_bits.numel() < n:
+            self._pin_bits = torch.empty(max(n, 2 * (self._pin_bits.numel() if self._pin_bits is not None else 0)),
+                                         dtype=torch.int32).pin_memory()
+        else:
+            # the previous upload from this buffer must have left the host before it is overwritten
+            self._pin_event.synchronize()
+        stage = self._pin_bits[:n].view(words.shape)
+        stage.numpy()[...] = words
+        dev = stage.to(self.device, non_blocking=True)
+        self._pin_event.record(torch.cuda.current_stream())
+        return dev
+
+    def launch_count(self) -> int:
+        """Kernel launches issued by eval_bits / eval_waveforms on this engine so far (counted in the library)."""
+        return int(self.lib.w2s_launch_count(self._h))
 
     def flops_per_forward(self, num_samples: Optional[int] = None) -> float:
         return float(self.lib.w2s_flops_per_forward(self._h, int(num_samples or self.num_samples)))
@@ -228,13 +251,21 @@ class Engine:
         return int(a.value), int(b.value)
 
 
-def debug_gemm(a: torch.Tensor, w: torch.Tensor, bias=None, act: int = 0, out_fp32: bool = True, tcgen05: bool = True):
-    """out[M, N] = act(a[M, K] @ w[N, K]^T + bias) through the library's contraction kernels (tests only)."""
+def debug_gemm(a: torch.Tensor, w: torch.Tensor, bias=None, act: int = 0, out_fp32: bool = True, tcgen05: bool = True,
+               residual=None, alpha: float = 1.0, accumulate_into=None):
+    """out[M, N] = act(a[M, K] @ w[N, K]^T + bias) * alpha + residual through the library's contraction kernels
+    (tests only).  ``accumulate_into`` (fp32 [M, N]): in-place accumulation, residual == out -- the case the CTA-pair
+    kernel serves with TMA reduce-add."""
     lib = _lib.load()
     M, K = a.shape
     N = w.shape[0]
-    out = torch.empty((M, N), dtype=torch.float32 if out_fp32 else torch.bfloat16, device=a.device)
+    if accumulate_into is not None:
+        out, residual, out_fp32 = accumulate_into, accumulate_into, True
+    else:
+        out = torch.empty((M, N), dtype=torch.float32 if out_fp32 else torch.bfloat16, device=a.device)
     rc = lib.w2s_debug_gemm(int(tcgen05), a.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None,
+                            residual.data_ptr() if residual is not None else None,
+                            int(residual is not None and residual.dtype == torch.float32), float(alpha),
                             out.data_ptr(), M, N, K, act, int(out_fp32), torch.cuda.current_stream().cuda_stream)
     if rc != 0:
         raise RuntimeError("w2s_debug_gemm: " + lib.w2s_last_error(None).decode())

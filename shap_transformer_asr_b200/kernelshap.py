@@ -9,6 +9,7 @@ pinned to ``False`` (plain constrained WLS, solved on the device by ``w2s_wls``)
 """
 from __future__ import annotations
 
+import ctypes as C
 import itertools
 from math import comb
 from typing import Optional
@@ -16,24 +17,38 @@ from typing import Optional
 import numpy as np
 import torch
 
+from . import _lib
 from . import dist as wdist
-from .preprocess import pack_coalitions
 from .targets import char_targets
 
 
-def sample_coalitions(M: int, nsamples="auto", seed: Optional[int] = None):
-    """-> (Z uint8 [K, M] with 1 = segment kept, kernel weights float64 [K], info dict)."""
+def unpack_coalitions(words: np.ndarray, M: int) -> np.ndarray:
+    """uint32 words [K, ceil(M/32)] -> uint8 {0,1} matrix [K, M] (inverse of preprocess.pack_coalitions)."""
+    w = np.ascontiguousarray(words, dtype=np.uint32)
+    bits = np.unpackbits(w.view(np.uint8).reshape(w.shape[0], -1), axis=1, bitorder="little")
+    return np.ascontiguousarray(bits[:, :M])
+
+
+def sample_coalitions(M: int, nsamples="auto", seed: Optional[int] = None, packed: bool = False):
+    """-> (Z uint8 [K, M] with 1 = segment kept, kernel weights float64 [K], info dict); ``packed=True`` returns the
+    bit-packed uint32 words [K, ceil(M/32)] (what the device consumes) instead of Z.
+
+    All floating-point work (size weights, ``np.random.choice``, weight scaling) is numpy's own; the per-draw
+    ``np.random.permutation(M)`` loop runs natively on numpy's MT19937 state (``w2s_sample_rows``, csrc/sampler.cu)."""
     if seed is not None:
         np.random.seed(seed)
     M = int(M)
     if M < 2:
         raise ValueError("KernelSHAP needs at least 2 features")
+    if M > 2048:
+        raise ValueError("at most 2048 segments are supported")
     nsamples = 2 * M + 2 ** 11 if nsamples == "auto" else int(nsamples)
     max_samples = 2 ** 30
     if M <= 30:
         max_samples = 2 ** M - 2
         nsamples = min(nsamples, max_samples)
-    Z = np.zeros((nsamples, M), dtype=np.uint8)
+    W = (M + 31) // 32
+    words = np.zeros((nsamples, W), dtype=np.uint32)
     kw = np.zeros(nsamples, dtype=np.float64)
     added = 0
 
@@ -47,6 +62,8 @@ def sample_coalitions(M: int, nsamples="auto", seed: Optional[int] = None):
     n_full = 0
     left = nsamples
     rem = wv.copy()
+    full = np.uint32(0xFFFFFFFF)
+    tail = np.uint32((1 << (M % 32)) - 1) if M % 32 else full
     for size in range(1, n_sizes + 1):
         nsub = float(comb(M, size))
         if size <= n_paired:
@@ -59,14 +76,21 @@ def sample_coalitions(M: int, nsamples="auto", seed: Optional[int] = None):
             w = wv[size - 1] / comb(M, size)
             if size <= n_paired:
                 w /= 2.0
-            for inds in itertools.combinations(range(M), size):
-                Z[added, list(inds)] = 1
-                kw[added] = w
-                added += 1
-                if size <= n_paired:
-                    Z[added] = 1 - Z[added - 1]
-                    kw[added] = w
-                    added += 1
+            # itertools.combinations order, each subset followed by its complement when paired
+            idx = np.fromiter(itertools.chain.from_iterable(itertools.combinations(range(M), size)), dtype=np.int64)
+            idx = idx.reshape(-1, size)
+            rows = np.zeros((idx.shape[0], W), dtype=np.uint32)
+            r = np.repeat(np.arange(idx.shape[0]), size)
+            np.bitwise_or.at(rows, (r, (idx >> 5).ravel()), (np.uint32(1) << (idx & 31).astype(np.uint32)).ravel())
+            if size <= n_paired:
+                comp = ~rows
+                comp[:, -1] &= tail
+                block = np.stack([rows, comp], axis=1).reshape(-1, W)
+            else:
+                block = rows
+            words[added:added + block.shape[0]] = block
+            kw[added:added + block.shape[0]] = w
+            added += block.shape[0]
         else:
             break
 
@@ -77,48 +101,25 @@ def sample_coalitions(M: int, nsamples="auto", seed: Optional[int] = None):
         rem[:n_paired] /= 2
         rem = rem[n_full:]
         rem /= np.sum(rem)
-        ind_set = np.random.choice(len(rem), 4 * samples_left, p=rem)
-        pos = 0
-        seen = {}
-        # rows are collected as (index in Z, permutation prefix, complement flag) and written in one vectorised pass at
-        # the end; the RNG call sequence (one permutation per draw) is exactly shap's
-        row = np.zeros(M, dtype=np.uint8)
-        new_at, new_rows, comp_at = [], [], []
-        while samples_left > 0 and pos < len(ind_set):
-            size = int(ind_set[pos]) + n_full + 1
-            pos += 1
-            row[:] = 0
-            row[np.random.permutation(M)[:size]] = 1
-            key = row.tobytes()
-            at = seen.get(key)
-            fresh = at is None
-            if fresh:
-                seen[key] = added
-                samples_left -= 1
-                new_at.append(added)
-                new_rows.append(key)
-                kw[added] = 1.0
-                added += 1
-            else:
-                kw[at] += 1.0
-            if samples_left > 0 and size <= n_paired:
-                if fresh:
-                    samples_left -= 1
-                    comp_at.append((added, len(new_rows) - 1))
-                    kw[added] = 1.0
-                    added += 1
-                else:
-                    kw[at + 1] += 1.0
-        if new_rows:
-            R = np.frombuffer(b"".join(new_rows), dtype=np.uint8).reshape(len(new_rows), M)
-            Z[np.asarray(new_at)] = R
-            if comp_at:
-                ca = np.asarray(comp_at)
-                Z[ca[:, 0]] = 1 - R[ca[:, 1]]
+        ind_set = np.ascontiguousarray(np.random.choice(len(rem), 4 * samples_left, p=rem), dtype=np.int64)
+        # one np.random.permutation(M) per draw, de-duplication and complements: native, on numpy's own generator state
+        lib = _lib.load()
+        name, key, pos, has_gauss, cached = np.random.get_state()
+        key = np.ascontiguousarray(key, dtype=np.uint32).copy()
+        cpos = C.c_int32(int(pos))
+        used = C.c_int64(0)
+        new_added = lib.w2s_sample_rows(M, n_full, n_paired, ind_set.ctypes.data, len(ind_set), samples_left, added,
+                                        key.ctypes.data, C.byref(cpos), words.ctypes.data, kw.ctypes.data, nsamples,
+                                        C.byref(used))
+        if new_added < 0:
+            raise RuntimeError("w2s_sample_rows failed")
+        np.random.set_state((name, key, int(cpos.value), has_gauss, cached))
+        added = int(new_added)
         weight_left = np.sum(wv[n_full:])
-        kw[n_fixed:] *= weight_left / kw[n_fixed:].sum()
+        kw[n_fixed:added] *= weight_left / kw[n_fixed:added].sum()
     info = dict(nsamples=nsamples, n_fixed=n_fixed, n_full_sizes=n_full, max_samples=max_samples)
-    return Z[:added], kw[:added], info
+    words, kw = words[:added], kw[:added]
+    return (words if packed else unpack_coalitions(words, M)), kw, info
 
 
 class KernelShapExplainer:
@@ -142,45 +143,62 @@ class KernelShapExplainer:
         eng.set_targets(mode, frames, tokens)
         return frames, tokens, logits
 
-    def explain(self, clip, num_segments: int, mode: str = "logprob", targets=None, baseline: float = 0.0):
+    def explain(self, clip, num_segments: int, mode: str = "logprob", targets=None, baseline: float = 0.0,
+                check: bool = True):
+        """-> dict(phi[M, D] fp64 device, fx, fnull, frames, tokens, Z, weights, y, status, info).
+
+        ``check`` reads the solve's status word back (one 4-byte D2H after the solve) and raises if the regression
+        did not produce a usable answer; a rank-deficient design (status 2: fewer distinct coalitions than segments)
+        is solved for the minimum-norm attributions exactly as shap's ``lstsq`` fallback does and only warns."""
         eng = self.engine
         eng.set_clip(clip, num_segments=num_segments, baseline=baseline)
+        M = eng.num_segments
+        sampled = None
         if mode in ("max", "mean", "logits"):
             frames, tokens = (), ()
             eng.set_targets(mode)
-        M = eng.num_segments
-        Z = None
-        if mode in ("max", "mean", "logits"):
-            pass
         elif targets is None:
-            # the one-row target-selection forward is asynchronous on the engine's stream: draw the coalitions on the
-            # host while it runs, read the logits back afterwards
+            # the one-row target-selection forward (one graph replay) is asynchronous on the engine's stream: the
+            # coalitions are drawn on the host while it runs, the logits are read back afterwards
             eng.set_targets("logits")
             ones = eng.bits_to_device(np.ones((1, M), dtype=np.uint8))
             logits_dev = eng.eval_bits(ones)
-            Z, kw, info = sample_coalitions(M, self.nsamples, seed=self.seed)
+            sampled = sample_coalitions(M, self.nsamples, seed=self.seed, packed=True)
             logits = logits_dev.view(-1, eng.config.vocab_size).cpu().numpy()
             frames, tokens = char_targets(logits)
             eng.set_targets(mode, frames, tokens)
         else:
             frames, tokens = targets
             eng.set_targets(mode, frames, tokens)
-        if Z is None:
-            Z, kw, info = sample_coalitions(M, self.nsamples, seed=self.seed)
-        K = Z.shape[0]
-        # rows 0/1 of the evaluated matrix are the empty and the full coalition (fnull, fx)
-        Zall = np.concatenate([np.zeros((1, M), np.uint8), np.ones((1, M), np.uint8), Z])
+        if sampled is None:
+            sampled = sample_coalitions(M, self.nsamples, seed=self.seed, packed=True)
+        words, kw, info = sampled
+        K = words.shape[0]
+        # rows 0 / 1 of the evaluated matrix are the empty and the full coalition (fnull, fx): fx comes from the same
+        # reduction kernel as every y row, so the efficiency constraint is consistent to the last bit
+        head = np.zeros((2, words.shape[1]), dtype=np.uint32)
+        head[1] = 0xFFFFFFFF
+        if M % 32:
+            head[1, -1] = (1 << (M % 32)) - 1
         rank, world = wdist.rank_world()
         lo, hi = wdist.shard_range(K + 2, rank, world)
-        bits_all = eng.bits_to_device(Zall)
+        bits_all = eng.bits_to_device(np.concatenate([head, words]))
         y_local = eng.eval_bits(bits_all[lo:hi]) if hi > lo else torch.empty((0, eng.out_width()), device=eng.device)
         y_all = wdist.all_gather_rows(y_local, K + 2, rank, world)
         fnull = y_all[0].double()
         fx = y_all[1].double()
-        w_dev = torch.from_numpy(kw).to(eng.device)
-        phi, status = eng.wls(bits_all[2:], w_dev, y_all[2:].contiguous(), fx, fnull, M)
-        return dict(phi=phi, fx=fx, fnull=fnull, frames=frames, tokens=tokens, Z=Z, weights=kw, y=y_all[2:],
-                    status=status, info=info)
+        w_dev = torch.from_numpy(kw).to(eng.device, non_blocking=True)
+        phi, status = eng.wls(bits_all[2:], w_dev, y_all[2:], fx, fnull, M)
+        if check:
+            st = int(status.item())
+            if st == 1:
+                raise RuntimeError("KernelSHAP regression did not converge (w2s_wls status 1)")
+            if st == 2:
+                import warnings
+                warnings.warn(f"KernelSHAP design is rank deficient ({K} coalitions for {M} segments): minimum-norm "
+                              "attributions returned (shap's lstsq fallback)", RuntimeWarning)
+        return dict(phi=phi, fx=fx, fnull=fnull, frames=frames, tokens=tokens, Z=unpack_coalitions(words, M), weights=kw,
+                    y=y_all[2:], status=status, info=info, words=words)
 
 
 def expand_to_samples(phi: np.ndarray, bounds: np.ndarray, per_sample: bool = False) -> np.ndarray:

@@ -131,7 +131,9 @@ class _MockEngine:
 
     def bits_to_device(self, Z):
         from shap_transformer_asr_b200.preprocess import pack_coalitions
-        return torch.from_numpy(pack_coalitions(Z).view(np.int32))
+        Z = np.asarray(Z)
+        words = Z if Z.dtype == np.uint32 else pack_coalitions(Z)       # same contract as Engine.bits_to_device
+        return torch.from_numpy(np.ascontiguousarray(words).view(np.int32))
 
     def _unpack(self, bits):
         w = bits.numpy().view(np.uint32)
