@@ -42,21 +42,17 @@ def load_peaks():
 
 
 def ncu_traffic(workload):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if workload != "C2" or not os.path.exists(p):
-        return None
-    d = json.load(open(p))
-    return d["mean_traffic_bytes_per_launch"]
-
-
-def ncu_traffic_detail(workload):
-    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if workload != "C2" or not os.path.exists(p):
-        return None
-    d = json.load(open(p))
-    return {"dram_bytes_per_launch": d["mean_traffic_bytes_per_launch"],
-            "algorithmic_bytes_per_launch": d["mean_algorithmic_bytes_per_launch"], "source": "profiles/r01_ncu_traffic.json"}
+    """DRAM bytes per launch of the dominant kernel.  NOT measured in this run: read from the committed summary of an
+    `ncu --set full` capture of the same command (profiles/), and labelled as such in the line; None if absent."""
+    for name in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if workload == "C2" and os.path.exists(p):
+            d = json.load(open(p))
+            return d["mean_traffic_bytes_per_launch"], {
+                "dram_bytes_per_launch": d["mean_traffic_bytes_per_launch"],
+                "algorithmic_bytes_per_launch": d["mean_algorithmic_bytes_per_launch"],
+                "source": f"committed ncu file profiles/{name} (not captured in this run)"}
+    return None, None
 
 
 class ClockSampler:
@@ -140,10 +136,12 @@ def cpu_reference_rate(model, cfg, clip, Z, bounds, frames, tokens, n_rows, batc
     run(Z[:min(batch, 4)])                                                  # warm-up excluded
     t0 = time.perf_counter()
     done = 0
+    outs = []
     while done < n_rows:
-        run(Z[done:done + batch])
+        outs.append(run(Z[done:min(done + batch, n_rows)]))
         done += min(batch, n_rows - done)
     dt = time.perf_counter() - t0
+    cpu_reference_rate.last_outputs = torch.cat(outs).numpy()               # kept for the parity check of the bench line
     return done / dt, done, dt, threads
 
 
@@ -201,7 +199,8 @@ def run_b200(args):
     model = make_hf_model(cfg)
     # batch tile: rows = B * T' should fill whole waves of 128-row tiles on 148 SMs (B = floor(148*128*k / T'))
     # (the library picks B = floor(148*128*k / T') with B >= 128 itself when max_batch is 0)
-    eng = Engine(model, cfg, device=local, max_batch=max(0, args.batch))
+    eng = Engine(model, cfg, device=local, max_batch=max(0, args.batch), preln_bf16=args.preln_bf16, pdl=args.pdl,
+                 graphs=not args.no_graph)
     eng.set_clip(clip, num_segments=wl.num_segments)
     # targets: per-character frames of the unmasked clip (all frames if the random-init transcript is empty)
     eng.set_targets("logits")
@@ -232,11 +231,13 @@ def run_b200(args):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    launches0 = eng.launch_count()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     torch.cuda.synchronize()
+    launches = eng.launch_count() - launches0                            # counted inside the library at launch time
     if world > 1:
         td.barrier()
     ms = e0.elapsed_time(e1)
@@ -245,6 +246,42 @@ def run_b200(args):
         t = torch.tensor([ms], device=dev)
         td.all_reduce(t, op=td.ReduceOp.MAX)
         ms = float(t.item())
+
+    # ---- strong scaling, the split north_star names: ONE clip's K coalitions sharded over the ranks (rank r evaluates
+    #      rows [r K/G, (r+1) K/G)), then the single all-gather of the output rows; same timing discipline ----
+    lo, hi = wdist.shard_range(K, rank, world)
+    per = (K + world - 1) // world
+    shard_out = torch.zeros((per, D), dtype=torch.float32, device=dev)
+    strong_all = torch.empty((world * per, D), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def strong_step():
+        flush.fill_(1)
+        if hi > lo:
+            eng.eval_bits(bits[lo:hi], shard_out[:hi - lo])
+        if world > 1:
+            td.all_gather_into_tensor(strong_all, shard_out)
+
+    for _ in range(args.warmup):
+        strong_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        td.barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(args.steps):
+        strong_step()
+    s1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        td.barrier()
+    strong_ms = s0.elapsed_time(s1)
+    if world > 1:
+        t = torch.tensor([strong_ms], device=dev)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        strong_ms = float(t.item())
+        # the sharded outputs are the rows of the full evaluation (same kernels, other tile boundaries)
+        assert torch.equal(strong_all[:K], gathered[rank * K:(rank + 1) * K]) or \
+            (strong_all[:K] - gathered[rank * K:(rank + 1) * K]).abs().max().item() < 1e-3
     # ---- per-launch CUDA-event profile of the same K steps (events between launches cost ~3 us each, so this pass is
     #      kept out of the headline timing; the roofline numbers below come from it) ----
     eng.profile(True)
@@ -285,6 +322,10 @@ def run_b200(args):
     res = ex.explain(clip, num_segments=wl.num_segments)
     torch.cuda.synchronize()
     sec_per_clip = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([sec_per_clip], device=dev, dtype=torch.float64)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        sec_per_clip = float(t.item())
     wls_status = int(res["status"].item())
     eng.set_clip(clip, num_segments=wl.num_segments)
     eng.set_targets("logprob", frames, tokens)
@@ -299,29 +340,51 @@ def run_b200(args):
     total_prof_ms = sum(v["ms"] for v in prof.values())
     achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     launches_per_batch, tile = eng.kernel_count()
+    traffic, traffic_detail = ncu_traffic(wl.name)
     n_batches = (K + tile - 1) // tile
     flops_fwd = eng.flops_per_forward()
-    breakdown = {k: {"ms_per_step": v["ms"] / args.steps, "share": v["ms"] / total_prof_ms,
-                     "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["flops"] and v["ms"] > 0 else None,
-                     "gbs": (v["bytes"] / (v["ms"] / 1e3) / 1e9) if v["bytes"] and v["ms"] > 0 else None}
-                 for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+    # every launch class with its own roofline number: tensor-bound classes against the sustained bf16 peak, the others
+    # against the measured HBM copy bandwidth (conv0 carries both: it is bound by its output stream)
+    breakdown = {}
+    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+        tf = (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["flops"] and v["ms"] > 0 else None
+        gb = (v["bytes"] / (v["ms"] / 1e3) / 1e9) if v["bytes"] and v["ms"] > 0 else None
+        hbm_bound = gb is not None and (tf is None or k in ("conv0", "depthwise"))
+        breakdown[k] = {"ms_per_step": v["ms"] / args.steps, "share": v["ms"] / total_prof_ms, "launches": v["launches"],
+                        "tflops": tf, "gbs": gb, "bound": "hbm" if hbm_bound else "tensor",
+                        "frac_of_peak": (gb / peaks["hbm"]) if hbm_bound else (tf / peaks["tf_sustained"] if tf else None)}
 
     # ---- CPU baseline on this box's host cores: bounded sample of the same workload ----
-    cpu = None
+    cpu, parity = None, None
     if world == 1 and not args.no_cpu:
         from oracle import callback as CB
         bounds = CB.segment_bounds(wl.num_samples, wl.num_segments)
         r0, _, _, threads = cpu_reference_rate(model, cfg, clip, Z, bounds, frames, tokens, 8, batch=8)
         n_rows = int(max(16, min(K, (r0 * 20.0) // 8 * 8)))
         r, done, dt, threads = cpu_reference_rate(model, cfg, clip, Z, bounds, frames, tokens, n_rows, batch=32)
-        # the same rows through the B200 path, checked against the CPU result (oracle as checker only)
         cpu = {"value": r, "unit": UNIT, "cores": threads, "kind": "reference",
                "sample": f"{done} of {K} coalitions in {dt:.1f} s; transformers fp32 forward + log_softmax + gather, batch 32"}
+        # the same rows as evaluated by the B200 path in the timed steps (first `done` rows of `out`), checked against
+        # the CPU result -- the reference as checker only
+        ref_rows = cpu_reference_rate.last_outputs
+        gpu_rows = out[:done].cpu().numpy()
+        tol = 0.025 * float(np.abs(lg).max())
+        parity = {"rows": int(done), "outputs_per_row": int(D), "max_abs_err": float(np.abs(gpu_rows - ref_rows).max()),
+                  "tolerance": tol, "what": "per-character log-probabilities, B200 path vs transformers fp32 on the same coalitions",
+                  "ok": bool(np.abs(gpu_rows - ref_rows).max() < tol)}
+        if not parity["ok"]:
+            raise SystemExit(f"bench.py: parity check failed: {parity}")
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
+        # one clip's coalitions sharded over the N ranks + the all-gather (north_star's split), timed like `value`;
+        # efficiency = what N ranks achieve on one clip / (N x what one rank achieves on the same clip, measured by the
+        # weak leg of this very run, where every rank evaluates the full set)
+        "strong": {"forwards_per_s": K * args.steps / (strong_ms / 1e3), "ms_per_clip_forward_part": strong_ms / args.steps,
+                   "rows_per_rank": int(per), "efficiency_vs_n1": (ms / world) / strong_ms},
+        "parity": parity,
         "config": {"workload": f"{wl.name}: {wl.description}", "coalitions_per_step_per_gpu": K, "outputs_per_coalition": D,
                    "batch_tile": tile, "gflop_per_forward": flops_fwd / 1e9,
                    "l2": "256 MB flush write between steps; per-step activation stream >> 126 MB L2",
@@ -331,14 +394,17 @@ def run_b200(args):
                    f"+ all-gather + device WLS (status {wls_status})"},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(cb.h2d_bytes), "d2h_bytes_per_step": int(cb.d2h_bytes)},
-        "gpu_launches": int(args.steps * (n_batches * launches_per_batch + 1)),
+        "gpu_launches": int(launches),
+        "gpu_launches_note": f"counted by the library at launch time over the {args.steps} timed steps ({n_batches} tiles x "
+                             f"{launches_per_batch} kernels per step; each tile's plan is replayed as one CUDA graph)",
         "roofline": {"bound": "tensor", "kernel": "gemm_tc2_kernel<256> and the other contraction launches (gemm_tc_kernel, posconv_kernel)", "achieved": achieved,
                      "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"],
-                     "traffic": ncu_traffic(wl.name), "traffic_detail": ncu_traffic_detail(wl.name),
+                     "traffic": traffic, "traffic_detail": traffic_detail,
                      "peak_source": peaks["source"] + " bf16_tflops_sustained",
                      "launches": int(gemm_n), "share_of_step": gemm_ms / total_prof_ms,
                      "profiled_ms_per_step": prof_ms / args.steps,
-                     "whole_step_tflops": value * flops_fwd / 1e12 / world},
+                     "whole_step_tflops": value * flops_fwd / 1e12 / world,
+                     "whole_step_frac": value * flops_fwd / 1e12 / world / peaks["tf_sustained"]},
         "cpu_baseline": cpu,
         "kernel_breakdown": breakdown,
     }
@@ -357,6 +423,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--coalitions", type=int, default=0, help="profiling aid: evaluate only the first N coalitions per step")
+    ap.add_argument("--preln-bf16", action="store_true", help="A/B: bf16 pre-LayerNorm tensors (W2S_FLAG_BF16_PRELN)")
+    ap.add_argument("--pdl", action="store_true", help="A/B: programmatic dependent launch, eager launches (W2S_FLAG_PDL)")
+    ap.add_argument("--no-graph", action="store_true", help="A/B: launch every kernel of a tile instead of replaying a graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -14,7 +14,7 @@ namespace w2s {
 // =================================================================================================
 // validation kernel
 // =================================================================================================
-constexpr int SIMT_MAXC = 16;  // key chunks of 32 -> T <= 512
+constexpr int SIMT_MAXC = 32;  // key chunks of 32 -> T <= 1024
 
 __global__ void __launch_bounds__(128) attention_simt_kernel(const AttnParams p) {
   __shared__ float qs[4][2][128];  // per warp: q + u, q + v  (hd <= 128)
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(128) attention_simt_kernel(const AttnParams p)
 }
 
 std::string launch_attention_simt(const AttnParams& p, cudaStream_t s) {
-  if (p.T > 32 * SIMT_MAXC) return "attention (validation kernel): T' > 512 not supported";
+  if (p.T > 32 * SIMT_MAXC) return "attention (validation kernel): T' > 1024 not supported";
   if (p.hd > 128 || (p.hd & 1)) return "attention (validation kernel): head_dim must be even and <= 128";
   const long long total = (long long)p.B * p.heads * p.T;
   if (total == 0) return "";
@@ -122,8 +122,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(int M, int N) {
 //   BD  [128 x 256] = (Q+v) PP_window^T, window row w <-> r = r_lo + w  columns 128..383
 // and the "shift trick" of the reference is an index shift per query row: bd[i, j] = BD[i, 127 - i_local + (j - j0)].
 // Each warp reads its 64 raw BD columns per 32-key chunk, stages them in its private shared-memory strip and reads
-// them back with the lane-dependent offset.  Each half keeps its own softmax maximum and its own O accumulator
-// (columns 384..447 / 448..511); the halves are merged in the epilogue, so nothing in TMEM is ever rescaled.
+// them back with the lane-dependent offset.  Each key block keeps its own softmax maximum and its own O accumulator
+// (columns 384..447 / 448..511, alternating); a finished block is folded into a per-thread running (max, sum, 32 output
+// columns) while the next block's scores are computed, so nothing in TMEM is ever rescaled and the number of key
+// blocks -- the clip length -- is unbounded.
 // =================================================================================================
 struct AttnRelDev {
   __nv_bfloat16* ctx;
@@ -145,7 +147,7 @@ attention_rel_kernel(const __grid_constant__ CUtensorMap mapQU, const __grid_con
                      const __grid_constant__ CUtensorMap mapP, const AttnRelDev p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ float s_red[2][128];
-  __shared__ float s_sum[2][2][128];
+  __shared__ float s_sum[1][2][128];
   __shared__ uint64_t s_bar[4];
   __shared__ uint32_t s_tmem;
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -186,8 +188,27 @@ attention_rel_kernel(const __grid_constant__ CUtensorMap mapQU, const __grid_con
     tma_load_4d(base + REL_QV, &mapQV, bar_q, 0, qt * 128, h, b);
   }
 
-  float m_h[2] = {-INFINITY, -INFINITY};
-  float l_h[2] = {0.f, 0.f};
+  // running state of this thread's query row: its 32 output columns relative to m_run (maximum over the FOLDED blocks),
+  // and its share of the row sum (its 64 keys per block) relative to m_l (maximum over the blocks whose softmax is done:
+  // one block ahead of m_run, because a block's output is folded only after its P V has completed)
+  float m_run = -3.0e38f, m_l = -3.0e38f, l_run = 0.f;
+  float o_run[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) o_run[j] = 0.f;
+  float m_prev = 0.f;   // maximum of the block whose P V is in flight (folded one block later)
+
+  // fold block hk (maximum m_blk, accumulator slot hk & 1) into the running state; its P V has completed
+  auto fold = [&](int hk, float m_blk) {
+    const float m_new = fmaxf(m_run, m_blk);
+    const float alpha = ex2_approx((m_run - m_new) * p.scale_log2e);
+    const float a = ex2_approx((m_blk - m_new) * p.scale_log2e);
+    float v[32];
+    tmem_ld_32x32(trow + 384 + 64 * (hk & 1) + hf * 32, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o_run[j] = fmaf(alpha, o_run[j], a * v[j]);
+    m_run = m_new;
+  };
+
   for (int hk = 0; hk < p.nh; ++hk) {
     const int j0 = hk * 128;
     if (warp == 0 && elect_one()) {
@@ -207,6 +228,12 @@ attention_rel_kernel(const __grid_constant__ CUtensorMap mapQU, const __grid_con
 #pragma unroll
       for (int k = 0; k < 4; ++k) umma_bf16(tmem + 128, dqv + 2u * k, dp + 2u * k, umma_idesc_bf16(128, 256), k != 0);
       umma_commit(bar_mma);
+    }
+    // while the score MMAs of this block run: fold the previous block (its P V is complete once bar_pv has flipped)
+    if (hk > 0) {
+      mbar_wait(bar_pv, (hk - 1) & 1);
+      tc_fence_after();
+      fold(hk - 1, m_prev);
     }
     mbar_wait(bar_mma, hk & 1);
     tc_fence_after();
@@ -240,7 +267,6 @@ attention_rel_kernel(const __grid_constant__ CUtensorMap mapQU, const __grid_con
     s_red[hf][row] = mx;
     __syncthreads();
     mx = fmaxf(s_red[0][row], s_red[1][row]);
-    m_h[hk] = mx;
     const float2 sc2 = make_float2(p.scale_log2e, p.scale_log2e);
     const float2 nm2 = make_float2(-mx * p.scale_log2e, -mx * p.scale_log2e);
     float2 acc2 = make_float2(0.f, 0.f);
@@ -257,10 +283,16 @@ attention_rel_kernel(const __grid_constant__ CUtensorMap mapQU, const __grid_con
       sts128(sp_row + (((uint32_t)c8 ^ ((uint32_t)row & 7u)) << 4), pack_bf16x2(e[0].x, e[0].y),
              pack_bf16x2(e[1].x, e[1].y), pack_bf16x2(e[2].x, e[2].y), pack_bf16x2(e[3].x, e[3].y));
     }
-    l_h[hk] = acc2.x + acc2.y;
+    {
+      const float m_new = fmaxf(m_l, mx);
+      l_run = fmaf(l_run, ex2_approx((m_l - m_new) * p.scale_log2e),
+                   (acc2.x + acc2.y) * ex2_approx((mx - m_new) * p.scale_log2e));
+      m_l = m_new;
+    }
+    m_prev = mx;
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();   // also orders the s_red reads above before the next half overwrites it
+    __syncthreads();   // also orders the s_red reads above before the next block overwrites it
     if (warp == 0 && elect_one()) {
       tc_fence_after();
       constexpr uint32_t idesc = umma_idesc_bf16_bmn(128, 64);
@@ -268,47 +300,30 @@ attention_rel_kernel(const __grid_constant__ CUtensorMap mapQU, const __grid_con
         const uint64_t dpp = umma_desc_sw128(base + REL_P + kb * 16384);
         const uint64_t dv = umma_desc_sw128_mn(base + REL_V + kb * 8192);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem + 384 + 64 * hk, dpp + 2u * k, dv + 128u * k, idesc, (kb | k) != 0);
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem + 384 + 64 * (hk & 1), dpp + 2u * k, dv + 128u * k, idesc, (kb | k) != 0);
       }
       umma_commit(bar_pv);
     }
   }
-  // ---- merge the halves: out = (a0 O0 + a1 O1) / (a0 l0 + a1 l1), a_h = exp((m_h - m) scale) ------------------------------
-  s_sum[0][hf][row] = l_h[0];
-  s_sum[1][hf][row] = l_h[1];
+  // ---- last block, then out = o_run / (row sum over both key halves of every block) ---------------------------------
   mbar_wait(bar_pv, (p.nh - 1) & 1);
   tc_fence_after();
+  fold(p.nh - 1, m_prev);
+  s_sum[0][hf][row] = l_run;
   __syncthreads();
-  const float l0 = s_sum[0][0][row] + s_sum[0][1][row];
-  const float l1 = s_sum[1][0][row] + s_sum[1][1][row];
-  const float m = fmaxf(m_h[0], m_h[1]);
-  const float a0 = ex2_approx((m_h[0] - m) * p.scale_log2e);
-  const float a1 = (p.nh > 1) ? ex2_approx((m_h[1] - m) * p.scale_log2e) : 0.f;
-  const float inv = 1.0f / (a0 * l0 + a1 * l1);
+  const float inv = 1.0f / (s_sum[0][0][row] + s_sum[0][1][row]);
   const int i = qt * 128 + row;
   __nv_bfloat16* orow = p.ctx + ((long long)b * p.T + i) * p.H + h * 64 + hf * 32;
-  {
-    float o0[32], o1[32];
-    tmem_ld_32x32(trow + 384 + hf * 32, o0);
-    if (p.nh > 1) {
-      tmem_ld_32x32(trow + 448 + hf * 32, o1);
-    } else {
+  if (i < p.T) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) o1[j] = 0.f;
-    }
-    if (i < p.T) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        float y[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) y[t] = (a0 * o0[j + t] + a1 * o1[j + t]) * inv;
-        uint4 u;
-        u.x = pack_bf16x2(y[0], y[1]);
-        u.y = pack_bf16x2(y[2], y[3]);
-        u.z = pack_bf16x2(y[4], y[5]);
-        u.w = pack_bf16x2(y[6], y[7]);
-        *reinterpret_cast<uint4*>(orow + j) = u;
-      }
+    for (int j = 0; j < 32; j += 8) {
+      uint4 u;
+      u.x = pack_bf16x2(o_run[j] * inv, o_run[j + 1] * inv);
+      u.y = pack_bf16x2(o_run[j + 2] * inv, o_run[j + 3] * inv);
+      u.z = pack_bf16x2(o_run[j + 4] * inv, o_run[j + 5] * inv);
+      u.w = pack_bf16x2(o_run[j + 6] * inv, o_run[j + 7] * inv);
+      *reinterpret_cast<uint4*>(orow + j) = u;
     }
   }
   tc_fence_before();
@@ -320,7 +335,7 @@ attention_rel_kernel(const __grid_constant__ CUtensorMap mapQU, const __grid_con
 }
 
 bool attention_rel_supported(const AttnParams& p) {
-  return p.pos_proj != nullptr && p.hd == 64 && p.T <= 256 && (p.H % 8 == 0);
+  return p.pos_proj != nullptr && p.hd == 64 && (p.H % 8 == 0);
 }
 std::string attention_rel_init() {
   cudaError_t e = cudaFuncSetAttribute(attention_rel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)REL_SMEM);

@@ -18,9 +18,10 @@ from shap_transformer_asr_b200.config import MODELS
 
 pytestmark = pytest.mark.gpu
 
-LOGIT_TOL = 0.04        # 12-layer models and the tiny variants
-LOGIT_TOL_DEEP = 0.06   # 24-layer models (bf16 rounding accumulates with depth; measured 0.020 / 0.041 on C3 / C4)
-PHI_TOL = 0.10
+# about twice the measured errors (so a regression such as one extra bf16 rounding per sub-layer fails):
+LOGIT_TOL = 0.025       # 12-layer models and the tiny variants (measured 1.1-1.5e-2)
+LOGIT_TOL_DEEP = 0.05   # 24-layer models (bf16 rounding accumulates with depth; measured 0.020 / 0.041 on C3 / C4)
+PHI_TOL = 0.02          # attributions (measured 8.5e-3 at C1)
 
 IMPLEMENTED = ["tiny_group", "tiny_layer_stable", "tiny_conformer_rel", "tiny_conformer_rotary"]
 
@@ -71,8 +72,12 @@ def test_c1_base_logits_match_golden(P, base_engine, golden_dir):
     top2 = np.sort(g["logits"][0], -1)
     near_tie = (top2[:, -1] - top2[:, -2]) < 2 * np.abs(out[0] - g["logits"][0]).max()
     assert np.all(same | near_tie)
+    # per-character targets selected from the GPU logits are the ones the reference logits select
     f, t = P.char_targets(out[0])
+    fr, tr = P.char_targets(g["logits"][0])
     assert len(f) > 0
+    if np.all(same):
+        assert np.array_equal(f, fr) and np.array_equal(t, tr)
 
 
 def test_callback_shapes_match_reference_interfaces(P, base_engine):
@@ -233,6 +238,215 @@ def test_sweep_writes_reference_compatible_files(P, tmp_path):
         assert np.isfinite(shap).all() and np.abs(shap).max() > 0
         eta = P.eta_raw(audio - noise, noise, shap.squeeze(), 16000)       # calculate_metric.py main: clean = audio - noise
         assert 0.0 <= eta <= 1.0
-        assert 0.0 <= P.wer(text, o["hypothesis"]) or True
+        assert P.wer(text, o["hypothesis"]) >= 0.0
+        if item["type"] == "clean":
+            assert P.wer(text, o["hypothesis"]) == 0.0
     assert out[0]["text"] == out[0]["hypothesis"]       # the clean item is its own reference transcript
+    eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the MEASURED configuration: C2 with the library's own batch tile (max_batch = 0 -> 152 coalitions: every encoder
+# contraction takes the CTA-pair kernel with TMA-store epilogues, the plan is replayed as a CUDA graph)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def c2_bench_engine(P):
+    cfg = MODELS["wav2vec2-base"]
+    model = build_model(cfg)
+    eng = P.Engine(model, cfg, max_batch=0)
+    yield eng, model, cfg
+    eng.close()
+
+
+def test_c2_bench_configuration_matches_transformers(P, c2_bench_engine):
+    eng, model, cfg = c2_bench_engine
+    clip = P.synthetic_clip(80000)
+    M, K = 100, 2048
+    eng.set_clip(clip, num_segments=M)
+    Z, kw, _ = P.sample_coalitions(M, K, seed=0)
+    eng.set_targets("logits")
+    bits = eng.bits_to_device(Z)
+    lg = eng.eval_bits(bits).view(K, 249, 32)                      # all 2048 rows, 13 full tiles of 152 + 72
+    assert eng.kernel_count()[1] == 152
+    idx = np.unique(np.linspace(0, K - 1, 32).astype(int))        # 32 rows spread over the tiles, incl. first / last
+    bounds = CB.segment_bounds(80000, M)
+    X = torch.from_numpy(CB.materialize(clip, Z[idx], bounds))
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        ref = torch.cat([model(X[i:i + 8]).logits for i in range(0, len(idx), 8)]).numpy()   # transformers fp32
+    out = lg[torch.from_numpy(idx).cuda()].cpu().numpy()
+    err = rel_err(out, ref)
+    print(f"C2 @ tile 152: logits rel err over {len(idx)} rows {err:.3e}")
+    assert err < LOGIT_TOL
+    frames, tokens = P.char_targets(ref[0])
+    eng.set_targets("logprob", frames, tokens)
+    lp = eng.eval_bits(bits)[torch.from_numpy(idx).cuda()].cpu().numpy()
+    ref_lp = torch.log_softmax(torch.from_numpy(ref), -1)[:, torch.from_numpy(frames).long(), torch.from_numpy(tokens).long()].numpy()
+    e_lp = np.abs(lp - ref_lp).max()
+    print(f"C2 @ tile 152: log-prob max abs err {e_lp:.3e} (max |logit| {np.abs(ref).max():.2f})")
+    assert e_lp < LOGIT_TOL * np.abs(ref).max()
+
+
+def test_c2_attributions_match_oracle(P, c2_bench_engine):
+    """C2 attributions (M = 100 segments) from 512 coalitions at the bench's batch tile against the oracle solve on the
+    oracle's (transformers fp32) outputs for the same coalition rows."""
+    eng, model, cfg = c2_bench_engine
+    sd, d = W.state_dict_of(model), cfg.to_dict()
+    clip = P.synthetic_clip(80000)
+    M, K = 100, 512
+    res = P.KernelShapExplainer(eng, nsamples=K, seed=0).explain(clip, num_segments=M)
+    frames, tokens = res["frames"], res["tokens"]
+    bounds = CB.segment_bounds(80000, M)
+    torch.set_num_threads(os.cpu_count() or 1)
+    f = lambda Zm: CB.evaluate_coalitions(sd, d, clip, Zm, bounds, mode="logprob", frames=frames, tokens=tokens, batch=16)
+    ref = KernelExplainerRef(f, M)
+    np.random.seed(0)
+    Zr, wr = ref.sample(K)
+    assert np.array_equal(res["Z"], Zr.astype(np.uint8)) and np.array_equal(res["weights"], wr)
+    y_ref = f(Zr)
+    fx, fnull = f(np.ones((1, M)))[0], f(np.zeros((1, M)))[0]
+    phi_ref = ref.solve(y_ref, fx, fnull)
+    phi = res["phi"].cpu().numpy()
+    e_phi = np.abs(phi - phi_ref).max() / np.abs(phi_ref).max()
+    corr = np.corrcoef(np.abs(phi).sum(1), np.abs(phi_ref).sum(1))[0, 1]
+    print(f"C2 KernelSHAP (K=512): phi max rel err {e_phi:.3e}; |phi| corr {corr:.5f}; D={len(frames)}")
+    assert int(res["status"].item()) == 0
+    assert e_phi < PHI_TOL and corr > 0.99
+
+
+@pytest.mark.parametrize("workload,n", [("C3", 20), ("C4", 40)])
+def test_large_models_at_pair_kernel_tiles(P, workload, n):
+    """C3 (stable-LN? no: post-LN large) and C4 (conformer: in-place fp32 residual stream) with a batch tile whose
+    contractions take the CTA-pair kernel (>= 296 output tiles), i.e. the TMA-store and TMA reduce-add epilogues the
+    bench numbers of these workloads come from; 5 of the n rows are compared with the transformers fp32 forward."""
+    from shap_transformer_asr_b200.config import WORKLOADS
+    wl = WORKLOADS[workload]
+    cfg = MODELS[wl.model]
+    model = build_model(cfg)
+    clip = P.synthetic_clip(wl.num_samples)
+    M = wl.num_segments
+    Z, kw, _ = P.sample_coalitions(M, wl.num_coalitions, seed=0)
+    rows = np.concatenate([np.ones((1, M), np.uint8), Z[:n - 1]])
+    pick = np.array([0, 1, n // 2, n - 2, n - 1])
+    bounds = CB.segment_bounds(wl.num_samples, M)
+    X = torch.from_numpy(CB.materialize(clip, rows[pick], bounds))
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        ref = torch.cat([model(X[i:i + 1]).logits for i in range(len(pick))]).numpy()
+    eng = P.Engine(model, cfg, max_batch=n)
+    eng.set_clip(clip, num_segments=M)
+    eng.set_targets("logits")
+    out = eng.eval_bits(eng.bits_to_device(rows)).view(n, *ref.shape[1:])[torch.from_numpy(pick).cuda()].cpu().numpy()
+    err = rel_err(out, ref)
+    print(f"{workload} @ tile {n}: logits rel err {err:.3e}")
+    assert err < LOGIT_TOL_DEEP
+    eng.close()
+
+
+def test_stable_layer_norm_model_at_pair_kernel_tile(P):
+    """wav2vec2-large-lv60 style (layer-norm front end, stable-LN encoder, in-place fp32 residual stream) at a tile that
+    reaches the pair kernel: 4 layers are enough to exercise every epilogue."""
+    import dataclasses
+    cfg = dataclasses.replace(MODELS["wav2vec2-large"], feat_extract_norm="layer", conv_bias=True,
+                              do_stable_layer_norm=True, num_hidden_layers=4)
+    model = build_model(cfg)
+    x = np.random.default_rng(2).standard_normal((80, 40000)).astype(np.float32)     # T' = 124: 9920 rows
+    with torch.no_grad():
+        ref = model(torch.from_numpy(x[[0, 41, 79]])).logits.numpy()
+    eng = P.Engine(model, cfg, max_batch=80)
+    eng.set_targets("logits")
+    out = eng.eval_waveforms(torch.from_numpy(x).cuda()).view(80, *ref.shape[1:])[[0, 41, 79]].cpu().numpy()
+    err = rel_err(out, ref)
+    print(f"stable-LN large (4 layers) @ tile 80: logits rel err {err:.3e}")
+    assert err < LOGIT_TOL
+    eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clips beyond 512 frames: the lengths of the reference's own recorded runs (L = 183600 -> T' = 573, evaluation.ipynb:
+# 460,463; L = 199760 -> T' = 624, shap_value_test.ipynb:301,342) -- streaming attention, 5 key blocks
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,L", [("tiny_group", 183600), ("tiny_group", 199760), ("tiny_layer_stable", 183600),
+                                    ("tiny_conformer_rel", 183600), ("tiny_conformer_rel", 100000),
+                                    ("tiny_conformer_rotary", 199760), ("tiny_group", 330000)])
+def test_clips_beyond_512_frames(P, name, L):
+    cfg = VARIANTS[name]
+    model = build_model(cfg)
+    x = np.random.default_rng(L).standard_normal((3, L)).astype(np.float32)
+    with torch.no_grad():
+        ref = W.ctc_logits(W.state_dict_of(model), cfg.to_dict(), torch.from_numpy(x)).numpy()
+    eng = P.Engine(model, cfg, max_batch=2)
+    eng.set_targets("logits")
+    out = eng.eval_waveforms(torch.from_numpy(x).cuda()).view(ref.shape).cpu().numpy()
+    err = rel_err(out, ref)
+    print(f"{name} L={L} T'={ref.shape[1]} logits rel err {err:.3e}")
+    assert err < LOGIT_TOL
+    eng.close()
+
+
+def test_base_model_on_the_reference_clip_length(P, base_engine):
+    """wav2vec2-base on an 11.5 s clip (L = 183600, T' = 573: the clip of the reference's recorded run)."""
+    eng, model, cfg = base_engine
+    x = np.stack([P.synthetic_clip(183600), P.synthetic_clip(183600, seed=5)])
+    with torch.no_grad():
+        ref = model(torch.from_numpy(x)).logits.numpy()
+    assert ref.shape[1] == 573
+    eng.set_targets("logits")
+    out = eng.eval_waveforms(torch.from_numpy(x).cuda()).view(ref.shape).cpu().numpy()
+    err = rel_err(out, ref)
+    print(f"base L=183600 T'=573 logits rel err {err:.3e}")
+    assert err < LOGIT_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# an independent pin of the KernelSHAP half through the GPU: exact Shapley values by brute force
+# ---------------------------------------------------------------------------------------------------------------------
+def test_full_enumeration_on_the_gpu_equals_brute_force_shapley(P):
+    """M = 10 segments, nsamples >= 2^M - 2: the sampler enumerates every coalition, so KernelSHAP is exact and must
+    equal the Shapley values computed by brute force from the ORACLE callback (transformers-pinned forward) -- a check
+    that depends neither on the sampler restatement nor on the oracle's solve."""
+    from oracle.kernelshap_ref import brute_force_shapley
+    cfg = VARIANTS["tiny_group"]
+    model = build_model(cfg)
+    sd, d = W.state_dict_of(model), cfg.to_dict()
+    clip = P.synthetic_clip(12000)
+    M = 10
+    eng = P.Engine(model, cfg, max_batch=64)
+    res = P.KernelShapExplainer(eng, nsamples=2 ** M, seed=0).explain(clip, num_segments=M)
+    assert res["Z"].shape[0] == 2 ** M - 2 and int(res["status"].item()) == 0
+    bounds = CB.segment_bounds(len(clip), M)
+    f = lambda Zm: CB.evaluate_coalitions(sd, d, clip, np.atleast_2d(Zm), bounds, mode="logprob", frames=res["frames"],
+                                          tokens=res["tokens"], batch=64)
+    shap_exact = brute_force_shapley(f, M)
+    phi = res["phi"].cpu().numpy()
+    err = np.abs(phi - shap_exact).max() / np.abs(shap_exact).max()
+    print(f"full enumeration M={M}: GPU KernelSHAP vs brute-force Shapley max rel err {err:.3e}")
+    assert err < 2e-2
+    eng.close()
+
+
+def test_lowpass_clip_under_differencing_filters(P):
+    """GroupNorm statistics of conv0 under heavy cancellation (advisor finding): a low-pass clip through second-difference
+    style filters.  The reference here is the transformers forward in float64."""
+    cfg = VARIANTS["tiny_group"]
+    model = build_model(cfg)
+    rng = np.random.default_rng(4)
+    with torch.no_grad():
+        w = model.wav2vec2.feature_extractor.conv_layers[0].conv.weight          # [64, 1, 10]
+        base = torch.tensor([0., 0., 1., -2., 1., 0., 0., 0., 0., 0.])
+        for c in range(w.shape[0]):
+            w[c, 0] = torch.roll(base, int(rng.integers(0, 6))) * float(rng.uniform(0.5, 2.0)) + 1e-3 * torch.randn(10)
+    t = np.arange(40000) / 16000.0
+    clip = np.sin(2 * np.pi * 120 * t) + 0.5 * np.sin(2 * np.pi * 300 * t + 1.0) + 2e-3 * rng.standard_normal(40000)
+    clip = P.normalize_clip(clip)
+    x = np.stack([clip, np.where(np.arange(40000) // 4000 % 2 == 0, clip, 0.0).astype(np.float32)])
+    with torch.no_grad():
+        ref = model.double()(torch.from_numpy(x).double()).logits.float().numpy()
+    model.float()
+    eng = P.Engine(model, cfg, max_batch=2)
+    eng.set_targets("logits")
+    out = eng.eval_waveforms(torch.from_numpy(x).cuda()).view(ref.shape).cpu().numpy()
+    err = rel_err(out, ref)
+    print(f"low-pass clip, differencing conv0 filters: logits rel err vs float64 {err:.3e}")
+    assert err < LOGIT_TOL
     eng.close()
