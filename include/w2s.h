@@ -42,7 +42,9 @@ enum {
   W2S_FLAG_VALIDATE_ATTN = 2,  /* run attention on the CUDA-core validation kernel                            */
   W2S_FLAG_BF16_PRELN    = 4,  /* post-LN models: bf16 (instead of fp32) pre-LayerNorm tensors -- A/B measurement */
   W2S_FLAG_PDL           = 8,  /* programmatic dependent launch between the kernels of a tile -- A/B measurement  */
-  W2S_FLAG_NO_GRAPH      = 16  /* launch the kernels of a tile one by one instead of replaying a CUDA graph        */
+  W2S_FLAG_NO_GRAPH      = 16, /* launch the kernels of a tile one by one instead of replaying a CUDA graph        */
+  W2S_FLAG_UNFUSED_LN    = 32  /* post-LN models: standalone LayerNorm kernels instead of LayerNorm carried through
+                                  the contraction epilogues -- A/B measurement                                     */
 };
 
 /* Mirrors transformers.Wav2Vec2Config / Wav2Vec2ConformerConfig (the objects the reference

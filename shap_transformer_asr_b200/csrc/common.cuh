@@ -207,6 +207,13 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   return t;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef W2S_MBAR_POLLCOUNT   // A/B build of the round-1 form (bounded by a poll count)
+  uint32_t n = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++n > (1u << 24)) __trap();
+  }
+  return;
+#endif
   if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   uint64_t t0 = 0;

@@ -18,7 +18,8 @@ struct Tc2Cfg {
   static constexpr int A_BYTES = 128 * 64 * 2;
   static constexpr int B_BYTES = (BN / 2) * 64 * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_BYTES = 8 * 4096 + 8 * 512;   // per-warp 32 x 128 B output staging + bias strip
+  static constexpr int EPI_BYTES = 8 * 4096 + 8 * 2048;  // per-warp 32 x 128 B output staging + four 512 B column strips
+                                                         // (bias, and the carried-LayerNorm vectors c1 / gamma / beta)
   // the operand ring takes what the epilogue strips leave: 5 x 32 KB (BN = 256) or 7 x 24 KB (BN = 128)
   static constexpr int STAGES = (227 * 1024 - 1024 - 256 - EPI_BYTES) / STAGE_BYTES > 8
                                     ? 8 : (227 * 1024 - 1024 - 256 - EPI_BYTES) / STAGE_BYTES;
@@ -143,7 +144,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const bool lead = elect_one();   // the lane that owns this warp's TMA-store bulk groups
     const uint32_t stg = epi_smem + warp * 4096;              // this warp's 32 rows x 128 B staging strip
     const uint32_t stg_row = stg + lane * 128;
-    float* sbias = reinterpret_cast<float*>(tiles_ptr + C::STAGES * C::STAGE_BYTES + 8 * 4096 + warp * 512);
+    float* sbias = reinterpret_cast<float*>(tiles_ptr + C::STAGES * C::STAGE_BYTES + 8 * 4096 + warp * 2048);
+    float *sc1 = sbias + 128, *sg = sbias + 256, *sb = sbias + 384;
     const bool f32 = p.epi.out_fp32 != 0;
     // in-place fp32 accumulation (out == residual): let the TMA engine add in L2 instead of loading the residual
     const bool reduce_add = tma_out && f32 && p.epi.res_fp32 && p.epi.residual == p.epi.out;
@@ -165,11 +167,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         // shared-memory strip BEFORE the accumulator wait, so the global latency hides behind the MMAs.
         const int bw = f32 ? 32 : 64;
         const int nblk = BN / (2 * bw);
-        if (p.epi.bias) {
+        if (p.epi.bias || p.epi.ln_in || p.epi.res_ln) {
           for (int i = lane; i < nblk * bw; i += 32) {
             const int col = (2 * (i / bw) + hsel) * bw + (i % bw);
-            sbias[i] = __ldg(p.epi.bias + (long long)g * p.N + n0 + col);
+            if (p.epi.bias) sbias[i] = __ldg(p.epi.bias + (long long)g * p.N + n0 + col);
+            if (p.epi.ln_in) sc1[i] = __ldg(p.epi.ln_c1 + n0 + col);
+            if (p.epi.res_ln) {
+              sg[i] = __ldg(p.epi.res_g + n0 + col);
+              sb[i] = __ldg(p.epi.res_b + n0 + col);
+            }
           }
+        }
+        // the row's LayerNorm statistics (carried-LayerNorm forms), also fetched ahead of the accumulator
+        float2 st_in = make_float2(0.f, 1.f), st_res = make_float2(0.f, 1.f);
+        if (row_ok) {
+          if (p.epi.ln_in) st_in = __ldg(p.epi.ln_in + m);
+          if (p.epi.res_ln) st_res = __ldg(p.epi.res_ln + m);
         }
         __syncwarp();
         mbar_wait(tfull_bar(acc), acc_phase);
@@ -186,7 +199,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           const int c = sub_col(sidx);
           const int sub = f32 ? 0 : (sidx & 1);
           tmem_ld_wait();
-          epi_math32(p.epi, p.epi.bias ? sbias + sidx * 32 : nullptr, p.N, g, b, m, n0 + c, row_ok, v, reduce_add);
+          epi_math32(p.epi, p.epi.bias ? sbias + sidx * 32 : nullptr, p.N, g, b, m, n0 + c, row_ok, v, reduce_add,
+                     p.epi.ln_in ? sc1 + sidx * 32 : nullptr, st_in, p.epi.res_ln ? sg + sidx * 32 : nullptr,
+                     sb + sidx * 32, st_res);
+          if (p.epi.stats_out && row_ok) {   // partial LayerNorm statistics of the stored row (see gemm.cuh)
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              s1 += v[j];
+              s2 = fmaf(v[j], v[j], s2);
+            }
+            p.epi.stats_out[(long long)m * (p.N >> 5) + ((n0 + c) >> 5)] = make_float2(s1, s2);
+          }
           if (f32) {
             if (lead) tma_store_wait_read();   // the previous store of this warp has drained the strip
             __syncwarp();

@@ -11,6 +11,11 @@ template <int CH>
 __device__ __forceinline__ void epi_store(const EpiParams& e, int N, int g, int b, int m, int ncol0, float* v) {
   // N is a multiple of the column chunk in both kernels (N % 4 == 0; tcgen05 tiles divide N exactly)
   if (ncol0 >= N) return;
+  if (e.ln_in) {   // consumer form of a carried LayerNorm: rstd (acc - mean c1[n]); c0 follows as the bias
+    const float2 st = __ldg(e.ln_in + m);
+#pragma unroll
+    for (int j = 0; j < CH; ++j) v[j] = st.y * fmaf(-st.x, __ldg(e.ln_c1 + ncol0 + j), v[j]);
+  }
   if (e.bias) {
     const float4* bp = reinterpret_cast<const float4*>(e.bias + (long long)g * N + ncol0);
 #pragma unroll
@@ -51,7 +56,12 @@ __device__ __forceinline__ void epi_store(const EpiParams& e, int N, int g, int 
         if (e.residual)
           r = e.res_fp32 ? reinterpret_cast<const float*>(e.residual)[off + j]
                          : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(e.residual)[off + j]);
+        if (e.res_ln) {
+          const float2 st = __ldg(e.res_ln + m);
+          r = fmaf(fmaf(r, st.y, -st.x * st.y), __ldg(e.res_g + nout0 + j), __ldg(e.res_b + nout0 + j));
+        }
         const float o = fmaf(v[j], e.alpha, r);
+        v[j] = o;
         if (e.out_fp32) reinterpret_cast<float*>(e.out)[off + j] = o;
         else reinterpret_cast<__nv_bfloat16*>(e.out)[off + j] = __float2bfloat16_rn(o);
       }
@@ -72,14 +82,29 @@ __device__ __forceinline__ void epi_store(const EpiParams& e, int N, int g, int 
         }
       } else {
         const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(e.residual) + off;
+        float ra = 1.f, rs = 0.f;   // residual LayerNorm on the fly: (r - mean) rstd = r ra + rs
+        if (e.res_ln) {
+          const float2 st = __ldg(e.res_ln + m);
+          ra = st.y;
+          rs = -st.x * st.y;
+        }
 #pragma unroll
         for (int j = 0; j < CH; j += 4) {
           if (j < nvals && nout0 + j < Nout) {
             uint2 r = *reinterpret_cast<const uint2*>(rp + j);
-            v[j] = fmaf(v[j], e.alpha, bf16_lo(r.x));
-            v[j + 1] = fmaf(v[j + 1], e.alpha, bf16_hi(r.x));
-            v[j + 2] = fmaf(v[j + 2], e.alpha, bf16_lo(r.y));
-            v[j + 3] = fmaf(v[j + 3], e.alpha, bf16_hi(r.y));
+            float r4[4] = {bf16_lo(r.x), bf16_hi(r.x), bf16_lo(r.y), bf16_hi(r.y)};
+            if (e.res_ln) {
+              const float4 gg = __ldg(reinterpret_cast<const float4*>(e.res_g + nout0 + j));
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(e.res_b + nout0 + j));
+              r4[0] = fmaf(fmaf(r4[0], ra, rs), gg.x, bb.x);
+              r4[1] = fmaf(fmaf(r4[1], ra, rs), gg.y, bb.y);
+              r4[2] = fmaf(fmaf(r4[2], ra, rs), gg.z, bb.z);
+              r4[3] = fmaf(fmaf(r4[3], ra, rs), gg.w, bb.w);
+            }
+            v[j] = fmaf(v[j], e.alpha, r4[0]);
+            v[j + 1] = fmaf(v[j + 1], e.alpha, r4[1]);
+            v[j + 2] = fmaf(v[j + 2], e.alpha, r4[2]);
+            v[j + 3] = fmaf(v[j + 3], e.alpha, r4[3]);
           }
         }
       }
@@ -108,13 +133,53 @@ __device__ __forceinline__ void epi_store(const EpiParams& e, int N, int g, int 
       }
     }
   }
+  if (e.stats_out) {
+    // partial LayerNorm statistics of the stored row, one (sum, sum of squares) per 32-column block, summed in column
+    // order so that every contraction kernel produces the same bits
+    if constexpr (CH == 32) {
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        s1 += v[j];
+        s2 = fmaf(v[j], v[j], s2);
+      }
+      e.stats_out[(long long)m * (N >> 5) + (ncol0 >> 5)] = make_float2(s1, s2);
+    } else if constexpr (CH == 4) {
+      // validation kernel: 8 neighbouring threads hold the 32 columns of a block (tree order: not bit-identical to the
+      // sequential sum of the tensor-core kernels, same value to fp32 round-off)
+      float s1 = (v[0] + v[1]) + (v[2] + v[3]);
+      float s2 = fmaf(v[0], v[0], fmaf(v[1], v[1], fmaf(v[2], v[2], v[3] * v[3])));
+      const unsigned msk = __activemask();
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        s1 += __shfl_xor_sync(msk, s1, o);
+        s2 += __shfl_xor_sync(msk, s2, o);
+      }
+      if (((ncol0 >> 2) & 7) == 0) e.stats_out[(long long)m * (N >> 5) + (ncol0 >> 5)] = make_float2(s1, s2);
+    }
+  }
 }
 
 
 // Pair-kernel epilogue, first half: bias (from the warp's shared-memory strip) + activation + alpha / residual on
 // 32 consecutive columns of one row; the caller stores the result (TMA staging).
+// `sc1` / `sg` / `sb`: the warp's shared-memory strips of ln_c1 / res_g / res_b for these 32 columns; `st_in` / `st_res`:
+// the row's (mean, rstd) for the consumer form / the residual LayerNorm.
 __device__ __forceinline__ void epi_math32(const EpiParams& e, const float* sbias, int N, int g, int b, int m,
-                                           int ncol0, bool row_ok, float* v, bool skip_residual = false) {
+                                           int ncol0, bool row_ok, float* v, bool skip_residual = false,
+                                           const float* sc1 = nullptr, float2 st_in = make_float2(0.f, 1.f),
+                                           const float* sg = nullptr, const float* sb = nullptr,
+                                           float2 st_res = make_float2(0.f, 1.f)) {
+  if (sc1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = *reinterpret_cast<const float4*>(sc1 + 4 * j);
+      v[4 * j] = st_in.y * fmaf(-st_in.x, t.x, v[4 * j]);
+      v[4 * j + 1] = st_in.y * fmaf(-st_in.x, t.y, v[4 * j + 1]);
+      v[4 * j + 2] = st_in.y * fmaf(-st_in.x, t.z, v[4 * j + 2]);
+      v[4 * j + 3] = st_in.y * fmaf(-st_in.x, t.w, v[4 * j + 3]);
+    }
+  }
   if (sbias) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -151,17 +216,18 @@ __device__ __forceinline__ void epi_math32(const EpiParams& e, const float* sbia
         }
       } else {
         const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(e.residual) + off;
+        const float ra = st_res.y, rs = -st_res.x * st_res.y;
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           const uint4 r = *reinterpret_cast<const uint4*>(rp + j);
-          v[j] = fmaf(v[j], e.alpha, bf16_lo(r.x));
-          v[j + 1] = fmaf(v[j + 1], e.alpha, bf16_hi(r.x));
-          v[j + 2] = fmaf(v[j + 2], e.alpha, bf16_lo(r.y));
-          v[j + 3] = fmaf(v[j + 3], e.alpha, bf16_hi(r.y));
-          v[j + 4] = fmaf(v[j + 4], e.alpha, bf16_lo(r.z));
-          v[j + 5] = fmaf(v[j + 5], e.alpha, bf16_hi(r.z));
-          v[j + 6] = fmaf(v[j + 6], e.alpha, bf16_lo(r.w));
-          v[j + 7] = fmaf(v[j + 7], e.alpha, bf16_hi(r.w));
+          float r8[8] = {bf16_lo(r.x), bf16_hi(r.x), bf16_lo(r.y), bf16_hi(r.y),
+                         bf16_lo(r.z), bf16_hi(r.z), bf16_lo(r.w), bf16_hi(r.w)};
+          if (sg) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) r8[t] = fmaf(fmaf(r8[t], ra, rs), sg[j + t], sb[j + t]);
+          }
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v[j + t] = fmaf(v[j + t], e.alpha, r8[t]);
         }
       }
     }

@@ -37,7 +37,7 @@ class Engine:
 
     def __init__(self, model, config: Optional[ModelConfig] = None, device: int = 0, max_batch: int = 0,
                  validate_gemm: bool = False, validate_attn: bool = False, preln_bf16: bool = False,
-                 pdl: bool = False, graphs: bool = True):
+                 pdl: bool = False, graphs: bool = True, fused_ln: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("no CUDA device: the masked-coalition path has no CPU fallback")
         self.lib = _lib.load()
@@ -89,7 +89,7 @@ class Engine:
         cfg.max_batch = int(max_batch)
         cfg.flags = ((_lib.FLAG_VALIDATE_GEMM if validate_gemm else 0) | (_lib.FLAG_VALIDATE_ATTN if validate_attn else 0)
                      | (_lib.FLAG_BF16_PRELN if preln_bf16 else 0) | (_lib.FLAG_PDL if pdl else 0)
-                     | (0 if graphs else _lib.FLAG_NO_GRAPH))
+                     | (0 if graphs else _lib.FLAG_NO_GRAPH) | (0 if fused_ln else _lib.FLAG_UNFUSED_LN))
         names = list(keep.keys())
         n = len(names)
         c_names = (C.c_char_p * n)(*[s.encode() for s in names])

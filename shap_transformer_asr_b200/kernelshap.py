@@ -129,10 +129,14 @@ class KernelShapExplainer:
     initialised, the coalition rows are sharded across ranks (no data-path collective), the
     per-coalition outputs are all-gathered once, and every rank solves the regression."""
 
-    def __init__(self, engine, nsamples="auto", seed: int = 0):
+    def __init__(self, engine, nsamples="auto", seed: int = 0, shard_coalitions: bool = True):
+        """``shard_coalitions=False`` keeps every coalition of a clip on this rank even when torch.distributed is
+        initialised -- the clip-level sharding of batch sweeps (BASELINE config 5), where ranks explain DIFFERENT clips
+        and must not meet in a collective."""
         self.engine = engine
         self.nsamples = nsamples
         self.seed = seed
+        self.shard_coalitions = shard_coalitions
 
     def select_targets(self, mode: str = "logprob"):
         eng = self.engine
@@ -180,7 +184,7 @@ class KernelShapExplainer:
         head[1] = 0xFFFFFFFF
         if M % 32:
             head[1, -1] = (1 << (M % 32)) - 1
-        rank, world = wdist.rank_world()
+        rank, world = wdist.rank_world() if self.shard_coalitions else (0, 1)
         lo, hi = wdist.shard_range(K + 2, rank, world)
         bits_all = eng.bits_to_device(np.concatenate([head, words]))
         y_local = eng.eval_bits(bits_all[lo:hi]) if hi > lo else torch.empty((0, eng.out_width()), device=eng.device)

@@ -40,13 +40,17 @@ def make_test_set(num_clips: int = 2, num_samples: int = 102400, snrs=(5, 2, 1),
 
 
 def explain_test_set(engine, test_set: List[Dict], out_dir: str = "data", num_segments: int = 128, nsamples=2048,
-                     seed: int = 0, mode: str = "max") -> List[Dict]:
+                     seed: int = 0, mode: str = "max", save_limit=None, on_item=None) -> List[Dict]:
     """Explain every item and write ``{shap_values,audio,noise,text}_sample_{i}_{type}_{snr}.npy``
     (shap_calculation.py:200-210).  ``mode="max"`` explains the max logit of every output frame, which is what the
     reference's wrapper returns (shap_calculation.py:50), so the saved array has the reference's ``[1, L, T']`` shape.
-    The text of an item is the greedy transcript of its clip's clean version (random-init weights have no ground truth)."""
+    The text of an item is the greedy transcript of its clip's clean version (random-init weights have no ground truth).
+
+    Every item is explained on THIS rank's GPU (clip-level sharding: the caller hands each rank its items).
+    ``save_limit``: write the files of the first N items only (a 6.4 s item is 130 MB of float32 attributions);
+    ``on_item(index, item, shap_values, result)`` is called with the in-memory array of every item, saved or not."""
     os.makedirs(out_dir, exist_ok=True)
-    explainer = KernelShapExplainer(engine, nsamples=nsamples, seed=seed)
+    explainer = KernelShapExplainer(engine, nsamples=nsamples, seed=seed, shard_coalitions=False)
     results, clean_text = [], None
     for i, item in enumerate(test_set):
         x = normalize_clip(item["audio"])
@@ -64,10 +68,14 @@ def explain_test_set(engine, test_set: List[Dict], out_dir: str = "data", num_se
         phi = res["phi"].cpu().numpy()
         shap_values = expand_to_samples(phi, engine.bounds).astype(np.float32)      # [1, L, T']
         tag = f"sample_{i + 1}_{item['type']}_{item['snr']}"
-        np.save(os.path.join(out_dir, f"shap_values_{tag}"), shap_values)
-        np.save(os.path.join(out_dir, f"audio_{tag}"), item["audio"])
-        np.save(os.path.join(out_dir, f"noise_{tag}"), item["noise"])
-        np.save(os.path.join(out_dir, f"text_{tag}.npy"), text)
-        results.append(dict(tag=tag, hypothesis=hyp, text=text, shap_shape=shap_values.shape,
+        saved = save_limit is None or i < save_limit
+        if saved:
+            np.save(os.path.join(out_dir, f"shap_values_{tag}"), shap_values)
+            np.save(os.path.join(out_dir, f"audio_{tag}"), item["audio"])
+            np.save(os.path.join(out_dir, f"noise_{tag}"), item["noise"])
+            np.save(os.path.join(out_dir, f"text_{tag}.npy"), text)
+        results.append(dict(tag=tag, hypothesis=hyp, text=text, shap_shape=shap_values.shape, saved=saved,
                             status=int(res["status"].item())))
+        if on_item is not None:
+            on_item(i, item, shap_values, results[-1])
     return results

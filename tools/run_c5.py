@@ -31,31 +31,33 @@ def main():
     ap.add_argument("--coalitions", type=int, default=2048)
     ap.add_argument("--out", default="data_c5")
     ap.add_argument("--model", default="wav2vec2-base")
+    ap.add_argument("--save-limit", type=int, default=-1, help="write the four .npy files of the first N items per rank "
+                    "only (a 6.4 s item is 130 MB of attributions); -1 = all, as the reference does")
     args = ap.parse_args()
     rank, world = wdist.init_from_env("cuda") if int(os.environ.get("WORLD_SIZE", "1")) > 1 else (0, 1)
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     cfg = MODELS[args.model]
     model = build_random_init_model(cfg, seed=0)
-    eng = Engine(model, cfg, device=local, max_batch=128)
+    eng = Engine(model, cfg, device=local, max_batch=0)
     test_set = make_test_set(num_clips=args.clips, num_samples=args.samples, snrs=(5, 2, 1), seed=0)
     # keep each clip's clean item with its noisy versions on one rank (the clean transcript is their WER reference)
     mine = [i for i in range(len(test_set)) if (i // 4) % world == rank]
     torch.cuda.synchronize()
     wdist.barrier()
     t0 = time.perf_counter()
-    res = explain_test_set(eng, [test_set[i] for i in mine], out_dir=os.path.join(args.out, f"rank{rank}"),
-                           num_segments=args.segments, nsamples=args.coalitions, seed=0)
+    rows = []
+
+    def consume(k, item, shap_values, r):      # the downstream metrics of every item, from the in-memory attributions
+        rows.append(dict(item=mine[k], type=item["type"], snr=item["snr"], status=r["status"],
+                         eta_raw=eta_raw(item["audio"] - item["noise"], item["noise"], shap_values.squeeze(), 16000),
+                         wer=wer(r["text"], r["hypothesis"])))
+
+    explain_test_set(eng, [test_set[i] for i in mine], out_dir=os.path.join(args.out, f"rank{rank}"),
+                     num_segments=args.segments, nsamples=args.coalitions, seed=0,
+                     save_limit=None if args.save_limit < 0 else args.save_limit, on_item=consume)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    rows = []
-    for i, r in zip(mine, res):
-        item = test_set[i]
-        d = os.path.join(args.out, f"rank{rank}")
-        shap = np.load(os.path.join(d, f"shap_values_{r['tag']}.npy")).squeeze()
-        rows.append(dict(item=i, type=item["type"], snr=item["snr"], status=r["status"],
-                         eta_raw=eta_raw(item["audio"] - item["noise"], item["noise"], shap, 16000),
-                         wer=wer(r["text"], r["hypothesis"])))
     gathered = [None] * world
     if world > 1:
         td.all_gather_object(gathered, (rows, dt))
