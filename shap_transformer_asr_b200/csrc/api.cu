@@ -86,6 +86,7 @@ struct w2s_handle {
   // weights
   float *conv0_w = nullptr, *conv0_b = nullptr, *norm0_g = nullptr, *norm0_b = nullptr;
   float *ln0_wbar = nullptr, *ln0_gram = nullptr, *ln0_wb = nullptr;
+  bf16* ln0_wb48 = nullptr;
   float ln0_bmean = 0.f, ln0_b2mean = 0.f;
   bf16* conv_w[W2S_MAX_CONV_LAYERS] = {};
   float* conv_b[W2S_MAX_CONV_LAYERS] = {};
@@ -225,6 +226,10 @@ std::string load_weights(w2s_handle* h, const WeightTable& wt) {
         W2S_CUDA_OK(cudaMemcpy(hs, sc, sizeof(hs), cudaMemcpyDeviceToHost));
         h->ln0_bmean = hs[0];
         h->ln0_b2mean = hs[1];
+        if (kw == 10 && Cout % 64 == 0 && Cout <= 512) {
+          W2S_TRY(dalloc(h->allocs, &h->ln0_wb48, (size_t)Cout * 48));
+          W2S_TRY(launch_conv0_ln_b(h->conv0_w, h->conv0_b, h->norm0_g, h->norm0_b, Cout, kw, h->ln0_wb48, 0));
+        }
       }
     } else {
       const float* src = nullptr;
@@ -581,7 +586,7 @@ struct PlanBuilder {
       cp.w = h->conv0_w; cp.bias = h->conv0_b; cp.gamma = h->norm0_g; cp.beta = h->norm0_b;
       cp.gn_a = h->gn_a; cp.gn_b = h->gn_b; cp.gn_wb = h->gn_wb;
       cp.ln_wbar = h->ln0_wbar; cp.ln_gram = h->ln0_gram; cp.ln_wb = h->ln0_wb;
-      cp.ln_bmean = h->ln0_bmean; cp.ln_b2mean = h->ln0_b2mean;
+      cp.ln_bmean = h->ln0_bmean; cp.ln_b2mean = h->ln0_b2mean; cp.ln_wb48 = h->ln0_wb48;
       cp.out = h->bufA;
       if (!layer)
         add("conv0_stats", [=](cudaStream_t s) { return launch_conv0_stats(cp, s); }, 0.0,

@@ -368,12 +368,173 @@ __global__ void __launch_bounds__(256, 2) conv0_mma_kernel(const Conv0Params p, 
   }
 }
 
+// Layer-norm variant (feat_extract_norm = "layer": wav2vec2-large-lv60, the conformer checkpoints) in the same tensor-core
+// form.  Per frame f the LayerNorm over channels is affine in the conv output,
+//   y[f,c] = rstd_f gamma_c (sum_j w[c,j] x[f,j]) + rstd_f (gamma_c b_c) + (rstd_f mean_f)(-gamma_c) + beta_c,
+// so with the frame's rstd folded into the im2col row the whole layer is ONE K = 48 contraction whose B operand is a
+// constant of the model (built once at create by conv0_ln_b_kernel):
+//   A[f] = [xs_hi | xs_lo | xs_hi | r_hi r_lo r_hi | q_hi q_lo q_hi | 1 1 | 0...],  xs = rstd_f x,  r = rstd_f,  q = rstd_f mean_f
+//   B[c] = [gw_hi | gw_hi | gw_lo | t_hi t_hi t_lo | u_hi u_hi u_lo | beta_hi beta_lo | 0...],  gw = gamma_c w[c,:],  t = gamma_c b_c,  u = -gamma_c
+// (bf16 hi + lo terms; the lo x lo products, ~2^-18 relative, are dropped).  The frame statistics come from the 10-sample
+// window through the Gram matrix of the filter bank, as in the CUDA-core kernel this replaces.
+constexpr int C0L_K = 48, C0L_LDA = 112;   // 112-byte row pitch: 7 x 16 B, conflict-free ldmatrix
+
+template <int KW>
+__global__ void __launch_bounds__(256, 2) conv0_ln_mma_kernel(const Conv0Params p, int FT) {
+  extern __shared__ __align__(16) uint8_t smem_ln[];
+  __shared__ uint32_t zs[64];
+  uint8_t* im2col = smem_ln;                                             // [FT][112 B]
+  float* xs = reinterpret_cast<float*>(smem_ln + (size_t)FT * C0L_LDA);   // FT * stride + KW samples
+  pdl_trigger();
+  pdl_wait();
+  const int row = blockIdx.y;
+  const int f0 = blockIdx.x * FT;
+  const int nf = min(FT, p.T0 - f0);
+  const int nfp = (nf + 15) & ~15;
+  const WaveRow x = wave_row(p.dyn, row, zs);
+  const long long x0 = (long long)f0 * p.stride;
+  const int nwin = (nf - 1) * p.stride + KW;
+  for (int i = threadIdx.x; i < nwin; i += blockDim.x) xs[i] = x.at(x0 + i);
+  __syncthreads();
+  for (int f = threadIdx.x; f < nfp; f += blockDim.x) {
+    __nv_bfloat16* ar = reinterpret_cast<__nv_bfloat16*>(im2col + (size_t)f * C0L_LDA);
+    if (f >= nf) {
+#pragma unroll
+      for (int q = 0; q < C0L_K / 8; ++q) reinterpret_cast<uint4*>(ar)[q] = make_uint4(0u, 0u, 0u, 0u);
+      continue;
+    }
+    float xv[KW];
+#pragma unroll
+    for (int j = 0; j < KW; ++j) xv[j] = xs[f * p.stride + j];
+    // channel statistics of the conv output of this frame (quadratic form with the filter Gram matrix)
+    float mean = p.ln_bmean, ex2 = p.ln_b2mean;
+#pragma unroll
+    for (int j = 0; j < KW; ++j) {
+      mean = fmaf(p.ln_wbar[j], xv[j], mean);
+      ex2 = fmaf(2.0f * p.ln_wb[j], xv[j], ex2);
+      float gj = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < KW; ++jj) gj = fmaf(p.ln_gram[j * KW + jj], xv[jj], gj);
+      ex2 = fmaf(gj, xv[j], ex2);
+    }
+    const float rstd = rsqrtf(fmaxf(ex2 - mean * mean, 0.f) + 1e-5f);
+    auto split3 = [&](float v, int at) {   // (hi, lo, hi): pairs with (hi, hi, lo) on the B side
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      ar[at] = hi;
+      ar[at + 1] = __float2bfloat16_rn(v - __bfloat162float(hi));
+      ar[at + 2] = hi;
+    };
+#pragma unroll
+    for (int j = 0; j < KW; ++j) {
+      const float v = rstd * xv[j];
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      ar[j] = hi;
+      ar[KW + j] = __float2bfloat16_rn(v - __bfloat162float(hi));
+      ar[2 * KW + j] = hi;
+    }
+    split3(rstd, 3 * KW);
+    split3(rstd * mean, 3 * KW + 3);
+    ar[3 * KW + 6] = __float2bfloat16_rn(1.f);
+    ar[3 * KW + 7] = __float2bfloat16_rn(1.f);
+#pragma unroll
+    for (int k = 3 * KW + 8; k < C0L_K; ++k) ar[k] = __float2bfloat16_rn(0.f);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  uint32_t bfrag[8][3][2];
+  {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int ch = warp * 64 + (nt >> 2) * 32 + (g >> 1) * 8 + (nt & 3) * 2 + (g & 1);
+      const uint32_t* wr = reinterpret_cast<const uint32_t*>(p.ln_wb48 + (long long)ch * C0L_K);
+#pragma unroll
+      for (int ks = 0; ks < 3; ++ks) {
+        bfrag[nt][ks][0] = __ldg(wr + 8 * ks + t);
+        bfrag[nt][ks][1] = __ldg(wr + 8 * ks + t + 4);
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t a_base = smem_u32(im2col) + (lane & 15) * C0L_LDA + (lane >> 4) * 16;
+  __nv_bfloat16* out = p.out + ((long long)row * p.T0 + f0) * p.C + warp * 64 + t * 8;
+  for (int mb = 0; mb * 16 < nf; ++mb) {
+    uint32_t a[3][4];
+#pragma unroll
+    for (int ks = 0; ks < 3; ++ks) ldmatrix_x4(a[ks], a_base + mb * 16 * C0L_LDA + ks * 32);
+    float c[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 3; ++ks) mma_bf16_16816(c[nt], a[ks], bfrag[nt][ks]);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int f = mb * 16 + g + 8 * r;
+      if (f < nf) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 y = gelu_erf2(make_float2(c[4 * h + q][2 * r], c[4 * h + q][2 * r + 1]));
+            pk[q] = pack_bf16x2(y.x, y.y);
+          }
+          *reinterpret_cast<uint4*>(out + (long long)f * p.C + h * 32) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+    }
+  }
+}
+
+// B operand of conv0_ln_mma_kernel: [C][48] bf16, a constant of the model (run once at create)
+__global__ void conv0_ln_b_kernel(const float* w, const float* bias, const float* gamma, const float* beta, int C, int kw,
+                                  __nv_bfloat16* out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  __nv_bfloat16* o = out + (long long)c * C0L_K;
+  auto hi = [](float v) { return __float2bfloat16_rn(v); };
+  auto lo = [](float v) { return __float2bfloat16_rn(v - __bfloat162float(__float2bfloat16_rn(v))); };
+  const float g = gamma[c];
+  for (int j = 0; j < kw; ++j) {
+    const float v = g * w[c * kw + j];
+    o[j] = hi(v);
+    o[kw + j] = hi(v);
+    o[2 * kw + j] = lo(v);
+  }
+  const float t = g * (bias ? bias[c] : 0.f), u = -g;
+  o[3 * kw] = hi(t); o[3 * kw + 1] = hi(t); o[3 * kw + 2] = lo(t);
+  o[3 * kw + 3] = hi(u); o[3 * kw + 4] = hi(u); o[3 * kw + 5] = lo(u);
+  o[3 * kw + 6] = hi(beta[c]); o[3 * kw + 7] = lo(beta[c]);
+  for (int k = 3 * kw + 8; k < C0L_K; ++k) o[k] = __float2bfloat16_rn(0.f);
+}
+std::string launch_conv0_ln_b(const float* w, const float* bias, const float* gamma, const float* beta, int C, int kw,
+                              __nv_bfloat16* out, cudaStream_t s) {
+  if (3 * kw + 8 > C0L_K) return "conv0 (layer norm): kernel too wide for the K = 48 form";
+  conv0_ln_b_kernel<<<(C + 127) / 128, 128, 0, s>>>(w, bias, gamma, beta, C, kw, out);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
 std::string launch_conv0(const Conv0Params& p, bool layer_norm, cudaStream_t s) {
   if (p.kw != 10) return "conv0: only kernel width 10 is implemented for layer 0";
   if (!layer_norm && p.gn_wb && p.C % 64 == 0 && p.C <= 512 && p.n > 0) {
     const int FT = 512;
     dim3 grid((p.T0 + FT - 1) / FT, p.n);
     W2S_CUDA_OK(launch_pdl(conv0_mma_kernel<10>, grid, dim3(p.C / 2), (size_t)FT * 80, s, 1, p, FT));
+    W2S_CUDA_OK(cudaGetLastError());
+    return "";
+  }
+  if (layer_norm && p.ln_wb48 && p.C % 64 == 0 && p.C <= 512 && p.n > 0) {
+    const int FT = 512;
+    const size_t smem = (size_t)FT * C0L_LDA + (size_t)(FT * p.stride + p.kw + 4) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+      W2S_CUDA_OK(cudaFuncSetAttribute(conv0_ln_mma_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      attr = true;
+    }
+    if (smem > 100 * 1024) return "conv0 (layer norm): stride too large for the staged window";
+    dim3 grid((p.T0 + FT - 1) / FT, p.n);
+    W2S_CUDA_OK(launch_pdl(conv0_ln_mma_kernel<10>, grid, dim3(p.C / 2), smem, s, 1, p, FT));
     W2S_CUDA_OK(cudaGetLastError());
     return "";
   }
@@ -575,32 +736,39 @@ std::string launch_layernorm(const void* in, int in_fp32, long long rows, int H,
 // =================================================================================================
 // LayerNorm carried across two contractions (gemm.cuh: EpiParams): the two small kernels around the GEMM epilogues.
 // =================================================================================================
-// partial (sum, sum of squares) per 32-column block [rows][nparts] -> per-row (mean, rstd); summed in block order
+// partial (sum, sum of squares) per 32-column block [rows][nparts] -> per-row (mean, rstd).  Half a warp per row: lane i
+// sums the blocks i, i + 16, ... in order, then a fixed xor tree combines the 16 lanes (deterministic).
 __global__ void __launch_bounds__(256) ln_stats_finalize_kernel(const float2* __restrict__ parts, long long rows,
                                                                  int nparts, float inv_n, float eps,
                                                                  float2* __restrict__ out) {
   pdl_trigger();
   pdl_wait();
-  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  const float4* p4 = reinterpret_cast<const float4*>(parts + r * nparts);   // nparts is even
+  const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const int sub = threadIdx.x & 15;
   float s1 = 0.f, s2 = 0.f;
-  for (int i = 0; i < nparts / 2; ++i) {
-    const float4 t = __ldg(p4 + i);
-    s1 += t.x;
-    s2 += t.y;
-    s1 += t.z;
-    s2 += t.w;
+  if (r < rows) {
+    for (int i = sub; i < nparts; i += 16) {
+      const float2 t = __ldg(parts + r * nparts + i);
+      s1 += t.x;
+      s2 += t.y;
+    }
   }
-  const float mean = s1 * inv_n;
-  const float var = fmaxf(fmaf(-mean, mean, s2 * inv_n), 0.f);
-  out[r] = make_float2(mean, rsqrtf(var + eps));
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (r < rows && sub == 0) {
+    const float mean = s1 * inv_n;
+    const float var = fmaxf(fmaf(-mean, mean, s2 * inv_n), 0.f);
+    out[r] = make_float2(mean, rsqrtf(var + eps));
+  }
 }
 std::string launch_ln_stats_finalize(const float2* parts, long long rows, int N, float eps, float2* out, cudaStream_t s) {
   if (N % 64) return "carried LayerNorm: row length must be a multiple of 64";
   if (rows == 0) return "";
-  W2S_CUDA_OK(launch_pdl(ln_stats_finalize_kernel, dim3((unsigned)((rows + 255) / 256)), dim3(256), 0, s, 1, parts, rows,
-                         N / 32, 1.0f / (float)N, eps, out));
+  W2S_CUDA_OK(launch_pdl(ln_stats_finalize_kernel, dim3((unsigned)((rows * 16 + 255) / 256)), dim3(256), 0, s, 1, parts,
+                         rows, N / 32, 1.0f / (float)N, eps, out));
   W2S_CUDA_OK(cudaGetLastError());
   return "";
 }

@@ -185,32 +185,42 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           if (p.epi.res_ln) st_res = __ldg(p.epi.res_ln + m);
         }
         __syncwarp();
-        mbar_wait(tfull_bar(acc), acc_phase);
-        tc_fence_after();
         // 32-column sub-blocks of this warp, software-pipelined: the TMEM load of sub-block s+1 is in flight while the
         // values of s are written to the staging strip, and the wait for the TMA engine to have read the strip (previous
         // store) comes after the math of the sub-block instead of before its load.
         const int nsub = f32 ? nblk : 2 * nblk;
         auto sub_col = [&](int sidx) { return f32 ? (2 * sidx + hsel) * 32 : (2 * (sidx >> 1) + hsel) * 64 + (sidx & 1) * 32; };
+        // a bf16 residual row is fetched one sub-block ahead (the first one before the accumulator wait): its global
+        // latency then hides behind the main loop / the previous sub-block instead of stalling every sub-block
+        const bool res16 = p.epi.residual && !p.epi.res_fp32 && !reduce_add;
+        uint4 rnext[4] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u),
+                          make_uint4(0u, 0u, 0u, 0u)};
+        auto load_res = [&](int sidx_) {
+          if (res16 && row_ok) {
+            const uint4* rp = reinterpret_cast<const uint4*>(
+                reinterpret_cast<const __nv_bfloat16*>(p.epi.residual) + (long long)g * p.epi.ldg + (long long)b * p.epi.ldb +
+                (long long)m * p.epi.ldm + n0 + sub_col(sidx_));
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) rnext[q4] = __ldg(rp + q4);
+          }
+        };
+        load_res(0);
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
         float v[32];
         tmem_ld_32x32_issue(t0 + sub_col(0), v);
 #pragma unroll 1
         for (int sidx = 0; sidx < nsub; ++sidx) {
           const int c = sub_col(sidx);
           const int sub = f32 ? 0 : (sidx & 1);
+          uint4 rcur[4] = {rnext[0], rnext[1], rnext[2], rnext[3]};
+          if (sidx + 1 < nsub) load_res(sidx + 1);
           tmem_ld_wait();
           epi_math32(p.epi, p.epi.bias ? sbias + sidx * 32 : nullptr, p.N, g, b, m, n0 + c, row_ok, v, reduce_add,
                      p.epi.ln_in ? sc1 + sidx * 32 : nullptr, st_in, p.epi.res_ln ? sg + sidx * 32 : nullptr,
-                     sb + sidx * 32, st_res);
-          if (p.epi.stats_out && row_ok) {   // partial LayerNorm statistics of the stored row (see gemm.cuh)
-            float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              s1 += v[j];
-              s2 = fmaf(v[j], v[j], s2);
-            }
-            p.epi.stats_out[(long long)m * (p.N >> 5) + ((n0 + c) >> 5)] = make_float2(s1, s2);
-          }
+                     sb + sidx * 32, st_res, res16 ? rcur : nullptr);
+          if (p.epi.stats_out && row_ok)   // partial LayerNorm statistics of the stored row (see gemm.cuh)
+            p.epi.stats_out[(long long)m * (p.N >> 5) + ((n0 + c) >> 5)] = ln_partial32(v);
           if (f32) {
             if (lead) tma_store_wait_read();   // the previous store of this warp has drained the strip
             __syncwarp();

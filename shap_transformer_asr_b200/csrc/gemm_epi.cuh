@@ -4,6 +4,20 @@
 
 namespace w2s {
 
+// Partial LayerNorm statistics (sum, sum of squares) of 32 consecutive stored values.  The summation order is part of the
+// contract -- two interleaved chains (even / odd columns, i.e. one packed FADD2 / FFMA2 chain), then their sum -- so that
+// every contraction kernel produces the same bits for the same row.
+__device__ __forceinline__ float2 ln_partial32(const float* v) {
+  float2 s = make_float2(0.f, 0.f), q = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    const float2 t = make_float2(v[j], v[j + 1]);
+    s = __fadd2_rn(s, t);
+    q = __ffma2_rn(t, t, q);
+  }
+  return make_float2(s.x + s.y, q.x + q.y);
+}
+
 // ------------------------------------------------------------------------------------------------
 // epilogue shared by both kernels: CH consecutive columns of one output row
 // ------------------------------------------------------------------------------------------------
@@ -11,12 +25,15 @@ template <int CH>
 __device__ __forceinline__ void epi_store(const EpiParams& e, int N, int g, int b, int m, int ncol0, float* v) {
   // N is a multiple of the column chunk in both kernels (N % 4 == 0; tcgen05 tiles divide N exactly)
   if (ncol0 >= N) return;
-  if (e.ln_in) {   // consumer form of a carried LayerNorm: rstd (acc - mean c1[n]); c0 follows as the bias
+  if (e.ln_in) {
+    // consumer form of a carried LayerNorm: rstd (acc - mean c1[n]) + c0[n] = fma(a, acc, fma(b, c1[n], c0[n])) with
+    // a = rstd, b = -rstd mean (c0 arrives as the bias).  Every kernel uses exactly this operation sequence.
     const float2 st = __ldg(e.ln_in + m);
+    const float a = st.y, bb = -st.x * st.y;
 #pragma unroll
-    for (int j = 0; j < CH; ++j) v[j] = st.y * fmaf(-st.x, __ldg(e.ln_c1 + ncol0 + j), v[j]);
-  }
-  if (e.bias) {
+    for (int j = 0; j < CH; ++j)
+      v[j] = fmaf(a, v[j], fmaf(bb, __ldg(e.ln_c1 + ncol0 + j), __ldg(e.bias + ncol0 + j)));
+  } else if (e.bias) {
     const float4* bp = reinterpret_cast<const float4*>(e.bias + (long long)g * N + ncol0);
 #pragma unroll
     for (int j = 0; j < CH / 4; ++j) {
@@ -137,13 +154,7 @@ __device__ __forceinline__ void epi_store(const EpiParams& e, int N, int g, int 
     // partial LayerNorm statistics of the stored row, one (sum, sum of squares) per 32-column block, summed in column
     // order so that every contraction kernel produces the same bits
     if constexpr (CH == 32) {
-      float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        s1 += v[j];
-        s2 = fmaf(v[j], v[j], s2);
-      }
-      e.stats_out[(long long)m * (N >> 5) + (ncol0 >> 5)] = make_float2(s1, s2);
+      e.stats_out[(long long)m * (N >> 5) + (ncol0 >> 5)] = ln_partial32(v);
     } else if constexpr (CH == 4) {
       // validation kernel: 8 neighbouring threads hold the 32 columns of a block (tree order: not bit-identical to the
       // sequential sum of the tensor-core kernels, same value to fp32 round-off)
@@ -164,23 +175,26 @@ __device__ __forceinline__ void epi_store(const EpiParams& e, int N, int g, int 
 // Pair-kernel epilogue, first half: bias (from the warp's shared-memory strip) + activation + alpha / residual on
 // 32 consecutive columns of one row; the caller stores the result (TMA staging).
 // `sc1` / `sg` / `sb`: the warp's shared-memory strips of ln_c1 / res_g / res_b for these 32 columns; `st_in` / `st_res`:
-// the row's (mean, rstd) for the consumer form / the residual LayerNorm.
+// the row's (mean, rstd) for the consumer form / the residual LayerNorm; `rpre`: the 32 bf16 residual values of this
+// sub-block already in registers (the caller issued the loads one sub-block ahead, so their latency is not exposed).
 __device__ __forceinline__ void epi_math32(const EpiParams& e, const float* sbias, int N, int g, int b, int m,
                                            int ncol0, bool row_ok, float* v, bool skip_residual = false,
                                            const float* sc1 = nullptr, float2 st_in = make_float2(0.f, 1.f),
                                            const float* sg = nullptr, const float* sb = nullptr,
-                                           float2 st_res = make_float2(0.f, 1.f)) {
-  if (sc1) {
+                                           float2 st_res = make_float2(0.f, 1.f), const uint4* rpre = nullptr) {
+  if (sc1) {   // carried LayerNorm, consumer form (same operation sequence as epi_store), on the packed fp32 pipe
+    const float2 a2 = make_float2(st_in.y, st_in.y);
+    const float bb = -st_in.x * st_in.y;
+    const float2 b2 = make_float2(bb, bb);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float4 t = *reinterpret_cast<const float4*>(sc1 + 4 * j);
-      v[4 * j] = st_in.y * fmaf(-st_in.x, t.x, v[4 * j]);
-      v[4 * j + 1] = st_in.y * fmaf(-st_in.x, t.y, v[4 * j + 1]);
-      v[4 * j + 2] = st_in.y * fmaf(-st_in.x, t.z, v[4 * j + 2]);
-      v[4 * j + 3] = st_in.y * fmaf(-st_in.x, t.w, v[4 * j + 3]);
+      const float4 c = *reinterpret_cast<const float4*>(sc1 + 4 * j);
+      const float4 t = *reinterpret_cast<const float4*>(sbias + 4 * j);
+      const float2 lo = __ffma2_rn(a2, make_float2(v[4 * j], v[4 * j + 1]), __ffma2_rn(b2, make_float2(c.x, c.y), make_float2(t.x, t.y)));
+      const float2 hi = __ffma2_rn(a2, make_float2(v[4 * j + 2], v[4 * j + 3]), __ffma2_rn(b2, make_float2(c.z, c.w), make_float2(t.z, t.w)));
+      v[4 * j] = lo.x; v[4 * j + 1] = lo.y; v[4 * j + 2] = hi.x; v[4 * j + 3] = hi.y;
     }
-  }
-  if (sbias) {
+  } else if (sbias) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 t = *reinterpret_cast<const float4*>(sbias + 4 * j);
@@ -216,18 +230,28 @@ __device__ __forceinline__ void epi_math32(const EpiParams& e, const float* sbia
         }
       } else {
         const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(e.residual) + off;
-        const float ra = st_res.y, rs = -st_res.x * st_res.y;
+        const float rsv = -st_res.x * st_res.y;
+        const float2 ra2 = make_float2(st_res.y, st_res.y), rs2 = make_float2(rsv, rsv);
+        const float2 al2 = make_float2(e.alpha, e.alpha);
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
-          const uint4 r = *reinterpret_cast<const uint4*>(rp + j);
-          float r8[8] = {bf16_lo(r.x), bf16_hi(r.x), bf16_lo(r.y), bf16_hi(r.y),
-                         bf16_lo(r.z), bf16_hi(r.z), bf16_lo(r.w), bf16_hi(r.w)};
-          if (sg) {
-#pragma unroll
-            for (int t = 0; t < 8; ++t) r8[t] = fmaf(fmaf(r8[t], ra, rs), sg[j + t], sb[j + t]);
+          const uint4 r = rpre ? rpre[j >> 3] : *reinterpret_cast<const uint4*>(rp + j);
+          float2 r2[4] = {make_float2(bf16_lo(r.x), bf16_hi(r.x)), make_float2(bf16_lo(r.y), bf16_hi(r.y)),
+                          make_float2(bf16_lo(r.z), bf16_hi(r.z)), make_float2(bf16_lo(r.w), bf16_hi(r.w))};
+          if (sg) {   // residual LayerNorm on the fly: fma(fma(r, rstd, -mean rstd), gamma, beta), as in epi_store
+            const float4 g0 = *reinterpret_cast<const float4*>(sg + j), g1 = *reinterpret_cast<const float4*>(sg + j + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(sb + j), b1 = *reinterpret_cast<const float4*>(sb + j + 4);
+            r2[0] = __ffma2_rn(__ffma2_rn(r2[0], ra2, rs2), make_float2(g0.x, g0.y), make_float2(b0.x, b0.y));
+            r2[1] = __ffma2_rn(__ffma2_rn(r2[1], ra2, rs2), make_float2(g0.z, g0.w), make_float2(b0.z, b0.w));
+            r2[2] = __ffma2_rn(__ffma2_rn(r2[2], ra2, rs2), make_float2(g1.x, g1.y), make_float2(b1.x, b1.y));
+            r2[3] = __ffma2_rn(__ffma2_rn(r2[3], ra2, rs2), make_float2(g1.z, g1.w), make_float2(b1.z, b1.w));
           }
 #pragma unroll
-          for (int t = 0; t < 8; ++t) v[j + t] = fmaf(v[j + t], e.alpha, r8[t]);
+          for (int t = 0; t < 4; ++t) {
+            const float2 o = __ffma2_rn(make_float2(v[j + 2 * t], v[j + 2 * t + 1]), al2, r2[t]);
+            v[j + 2 * t] = o.x;
+            v[j + 2 * t + 1] = o.y;
+          }
         }
       }
     }

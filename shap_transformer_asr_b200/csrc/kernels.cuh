@@ -49,10 +49,15 @@ struct Conv0Params {
   const float* ln_gram;  // [kw][kw]   mean_c w[c][j] w[c][j']
   const float* ln_wb;    // [kw]       mean_c w[c][j] b[c]
   float ln_bmean, ln_b2mean;
+  const __nv_bfloat16* ln_wb48;  // [C][48] (optional) B operand of conv0_ln_mma_kernel: filters, bias and affine terms
+                                 // as bf16 hi/lo rows
   __nv_bfloat16* out;    // [n, T0, C] channels-last
 };
 std::string launch_conv0_stats(const Conv0Params& p, cudaStream_t s);         // group-norm statistics
 std::string launch_conv0(const Conv0Params& p, bool layer_norm, cudaStream_t s);
+// B operand of the tensor-core layer-norm variant (run once at create)
+std::string launch_conv0_ln_b(const float* w, const float* bias, const float* gamma, const float* beta, int C, int kw,
+                              __nv_bfloat16* out, cudaStream_t s);
 // filter-bank statistics for the layer-norm variant (run once at create)
 std::string launch_conv0_ln_prep(const float* w, const float* bias, int C, int kw, float* wbar, float* gram,
                                  float* wb, float* scalars /*[2]: mean b, mean b^2*/, cudaStream_t s);

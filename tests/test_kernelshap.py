@@ -167,3 +167,28 @@ def test_explain_orchestration_on_a_mock_engine(targets_given):
     assert eng.calls[0] == "set_clip" and eng.calls[-1] == f"eval:logprob:{Z.shape[0] + 2}"
     if not targets_given:
         assert "eval:logits:1" in eng.calls and len(res["frames"]) > 0
+
+
+def test_native_sampler_continues_numpys_global_generator():
+    """The per-draw permutations run natively (csrc/sampler.cu) on np.random's own MT19937 state: after a call the global
+    generator must be exactly where shap's pure-numpy loop would have left it, for unseeded continuation too."""
+    from shap_transformer_asr_b200.kernelshap import sample_coalitions, unpack_coalitions
+    from shap_transformer_asr_b200.preprocess import pack_coalitions
+    for M, K in [(7, 40), (33, 200), (100, 2048), (257, 300), (2048, 40)]:
+        np.random.seed(123)
+        np.random.random(17)                               # generator somewhere in the middle of its state block
+        Z1, w1, _ = sample_coalitions(M, K, seed=None)
+        Z2, w2, _ = sample_coalitions(M, K, seed=None)      # continues from the state the first call left
+        tail = np.random.random(3)
+        ref = KernelExplainerRef(lambda z: z.sum(1, keepdims=True), M)
+        np.random.seed(123)
+        np.random.random(17)
+        Za, wa = ref.sample(K)
+        ref2 = KernelExplainerRef(lambda z: z.sum(1, keepdims=True), M)
+        Zb, wb = ref2.sample(K)
+        assert np.array_equal(Z1, Za.astype(np.uint8)) and np.array_equal(w1, wa)
+        assert np.array_equal(Z2, Zb.astype(np.uint8)) and np.array_equal(w2, wb)
+        assert np.array_equal(tail, np.random.random(3))
+        words, w3, _ = sample_coalitions(M, K, seed=5, packed=True)
+        Z3, _, _ = sample_coalitions(M, K, seed=5)
+        assert np.array_equal(words, pack_coalitions(Z3)) and np.array_equal(unpack_coalitions(words, M), Z3)
