@@ -199,8 +199,8 @@ def run_b200(args):
     model = make_hf_model(cfg)
     # batch tile: rows = B * T' should fill whole waves of 128-row tiles on 148 SMs (B = floor(148*128*k / T'))
     # (the library picks B = floor(148*128*k / T') with B >= 128 itself when max_batch is 0)
-    eng = Engine(model, cfg, device=local, max_batch=max(0, args.batch), preln_bf16=args.preln_bf16, pdl=args.pdl,
-                 graphs=not args.no_graph, fused_ln=not args.unfused_ln)
+    eng = Engine(model, cfg, device=local, max_batch=max(0, args.batch), preln_fp32=args.preln_fp32,
+                 graphs=not args.no_graph)
     eng.set_clip(clip, num_segments=wl.num_segments)
     # targets: per-character frames of the unmasked clip (all frames if the random-init transcript is empty)
     eng.set_targets("logits")
@@ -428,9 +428,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--coalitions", type=int, default=0, help="profiling aid: evaluate only the first N coalitions per step")
-    ap.add_argument("--preln-bf16", action="store_true", help="A/B: bf16 pre-LayerNorm tensors (W2S_FLAG_BF16_PRELN)")
-    ap.add_argument("--pdl", action="store_true", help="A/B: programmatic dependent launch, eager launches (W2S_FLAG_PDL)")
-    ap.add_argument("--unfused-ln", action="store_true", help="A/B: standalone LayerNorm kernels (W2S_FLAG_UNFUSED_LN)")
+    ap.add_argument("--preln-fp32", action="store_true", help="A/B: fp32 pre-LayerNorm tensors (W2S_FLAG_FP32_PRELN)")
     ap.add_argument("--no-graph", action="store_true", help="A/B: launch every kernel of a tile instead of replaying a graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -40,11 +40,8 @@ enum {
 enum {
   W2S_FLAG_VALIDATE_GEMM = 1,  /* run every contraction on the CUDA-core validation kernels (same bf16 data) */
   W2S_FLAG_VALIDATE_ATTN = 2,  /* run attention on the CUDA-core validation kernel                            */
-  W2S_FLAG_BF16_PRELN    = 4,  /* post-LN models: bf16 (instead of fp32) pre-LayerNorm tensors -- A/B measurement */
-  W2S_FLAG_PDL           = 8,  /* programmatic dependent launch between the kernels of a tile -- A/B measurement  */
-  W2S_FLAG_NO_GRAPH      = 16, /* launch the kernels of a tile one by one instead of replaying a CUDA graph        */
-  W2S_FLAG_UNFUSED_LN    = 32  /* post-LN models: standalone LayerNorm kernels instead of LayerNorm carried through
-                                  the contraction epilogues -- A/B measurement                                     */
+  W2S_FLAG_FP32_PRELN    = 4,  /* post-LN models: fp32 (instead of bf16) pre-LayerNorm tensors -- A/B measurement */
+  W2S_FLAG_NO_GRAPH      = 16  /* launch the kernels of a tile one by one instead of replaying a CUDA graph        */
 };
 
 /* Mirrors transformers.Wav2Vec2Config / Wav2Vec2ConformerConfig (the objects the reference

@@ -16,7 +16,7 @@ MAX_CONV_LAYERS = 8
 
 OUT_MAX, OUT_LOGIT, OUT_LOGPROB, OUT_MEAN, OUT_LOGITS = 0, 1, 2, 3, 4
 MODE_IDS = {"max": OUT_MAX, "logit": OUT_LOGIT, "logprob": OUT_LOGPROB, "mean": OUT_MEAN, "logits": OUT_LOGITS}
-FLAG_VALIDATE_GEMM, FLAG_VALIDATE_ATTN, FLAG_BF16_PRELN, FLAG_PDL, FLAG_NO_GRAPH, FLAG_UNFUSED_LN = 1, 2, 4, 8, 16, 32
+FLAG_VALIDATE_GEMM, FLAG_VALIDATE_ATTN, FLAG_FP32_PRELN, FLAG_NO_GRAPH = 1, 2, 4, 16
 
 
 class W2SConfig(C.Structure):

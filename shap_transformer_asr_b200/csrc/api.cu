@@ -25,10 +25,6 @@ struct LayerW {
   bf16 *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
   float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
-  // post-LN models, LayerNorm carried across the contractions (gemm.cuh): consumer weights with gamma folded in and the
-  // correction vectors; qkv folds the PREVIOUS layer's final LayerNorm (layer 0 reads the normalised encoder input)
-  bf16 *wqkv_f = nullptr, *w1_f = nullptr;
-  float *qkv_c1 = nullptr, *qkv_c0 = nullptr, *f1_c1 = nullptr, *f1_c0 = nullptr;
   // conformer extras
   bf16 *f2w1 = nullptr, *f2w2 = nullptr, *wpos = nullptr, *pw1 = nullptr, *pw2 = nullptr;
   float *f2b1 = nullptr, *f2b2 = nullptr;
@@ -126,7 +122,6 @@ struct w2s_handle {
        *ffn = nullptr;
   float* pre = nullptr;
   float* logits = nullptr;
-  float2 *ln_parts = nullptr, *st_a = nullptr, *st_f = nullptr;   // carried LayerNorm: partial and per-row statistics
   bf16* hrot = nullptr;
   double* wls_work = nullptr;
   long long wls_cap = 0;
@@ -288,26 +283,6 @@ std::string load_weights(w2s_handle* h, const WeightTable& wt) {
       W2S_TRY(copy_f32(h, wt, lp + "feed_forward.output_dense.bias", H, &w.b2));
       W2S_TRY(copy_f32(h, wt, lp + "final_layer_norm.weight", H, &w.ln2_g));
       W2S_TRY(copy_f32(h, wt, lp + "final_layer_norm.bias", H, &w.ln2_b));
-      if (!c.do_stable_layer_norm && H % 64 == 0) {
-        const float* src = nullptr;
-        W2S_TRY(dalloc(h->allocs, &w.w1_f, (size_t)I * H));
-        W2S_TRY(dalloc(h->allocs, &w.f1_c1, (size_t)I));
-        W2S_TRY(dalloc(h->allocs, &w.f1_c0, (size_t)I));
-        W2S_TRY(wt.get(lp + "feed_forward.intermediate_dense.weight", (int64_t)I * H, &src));
-        W2S_TRY(launch_fold_ln(src, w.ln1_g, w.ln1_b, w.b1, I, H, w.w1_f, w.f1_c1, w.f1_c0, 0));
-        if (l > 0) {
-          const LayerW& pw = h->layers[l - 1];
-          W2S_TRY(dalloc(h->allocs, &w.wqkv_f, (size_t)3 * H * H));
-          W2S_TRY(dalloc(h->allocs, &w.qkv_c1, (size_t)3 * H));
-          W2S_TRY(dalloc(h->allocs, &w.qkv_c0, (size_t)3 * H));
-          const char* wn[3] = {"attention.q_proj.weight", "attention.k_proj.weight", "attention.v_proj.weight"};
-          for (int j = 0; j < 3; ++j) {
-            W2S_TRY(wt.get(lp + wn[j], (int64_t)H * H, &src));
-            W2S_TRY(launch_fold_ln(src, pw.ln2_g, pw.ln2_b, w.bqkv + (size_t)j * H, H, H, w.wqkv_f + (size_t)j * H * H,
-                                   w.qkv_c1 + (size_t)j * H, w.qkv_c0 + (size_t)j * H, 0));
-          }
-        }
-      }
     }
   } else {
     const int kd = c.conv_depthwise_kernel_size;
@@ -475,9 +450,6 @@ std::string ensure_workspace(w2s_handle* h, long long L) {
   W2S_TRY(dalloc(pool, &h->ctx, rows * H));
   W2S_TRY(dalloc(pool, &h->ffn, rows * I));
   W2S_TRY(dalloc(pool, &h->logits, rows * (size_t)h->head_ldl));
-  W2S_TRY(dalloc(pool, &h->ln_parts, rows * (size_t)(H / 32 + 1)));
-  W2S_TRY(dalloc(pool, &h->st_a, rows));
-  W2S_TRY(dalloc(pool, &h->st_f, rows));
   if (c.kind == 0) {
     W2S_TRY(dalloc(pool, &h->hp,
                    nb * (size_t)(T + c.num_conv_pos_embeddings) * c.num_conv_pos_embedding_groups * 64));
@@ -674,73 +646,12 @@ struct PlanBuilder {
     const double attn_flops = 4.0 * T * (double)T * H * n;
     const int act = c.hidden_act == 1 ? ACT_SWISH : ACT_GELU;
     const bool ln_res = !stable && (H == 128 || H == 256 || H == 512 || H == 768 || H == 1024);
-    // A/B switch for one measurement (bench.py --preln-bf16 sets it): post-LN models write the pre-LayerNorm tensor of
-    // out_proj / ffn2 as bf16 instead of fp32 -- halves the traffic of the one HBM-bound contraction and of both
-    // LayerNorms at the price of one more bf16 rounding per sub-layer.  Default: fp32.
-    const bool bf16_preln = (c.flags & W2S_FLAG_BF16_PRELN) != 0;
+    // Post-LN models write the pre-LayerNorm tensor of out_proj / ffn2 as bf16: it halves the traffic of the one
+    // HBM-bound contraction and of both LayerNorms (163.5 vs 170.4 ms per C2 step) at the price of one more bf16
+    // rounding per sub-layer, inside the parity tolerances (tests/test_gpu_parity.py).  W2S_FLAG_FP32_PRELN restores fp32.
+    const bool bf16_preln = (c.flags & W2S_FLAG_FP32_PRELN) == 0;
     const int pre32 = (bf16_preln && ln_res) ? 0 : 1;
-    // LayerNorm carried across the contractions (gemm.cuh: EpiParams) for post-LN models: out_proj / ffn2 store the
-    // un-normalised sums (bf16) + row statistics, qkv / ffn1 consume them through gamma-folded weights, and the
-    // normalised rows exist only inside epilogues.  The standalone-LayerNorm form stays for stable-LN models and as an
-    // A/B switch (W2S_FLAG_UNFUSED_LN).
-    const bool fused_ln = !stable && (H % 64 == 0) && !(c.flags & W2S_FLAG_UNFUSED_LN) && h->layers[0].w1_f != nullptr;
-    auto add_finalize = [&](const std::string& name, float2* dst) {
-      const float2* parts = h->ln_parts;
-      const float eps = c.layer_norm_eps;
-      add(name, [=](cudaStream_t s) { return launch_ln_stats_finalize(parts, rows, H, eps, dst, s); }, 0.0,
-          (double)rows * (H / 32 * 8.0 + 8.0));
-    };
-    for (int l = 0; l < c.num_hidden_layers && fused_ln; ++l) {
-      const LayerW& w = h->layers[l];
-      const std::string ls = "L" + std::to_string(l) + ".";
-      const LayerW* pw = l > 0 ? &h->layers[l - 1] : nullptr;
-      {   // layer 0 reads the normalised encoder input (hb); later layers the un-normalised x_f (also in hb)
-        GemmProblem p = plain(h->hb, rows, H, pw ? w.wqkv_f : w.wqkv, 3 * H);
-        p.epi.bias = pw ? w.qkv_c0 : w.bqkv;
-        if (pw) {
-          p.epi.ln_in = h->st_f;
-          p.epi.ln_c1 = w.qkv_c1;
-        }
-        p.epi.out = h->qkv;
-        W2S_TRY(add_gemm(ls + "qkv", p));
-      }
-      if (afl) add(ls + "attention", [=](cudaStream_t s) { return attention_fa_launch(afl, s); }, attn_flops);
-      else add(ls + "attention", [=](cudaStream_t s) { return launch_attention_simt(ap, s); }, attn_flops);
-      {   // x_a = LN_prev(x_f) + attention(...)  ->  h1 (bf16) + partial statistics
-        GemmProblem p = plain(h->ctx, rows, H, w.wo, H);
-        p.epi.bias = w.bo;
-        p.epi.residual = h->hb; p.epi.res_fp32 = 0;
-        if (pw) {
-          p.epi.res_ln = h->st_f; p.epi.res_g = pw->ln2_g; p.epi.res_b = pw->ln2_b;
-        }
-        p.epi.out = h->h1; p.epi.out_fp32 = 0;
-        p.epi.stats_out = h->ln_parts;
-        W2S_TRY(add_gemm(ls + "out_proj", p));
-      }
-      add_finalize(ls + "ln1_stats", h->st_a);
-      {
-        GemmProblem p = plain(h->h1, rows, H, w.w1_f, I);
-        p.epi.bias = w.f1_c0; p.epi.act = act;
-        p.epi.ln_in = h->st_a; p.epi.ln_c1 = w.f1_c1;
-        p.epi.out = h->ffn;
-        W2S_TRY(add_gemm(ls + "ffn1", p));
-      }
-      {   // x_f = LN1(x_a) + ffn(...)  ->  hb (bf16) + partial statistics
-        GemmProblem p = plain(h->ffn, rows, I, w.w2, H);
-        p.epi.bias = w.b2;
-        p.epi.residual = h->h1; p.epi.res_fp32 = 0;
-        p.epi.res_ln = h->st_a; p.epi.res_g = w.ln1_g; p.epi.res_b = w.ln1_b;
-        p.epi.out = h->hb; p.epi.out_fp32 = 0;
-        p.epi.stats_out = h->ln_parts;
-        W2S_TRY(add_gemm(ls + "ffn2", p));
-      }
-      if (l + 1 < c.num_hidden_layers) {
-        add_finalize(ls + "ln2_stats", h->st_f);
-      } else {   // the last LayerNorm feeds lm_head: applied in place (rows are read into registers before being written)
-        add_ln(ls + "ln2", h->hb, 0, rows, H, w.ln2_g, w.ln2_b, c.layer_norm_eps, ACT_NONE, h->hb, nullptr);
-      }
-    }
-    for (int l = 0; l < c.num_hidden_layers && !fused_ln; ++l) {
+    for (int l = 0; l < c.num_hidden_layers; ++l) {
       const LayerW& w = h->layers[l];
       const std::string ls = "L" + std::to_string(l) + ".";
       if (stable) add_ln(ls + "ln1", h->pre, 1, rows, H, w.ln1_g, w.ln1_b, c.layer_norm_eps, ACT_NONE, h->hb, nullptr);
@@ -1047,9 +958,8 @@ int w2s_create(const w2s_config* cfg, const char* const* names, const float* con
   h->num_sms = prop.multiProcessorCount;
   h->auto_batch = h->cfg.max_batch <= 0;
   if (h->auto_batch) h->cfg.max_batch = 64;
-  // graph replay needs fixed kernel arguments; the validation and PDL modes launch eagerly
-  h->use_graphs = (cfg->flags & (W2S_FLAG_NO_GRAPH | W2S_FLAG_VALIDATE_GEMM | W2S_FLAG_VALIDATE_ATTN | W2S_FLAG_PDL)) == 0;
-  pdl_flag() = (cfg->flags & W2S_FLAG_PDL) != 0;
+  // the validation modes launch eagerly
+  h->use_graphs = (cfg->flags & (W2S_FLAG_NO_GRAPH | W2S_FLAG_VALIDATE_GEMM | W2S_FLAG_VALIDATE_ATTN)) == 0;
   if (cudaMalloc((void**)&h->dyn_dev, sizeof(DynArgs)) != cudaSuccess ||
       cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
     g_create_error = "out of device memory";

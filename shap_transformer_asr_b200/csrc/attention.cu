@@ -179,8 +179,6 @@ attention_rel_kernel(const __grid_constant__ CUtensorMap mapQU, const __grid_con
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&s_tmem);
   const uint32_t trow = tmem + (static_cast<uint32_t>(qd * 32) << 16);
-  pdl_trigger();
-  pdl_wait();
 
   if (warp == 0 && elect_one()) {
     mbar_expect_tx(bar_q, 32768);

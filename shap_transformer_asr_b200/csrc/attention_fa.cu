@@ -113,8 +113,6 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
   // TMEM columns: S buffers at 0 / 128; O of block jj (0 / 1) of a chunk with running index gcx at 256 + 128 (gcx & 1) + 64 jj
-  pdl_trigger();
-  pdl_wait();
 
   if (warp == 8) {
     if (elect_one()) {

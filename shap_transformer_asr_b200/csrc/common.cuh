@@ -24,13 +24,8 @@ namespace w2s {
 #include <cstdlib>
 #include <utility>
 namespace w2s {
-// Launch with the programmatic-stream-serialization attribute (and an optional cluster width).
-// (W2S_FLAG_PDL at w2s_create; off by default: measured neutral at the 1 kW power cap in round 1)
-inline bool& pdl_flag() {
-  static bool on = false;
-  return on;
-}
-inline bool pdl_enabled() { return pdl_flag(); }
+// Launch through cudaLaunchKernelEx with an optional cluster width (the name is historical: programmatic dependent launch
+// was measured slower than plain launches -- 174.4 vs 170.4 ms per C2 step -- and removed in round 2).
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_x,
                               Args&&... args) {
@@ -46,11 +41,6 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[na].val.clusterDim.x = cluster_x;
     attr[na].val.clusterDim.y = 1;
     attr[na].val.clusterDim.z = 1;
-    ++na;
-  }
-  if (pdl_enabled()) {
-    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
   }
   cfg.attrs = attr;
@@ -435,12 +425,6 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-
-// Programmatic dependent launch: a kernel lets its successor's CTAs become resident (and run their prologue: barrier
-// init, TMEM allocation, descriptor prefetch) as soon as every CTA of this grid has passed pdl_trigger(); the successor
-// blocks in pdl_wait() until this grid has completed and its memory is visible.  Both are no-ops for plain launches.
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // UMMA shared-memory matrix descriptor, K-major operand tile stored as rows of 128 bytes (64 bf16) with the
 // TMA/UMMA 128-byte swizzle: 8-row groups are 1024 B apart (SBO), LBO unused for swizzled K-major.

@@ -34,8 +34,6 @@ __global__ void __launch_bounds__(256, 2) depthwise_kernel(const __nv_bfloat16* 
                                                          __nv_bfloat16* __restrict__ out) {
   constexpr int TT = 16, PAD = (K - 1) / 2, ROWS = 8 * TT + K - 1;
   __shared__ uint4 xs[ROWS * 8];   // [ROWS][64 channels] bf16, staged by the whole CTA with 16-byte loads
-  pdl_trigger();
-  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z;
   const int c_blk = blockIdx.y * 64;

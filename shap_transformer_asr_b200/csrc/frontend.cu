@@ -12,8 +12,6 @@ __global__ void __launch_bounds__(256) mask_kernel(const float* __restrict__ x, 
                                                     const uint32_t* __restrict__ zbits, int zwords, long long L,
                                                     float baseline, float* __restrict__ out, long long ld) {
   __shared__ uint32_t z[64];
-  pdl_trigger();
-  pdl_wait();
   const long long k = blockIdx.y;
   if (threadIdx.x < zwords) z[threadIdx.x] = zbits[k * zwords + threadIdx.x];
   __syncthreads();
@@ -98,8 +96,6 @@ __global__ void __launch_bounds__(256, 1) conv0_stats_kernel(const Conv0Params p
   __shared__ double red[8][NACC];
   __shared__ double tot[NACC];
   __shared__ uint32_t zs[64];
-  pdl_trigger();
-  pdl_wait();
   const int row = blockIdx.x;
   const WaveRow x = wave_row(p.dyn, row, zs);
   double acc[NACC];
@@ -203,8 +199,6 @@ __global__ void __launch_bounds__(256, 2) conv0_kernel(const Conv0Params p, int 
   float* frstd = fmean + FT;
   float2* xs2 = reinterpret_cast<float2*>(frstd + FT + ((FT * p.stride + KW) & 1));  // (x, x) pairs, 8-byte aligned
   __shared__ uint32_t zs[64];
-  pdl_trigger();
-  pdl_wait();
   const int row = blockIdx.y;
   const int f0 = blockIdx.x * FT;
   const int nf = min(FT, p.T0 - f0);
@@ -301,8 +295,6 @@ __global__ void __launch_bounds__(256, 2) conv0_mma_kernel(const Conv0Params p, 
   constexpr int LDA = 80;
   static_assert(3 * KW + 2 == 32, "K layout");
   __shared__ uint32_t zs[64];
-  pdl_trigger();
-  pdl_wait();
   const int row = blockIdx.y;
   const int f0 = blockIdx.x * FT;
   const int nf = min(FT, p.T0 - f0);
@@ -385,8 +377,6 @@ __global__ void __launch_bounds__(256, 2) conv0_ln_mma_kernel(const Conv0Params 
   __shared__ uint32_t zs[64];
   uint8_t* im2col = smem_ln;                                             // [FT][112 B]
   float* xs = reinterpret_cast<float*>(smem_ln + (size_t)FT * C0L_LDA);   // FT * stride + KW samples
-  pdl_trigger();
-  pdl_wait();
   const int row = blockIdx.y;
   const int f0 = blockIdx.x * FT;
   const int nf = min(FT, p.T0 - f0);
@@ -644,8 +634,6 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const void* __restri
                                                              __nv_bfloat16* __restrict__ out,
                                                              float* __restrict__ out_f32) {
   constexpr int H = 128 * NV;
-  pdl_trigger();
-  pdl_wait();
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -734,88 +722,12 @@ std::string launch_layernorm(const void* in, int in_fp32, long long rows, int H,
 }
 
 // =================================================================================================
-// LayerNorm carried across two contractions (gemm.cuh: EpiParams): the two small kernels around the GEMM epilogues.
-// =================================================================================================
-// partial (sum, sum of squares) per 32-column block [rows][nparts] -> per-row (mean, rstd).  Half a warp per row: lane i
-// sums the blocks i, i + 16, ... in order, then a fixed xor tree combines the 16 lanes (deterministic).
-__global__ void __launch_bounds__(256) ln_stats_finalize_kernel(const float2* __restrict__ parts, long long rows,
-                                                                 int nparts, float inv_n, float eps,
-                                                                 float2* __restrict__ out) {
-  pdl_trigger();
-  pdl_wait();
-  const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-  const int sub = threadIdx.x & 15;
-  float s1 = 0.f, s2 = 0.f;
-  if (r < rows) {
-    for (int i = sub; i < nparts; i += 16) {
-      const float2 t = __ldg(parts + r * nparts + i);
-      s1 += t.x;
-      s2 += t.y;
-    }
-  }
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) {
-    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-  }
-  if (r < rows && sub == 0) {
-    const float mean = s1 * inv_n;
-    const float var = fmaxf(fmaf(-mean, mean, s2 * inv_n), 0.f);
-    out[r] = make_float2(mean, rsqrtf(var + eps));
-  }
-}
-std::string launch_ln_stats_finalize(const float2* parts, long long rows, int N, float eps, float2* out, cudaStream_t s) {
-  if (N % 64) return "carried LayerNorm: row length must be a multiple of 64";
-  if (rows == 0) return "";
-  W2S_CUDA_OK(launch_pdl(ln_stats_finalize_kernel, dim3((unsigned)((rows * 16 + 255) / 256)), dim3(256), 0, s, 1, parts,
-                         rows, N / 32, 1.0f / (float)N, eps, out));
-  W2S_CUDA_OK(cudaGetLastError());
-  return "";
-}
-
-// consumer weights with the LayerNorm folded in (run once at create), one warp per output row n:
-//   w_out[n][k] = bf16(w[n][k] gamma[k]),  c1[n] = sum_k w_out[n][k] (the ROUNDED weights: acc - mean c1 then equals
-//   sum_k (x_k - mean) w_out[n][k] exactly),  c0[n] = sum_k w[n][k] beta[k] + bias[n]
-__global__ void __launch_bounds__(256) fold_ln_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, const float* __restrict__ bias,
-                                                       int N, int K, __nv_bfloat16* __restrict__ w_out,
-                                                       float* __restrict__ c1, float* __restrict__ c0) {
-  const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (n >= N) return;
-  double a1 = 0.0, a0 = 0.0;
-  for (int k = lane; k < K; k += 32) {
-    const float wv = w[(long long)n * K + k];
-    const __nv_bfloat16 q = __float2bfloat16_rn(wv * gamma[k]);
-    w_out[(long long)n * K + k] = q;
-    a1 += (double)__bfloat162float(q);
-    a0 += (double)wv * (double)beta[k];
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-  }
-  if (lane == 0) {
-    c1[n] = (float)a1;
-    c0[n] = (float)(a0 + (bias ? (double)bias[n] : 0.0));
-  }
-}
-std::string launch_fold_ln(const float* w, const float* gamma, const float* beta, const float* bias, int N, int K,
-                           __nv_bfloat16* w_out, float* c1, float* c0, cudaStream_t s) {
-  fold_ln_kernel<<<(N + 7) / 8, 256, 0, s>>>(w, gamma, beta, bias, N, K, w_out, c1, c0);
-  W2S_CUDA_OK(cudaGetLastError());
-  return "";
-}
-
-// =================================================================================================
 // positional-conv staging: zero-padded, 64-channel-per-group layout so that each tap of each group is one
 // 128-byte-wide TMA box (HF wav2vec2/modeling_wav2vec2.py:326-379: padding = k/2 on both sides).
 // =================================================================================================
 __global__ void __launch_bounds__(256) pos_pad_kernel(const __nv_bfloat16* __restrict__ h, int T, int H, int G,
                                                        int kpos, __nv_bfloat16* __restrict__ out) {
   // one thread = 8 consecutive channels (16 bytes) of one padded row
-  pdl_trigger();
-  pdl_wait();
   const int cpg = H / G;
   const int Tp = T + kpos;
   const int W8 = G * 8;

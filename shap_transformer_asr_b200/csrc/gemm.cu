@@ -99,8 +99,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  pdl_trigger();
-  pdl_wait();
 
   if (warp == 8) {
     if (elect_one()) {

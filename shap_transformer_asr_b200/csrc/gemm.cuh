@@ -18,21 +18,6 @@ struct EpiParams {
   void* out = nullptr;
   int out_fp32 = 0;
   long long ldg = 0, ldb = 0, ldm = 0;  // element strides of (group, batch, row); columns contiguous
-  // ---- LayerNorm carried across two contractions (post-LN encoder blocks; plain GEMMs only: G = Bz = 1) -----------
-  // A post-LN block computes h' = LN(h + f(h)).  Instead of a LayerNorm kernel between the contractions,
-  //   * the PRODUCER (out_proj / ffn2) stores the un-normalised sum x = h + f(h) as bf16 and, per 32-column block of
-  //     every row, the partial (sum, sum of squares) of the fp32 values          -> stats_out [rows][N/32] float2
-  //     (a tiny kernel turns them into per-row (mean, rstd));
-  //   * the CONSUMER (qkv / ffn1) multiplies x by weights with gamma folded in (W' = W gamma) and applies
-  //     LN(x) W^T + b = rstd (x W'^T - mean c1) + c0,  c1[n] = sum_k W'[n,k],  c0 = W beta + b   (bias = c0 here);
-  //   * where the normalised row is needed as the RESIDUAL of the next sub-layer, the producer's epilogue rebuilds it
-  //     from x on the fly: (x - mean) rstd gamma[n] + beta[n].
-  const float2* ln_in = nullptr;    // [rows] (mean, rstd) of this contraction's A rows (consumer form)
-  const float* ln_c1 = nullptr;     // [N]
-  const float2* res_ln = nullptr;   // [rows] (mean, rstd): the bf16 residual row is normalised on the fly
-  const float* res_g = nullptr;     // [N] gamma of that LayerNorm
-  const float* res_b = nullptr;     // [N] beta
-  float2* stats_out = nullptr;      // [rows][N/32] partial (sum, sum of squares) of the stored values
 };
 
 // C[g, b] (M x N) = A[g, b] (M x K) * W[g]^T (N x K).

@@ -18,8 +18,7 @@ struct Tc2Cfg {
   static constexpr int A_BYTES = 128 * 64 * 2;
   static constexpr int B_BYTES = (BN / 2) * 64 * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_BYTES = 8 * 4096 + 8 * 2048;  // per-warp 32 x 128 B output staging + four 512 B column strips
-                                                         // (bias, and the carried-LayerNorm vectors c1 / gamma / beta)
+  static constexpr int EPI_BYTES = 8 * 4096 + 8 * 512;   // per-warp 32 x 128 B output staging + bias strip
   // the operand ring takes what the epilogue strips leave: 5 x 32 KB (BN = 256) or 7 x 24 KB (BN = 128)
   static constexpr int STAGES = (227 * 1024 - 1024 - 256 - EPI_BYTES) / STAGE_BYTES > 8
                                     ? 8 : (227 * 1024 - 1024 - 256 - EPI_BYTES) / STAGE_BYTES;
@@ -77,8 +76,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  pdl_trigger();   // every CTA holds its smem/TMEM now: the next kernel may stage its prologue behind our tail
-  pdl_wait();      // operands and residuals of this kernel come from its predecessors
 
   if (warp == 8) {
     if (elect_one()) {
@@ -144,8 +141,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const bool lead = elect_one();   // the lane that owns this warp's TMA-store bulk groups
     const uint32_t stg = epi_smem + warp * 4096;              // this warp's 32 rows x 128 B staging strip
     const uint32_t stg_row = stg + lane * 128;
-    float* sbias = reinterpret_cast<float*>(tiles_ptr + C::STAGES * C::STAGE_BYTES + 8 * 4096 + warp * 2048);
-    float *sc1 = sbias + 128, *sg = sbias + 256, *sb = sbias + 384;
+    float* sbias = reinterpret_cast<float*>(tiles_ptr + C::STAGES * C::STAGE_BYTES + 8 * 4096 + warp * 512);
     const bool f32 = p.epi.out_fp32 != 0;
     // in-place fp32 accumulation (out == residual): let the TMA engine add in L2 instead of loading the residual
     const bool reduce_add = tma_out && f32 && p.epi.res_fp32 && p.epi.residual == p.epi.out;
@@ -167,60 +163,28 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         // shared-memory strip BEFORE the accumulator wait, so the global latency hides behind the MMAs.
         const int bw = f32 ? 32 : 64;
         const int nblk = BN / (2 * bw);
-        if (p.epi.bias || p.epi.ln_in || p.epi.res_ln) {
+        if (p.epi.bias) {
           for (int i = lane; i < nblk * bw; i += 32) {
             const int col = (2 * (i / bw) + hsel) * bw + (i % bw);
-            if (p.epi.bias) sbias[i] = __ldg(p.epi.bias + (long long)g * p.N + n0 + col);
-            if (p.epi.ln_in) sc1[i] = __ldg(p.epi.ln_c1 + n0 + col);
-            if (p.epi.res_ln) {
-              sg[i] = __ldg(p.epi.res_g + n0 + col);
-              sb[i] = __ldg(p.epi.res_b + n0 + col);
-            }
+            sbias[i] = __ldg(p.epi.bias + (long long)g * p.N + n0 + col);
           }
         }
-        // the row's LayerNorm statistics (carried-LayerNorm forms), also fetched ahead of the accumulator
-        float2 st_in = make_float2(0.f, 1.f), st_res = make_float2(0.f, 1.f);
-        if (row_ok) {
-          if (p.epi.ln_in) st_in = __ldg(p.epi.ln_in + m);
-          if (p.epi.res_ln) st_res = __ldg(p.epi.res_ln + m);
-        }
         __syncwarp();
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
         // 32-column sub-blocks of this warp, software-pipelined: the TMEM load of sub-block s+1 is in flight while the
         // values of s are written to the staging strip, and the wait for the TMA engine to have read the strip (previous
         // store) comes after the math of the sub-block instead of before its load.
         const int nsub = f32 ? nblk : 2 * nblk;
         auto sub_col = [&](int sidx) { return f32 ? (2 * sidx + hsel) * 32 : (2 * (sidx >> 1) + hsel) * 64 + (sidx & 1) * 32; };
-        // a bf16 residual row is fetched one sub-block ahead (the first one before the accumulator wait): its global
-        // latency then hides behind the main loop / the previous sub-block instead of stalling every sub-block
-        const bool res16 = p.epi.residual && !p.epi.res_fp32 && !reduce_add;
-        uint4 rnext[4] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u),
-                          make_uint4(0u, 0u, 0u, 0u)};
-        auto load_res = [&](int sidx_) {
-          if (res16 && row_ok) {
-            const uint4* rp = reinterpret_cast<const uint4*>(
-                reinterpret_cast<const __nv_bfloat16*>(p.epi.residual) + (long long)g * p.epi.ldg + (long long)b * p.epi.ldb +
-                (long long)m * p.epi.ldm + n0 + sub_col(sidx_));
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) rnext[q4] = __ldg(rp + q4);
-          }
-        };
-        load_res(0);
-        mbar_wait(tfull_bar(acc), acc_phase);
-        tc_fence_after();
         float v[32];
         tmem_ld_32x32_issue(t0 + sub_col(0), v);
 #pragma unroll 1
         for (int sidx = 0; sidx < nsub; ++sidx) {
           const int c = sub_col(sidx);
           const int sub = f32 ? 0 : (sidx & 1);
-          uint4 rcur[4] = {rnext[0], rnext[1], rnext[2], rnext[3]};
-          if (sidx + 1 < nsub) load_res(sidx + 1);
           tmem_ld_wait();
-          epi_math32(p.epi, p.epi.bias ? sbias + sidx * 32 : nullptr, p.N, g, b, m, n0 + c, row_ok, v, reduce_add,
-                     p.epi.ln_in ? sc1 + sidx * 32 : nullptr, st_in, p.epi.res_ln ? sg + sidx * 32 : nullptr,
-                     sb + sidx * 32, st_res, res16 ? rcur : nullptr);
-          if (p.epi.stats_out && row_ok)   // partial LayerNorm statistics of the stored row (see gemm.cuh)
-            p.epi.stats_out[(long long)m * (p.N >> 5) + ((n0 + c) >> 5)] = ln_partial32(v);
+          epi_math32(p.epi, p.epi.bias ? sbias + sidx * 32 : nullptr, p.N, g, b, m, n0 + c, row_ok, v, reduce_add);
           if (f32) {
             if (lead) tma_store_wait_read();   // the previous store of this warp has drained the strip
             __syncwarp();

@@ -1,0 +1,548 @@
+// Backward (input-gradient) kernels of the expected-gradients path -- the reference's production explainer
+// (shap.GradientExplainer, shap_calculation.py:125-162; loop structure feasability_tests/conformer_test.ipynb:95).
+// Expected gradients need d(output)/d(input) only: no weight gradients.  The dense contractions of the backward pass
+// (dX = dY W) run on the same tcgen05 contraction kernels as the forward pass, on pre-transposed weights; this file
+// holds what is left: the element-wise / normalisation / softmax backward steps and the data movement around the
+// strided convolutions.  First slice: Wav2Vec2 with a group-norm front end and a post-LN encoder (wav2vec2-base /
+// -large, the model family the reference runs).
+//
+// Conventions: activations saved by the forward pass are bf16 unless stated; gradients between contractions are bf16
+// (they feed a tensor-core A operand), gradients that are accumulated across a residual branch are fp32.
+#include "kernels.cuh"
+
+namespace w2s {
+
+// exact-erf GELU and its derivative (HF ACT2FN["gelu"]): gelu'(u) = Phi(u) + u phi(u)
+__device__ __forceinline__ float gelu_grad(float u) {
+  const float cdf = 0.5f * (1.0f + erff(u * 0.70710678118654752f));
+  const float pdf = 0.39894228040143268f * __expf(-0.5f * u * u);
+  return fmaf(u, pdf, cdf);
+}
+
+// y = gelu(u)   (the forward pass of the gradient path stores the pre-activation u and applies GELU separately)
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ y,
+                                                        long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 a = reinterpret_cast<const uint4*>(u)[i];
+    uint4 o;
+    o.x = pack_bf16x2(gelu_erf(bf16_lo(a.x)), gelu_erf(bf16_hi(a.x)));
+    o.y = pack_bf16x2(gelu_erf(bf16_lo(a.y)), gelu_erf(bf16_hi(a.y)));
+    o.z = pack_bf16x2(gelu_erf(bf16_lo(a.z)), gelu_erf(bf16_hi(a.z)));
+    o.w = pack_bf16x2(gelu_erf(bf16_lo(a.w)), gelu_erf(bf16_hi(a.w)));
+    reinterpret_cast<uint4*>(y)[i] = o;
+  }
+}
+std::string launch_gelu_fwd(const __nv_bfloat16* u, __nv_bfloat16* y, long long n, cudaStream_t s) {
+  if (n % 8) return "gelu_fwd: element count must be a multiple of 8";
+  if (n == 0) return "";
+  const long long n8 = n / 8;
+  gelu_fwd_kernel<<<(unsigned)((n8 + 255) / 256 > 148 * 16 ? 148 * 16 : (n8 + 255) / 256), 256, 0, s>>>(u, y, n8);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+// d <- d * gelu'(u)
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ d,
+                                                        long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 a = reinterpret_cast<const uint4*>(u)[i];
+    const uint4 g = reinterpret_cast<const uint4*>(d)[i];
+    uint4 o;
+    o.x = pack_bf16x2(bf16_lo(g.x) * gelu_grad(bf16_lo(a.x)), bf16_hi(g.x) * gelu_grad(bf16_hi(a.x)));
+    o.y = pack_bf16x2(bf16_lo(g.y) * gelu_grad(bf16_lo(a.y)), bf16_hi(g.y) * gelu_grad(bf16_hi(a.y)));
+    o.z = pack_bf16x2(bf16_lo(g.z) * gelu_grad(bf16_lo(a.z)), bf16_hi(g.z) * gelu_grad(bf16_hi(a.z)));
+    o.w = pack_bf16x2(bf16_lo(g.w) * gelu_grad(bf16_lo(a.w)), bf16_hi(g.w) * gelu_grad(bf16_hi(a.w)));
+    reinterpret_cast<uint4*>(d)[i] = o;
+  }
+}
+std::string launch_gelu_bwd(const __nv_bfloat16* u, __nv_bfloat16* d, long long n, cudaStream_t s) {
+  if (n % 8) return "gelu_bwd: element count must be a multiple of 8";
+  if (n == 0) return "";
+  const long long n8 = n / 8;
+  gelu_bwd_kernel<<<(unsigned)((n8 + 255) / 256 > 148 * 16 ? 148 * 16 : (n8 + 255) / 256), 256, 0, s>>>(u, d, n8);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+// fp32 -> bf16 copy of a gradient (A operand of the next contraction), optionally scaled element-wise by gelu'(u)
+__global__ void __launch_bounds__(256) grad_cast_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ u,
+                                                         __nv_bfloat16* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = g[i];
+    if (u) v *= gelu_grad(__bfloat162float(u[i]));
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+std::string launch_grad_cast(const float* g, const __nv_bfloat16* u, __nv_bfloat16* out, long long n, cudaStream_t s) {
+  if (n == 0) return "";
+  grad_cast_kernel<<<(unsigned)((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256), 256, 0, s>>>(g, u, out, n);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+// LayerNorm backward w.r.t. its input, one warp per row:
+//   xhat = (x - mean) rstd,  g = dy gamma,  dx = rstd (g - mean(g) - xhat mean(g xhat))  (+ add)
+// x is the saved LayerNorm INPUT (fp32 or bf16); statistics are recomputed from it (two-pass, fp32).
+template <bool X_F32>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const void* __restrict__ x, long long rows,
+                                                      int H, const float* __restrict__ gamma, float eps,
+                                                      const float* __restrict__ add, float* __restrict__ dx,
+                                                      __nv_bfloat16* __restrict__ dx16) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  constexpr int MAXV = 32;   // H <= 1024
+  float xv[MAXV], gv[MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    float t = 0.f;
+    if (idx < H) {
+      if constexpr (X_F32) t = reinterpret_cast<const float*>(x)[row * H + idx];
+      else t = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[row * H + idx]);
+    }
+    xv[i] = t;
+    sum += t;
+  }
+  const float mean = warp_sum(sum) / (float)H;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const float d = xv[i] - mean;
+    if (lane + 32 * i < H) sq = fmaf(d, d, sq);
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)H + eps);
+  float sg = 0.f, sgx = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    float g = 0.f;
+    if (idx < H) g = dy[row * H + idx] * __ldg(gamma + idx);
+    gv[i] = g;
+    xv[i] = (xv[i] - mean) * rstd;   // xhat
+    if (idx < H) {
+      sg += g;
+      sgx = fmaf(g, xv[i], sgx);
+    }
+  }
+  const float mg = warp_sum(sg) / (float)H, mgx = warp_sum(sgx) / (float)H;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < H) {
+      float v = rstd * (gv[i] - mg - xv[i] * mgx);
+      if (add) v += add[row * H + idx];
+      if (dx) dx[row * H + idx] = v;
+      if (dx16) dx16[row * H + idx] = __float2bfloat16_rn(v);
+    }
+  }
+}
+std::string launch_ln_bwd(const float* dy, const void* x, int x_fp32, long long rows, int H, const float* gamma, float eps,
+                          const float* add, float* dx, __nv_bfloat16* dx16, cudaStream_t s) {
+  if (H > 1024) return "ln_bwd: H > 1024 not supported";
+  if (rows == 0) return "";
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (x_fp32) ln_bwd_kernel<true><<<grid, 256, 0, s>>>(dy, x, rows, H, gamma, eps, add, dx, dx16);
+  else ln_bwd_kernel<false><<<grid, 256, 0, s>>>(dy, x, rows, H, gamma, eps, add, dx, dx16);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+// Start of the backward pass for the ModelWrapper output (max logit of frame `frames[b]`, shap_calculation.py:50):
+// d out / d logits is one-hot at (frames[b], argmax token), so d h[b, frames[b], :] = W_head[argmax, :] and zero elsewhere.
+// Also returns the selected output value.  logits: [n*T, ldl] fp32 from the forward pass.
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ logits, int ldl, int V,
+                                                        const __nv_bfloat16* __restrict__ w_head, int n, int T, int H,
+                                                        const int* __restrict__ frames, float* __restrict__ dh,
+                                                        float* __restrict__ out_val) {
+  const int b = blockIdx.x;
+  const int t = frames[b];
+  __shared__ int s_arg;
+  if (threadIdx.x < 32) {
+    const float* row = logits + ((long long)b * T + t) * ldl;
+    float best = -INFINITY;
+    int arg = 0;
+    for (int v = threadIdx.x; v < V; v += 32) {
+      const float x = row[v];
+      if (x > best) {
+        best = x;
+        arg = v;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (ob > best || (ob == best && oa < arg)) {   // first maximum, as torch.max
+        best = ob;
+        arg = oa;
+      }
+    }
+    if (threadIdx.x == 0) {
+      s_arg = arg;
+      if (out_val) out_val[b] = best;
+    }
+  }
+  __syncthreads();
+  const int arg = s_arg;
+  float* dst = dh + (long long)b * T * H;
+  for (long long i = threadIdx.x; i < (long long)T * H; i += blockDim.x) {
+    const int tt = (int)(i / H), k = (int)(i - (long long)tt * H);
+    dst[i] = tt == t ? __bfloat162float(w_head[(long long)arg * H + k]) : 0.f;
+  }
+}
+std::string launch_head_bwd(const float* logits, int ldl, int V, const __nv_bfloat16* w_head, int n, int T, int H,
+                            const int* frames, float* dh, float* out_val, cudaStream_t s) {
+  if (n == 0) return "";
+  head_bwd_kernel<<<n, 256, 0, s>>>(logits, ldl, V, w_head, n, T, H, frames, dh, out_val);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+// Self-attention backward (HF wav2vec2/modeling_wav2vec2.py:438-463; no mask, eval mode), CUDA cores, two passes that
+// need no atomics:
+//   pass 1, one warp per query row i:  S_i. = scale q_i K^T, P = softmax(S_i.), dP_ij = dO_i . v_j,
+//           D_i = sum_j P_ij dP_ij,  dS_ij = P_ij (dP_ij - D_i),  dq_i = scale sum_j dS_ij k_j;  saves (m_i, l_i, D_i)
+//   pass 2, one warp per key row j:    P_ij recomputed from (m_i, l_i),  dk_j = scale sum_i dS_ij q_i,  dv_j = sum_i P_ij dO_i
+// qkv: [B*T, ld] with q | k | v at column offsets 0 / H / 2H (+ head * hd);  dctx, dqkv likewise ([B*T, H], [B*T, 3H]).
+constexpr int AB_MAXC = 32;   // key chunks of 32 -> T <= 1024
+
+__global__ void __launch_bounds__(128) attn_bwd_q_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                          const __nv_bfloat16* __restrict__ dctx, int B, int T, int H,
+                                                          int heads, float scale, __nv_bfloat16* __restrict__ dqkv,
+                                                          float* __restrict__ stats /* [B, heads, T, 3] */) {
+  __shared__ float qs[4][64], dos[4][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long gw = (long long)blockIdx.x * 4 + warp;
+  if (gw >= (long long)B * heads * T) return;
+  const int i = (int)(gw % T), h = (int)((gw / T) % heads), b = (int)(gw / ((long long)T * heads));
+  const int ld = 3 * H;
+  const __nv_bfloat16* base = qkv + (long long)b * T * ld + h * 64;
+  for (int d = lane; d < 64; d += 32) {
+    qs[warp][d] = __bfloat162float(base[(long long)i * ld + d]);
+    dos[warp][d] = __bfloat162float(dctx[((long long)b * T + i) * H + h * 64 + d]);
+  }
+  __syncwarp();
+  float sc[AB_MAXC], dp[AB_MAXC];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < AB_MAXC; ++c) {
+    const int j = c * 32 + lane;
+    float a = -INFINITY, g = 0.f;
+    if (j < T) {
+      const __nv_bfloat16* kr = base + (long long)j * ld + H;
+      const __nv_bfloat16* vr = base + (long long)j * ld + 2 * H;
+      a = 0.f;
+      for (int d = 0; d < 64; d += 2) {
+        const uint32_t kk = *reinterpret_cast<const uint32_t*>(kr + d);
+        const uint32_t vv = *reinterpret_cast<const uint32_t*>(vr + d);
+        a = fmaf(qs[warp][d], bf16_lo(kk), a);
+        a = fmaf(qs[warp][d + 1], bf16_hi(kk), a);
+        g = fmaf(dos[warp][d], bf16_lo(vv), g);
+        g = fmaf(dos[warp][d + 1], bf16_hi(vv), g);
+      }
+      a *= scale;
+    }
+    sc[c] = a;
+    dp[c] = g;
+    mx = fmaxf(mx, a);
+  }
+  mx = warp_max(mx);
+  float l = 0.f;
+#pragma unroll
+  for (int c = 0; c < AB_MAXC; ++c) {
+    const float e = (c * 32 + lane < T) ? __expf(sc[c] - mx) : 0.f;
+    sc[c] = e;
+    l += e;
+  }
+  l = warp_sum(l);
+  const float inv = 1.0f / l;
+  float D = 0.f;
+#pragma unroll
+  for (int c = 0; c < AB_MAXC; ++c) {
+    sc[c] *= inv;                // P_ij
+    D = fmaf(sc[c], dp[c], D);
+  }
+  D = warp_sum(D);
+  // dq_i = scale sum_j dS_ij k_j: lanes own dims (2 each), dS broadcast by shuffle
+  float dq0 = 0.f, dq1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < AB_MAXC; ++c) {
+    if (c * 32 >= T) break;
+    const float ds = sc[c] * (dp[c] - D);
+    for (int l2 = 0; l2 < 32; ++l2) {
+      const int j = c * 32 + l2;
+      const float dsj = __shfl_sync(0xffffffffu, ds, l2);
+      if (j < T) {
+        const uint32_t kk = *reinterpret_cast<const uint32_t*>(base + (long long)j * ld + H + 2 * lane);
+        dq0 = fmaf(dsj, bf16_lo(kk), dq0);
+        dq1 = fmaf(dsj, bf16_hi(kk), dq1);
+      }
+    }
+  }
+  *reinterpret_cast<uint32_t*>(dqkv + ((long long)b * T + i) * ld + h * 64 + 2 * lane) = pack_bf16x2(dq0 * scale, dq1 * scale);
+  if (lane == 0) {
+    float* st = stats + (((long long)b * heads + h) * T + i) * 3;
+    st[0] = mx;
+    st[1] = inv;
+    st[2] = D;
+  }
+}
+
+__global__ void __launch_bounds__(128) attn_bwd_kv_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                           const __nv_bfloat16* __restrict__ dctx, int B, int T, int H,
+                                                           int heads, float scale, __nv_bfloat16* __restrict__ dqkv,
+                                                           const float* __restrict__ stats) {
+  __shared__ float ks[4][64], vs[4][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long gw = (long long)blockIdx.x * 4 + warp;
+  if (gw >= (long long)B * heads * T) return;
+  const int j = (int)(gw % T), h = (int)((gw / T) % heads), b = (int)(gw / ((long long)T * heads));
+  const int ld = 3 * H;
+  const __nv_bfloat16* base = qkv + (long long)b * T * ld + h * 64;
+  for (int d = lane; d < 64; d += 32) {
+    ks[warp][d] = __bfloat162float(base[(long long)j * ld + H + d]);
+    vs[warp][d] = __bfloat162float(base[(long long)j * ld + 2 * H + d]);
+  }
+  __syncwarp();
+  const float* st0 = stats + ((long long)b * heads + h) * T * 3;
+  float dk0 = 0.f, dk1 = 0.f, dv0 = 0.f, dv1 = 0.f;
+  for (int c = 0; c * 32 < T; ++c) {
+    const int i = c * 32 + lane;
+    float p = 0.f, ds = 0.f;
+    if (i < T) {
+      const __nv_bfloat16* qr = base + (long long)i * ld;
+      const __nv_bfloat16* dor = dctx + ((long long)b * T + i) * H + h * 64;
+      float a = 0.f, g = 0.f;
+      for (int d = 0; d < 64; d += 2) {
+        const uint32_t qq = *reinterpret_cast<const uint32_t*>(qr + d);
+        const uint32_t oo = *reinterpret_cast<const uint32_t*>(dor + d);
+        a = fmaf(bf16_lo(qq), ks[warp][d], a);
+        a = fmaf(bf16_hi(qq), ks[warp][d + 1], a);
+        g = fmaf(bf16_lo(oo), vs[warp][d], g);
+        g = fmaf(bf16_hi(oo), vs[warp][d + 1], g);
+      }
+      p = __expf(a * scale - st0[i * 3]) * st0[i * 3 + 1];
+      ds = p * (g - st0[i * 3 + 2]);
+    }
+    for (int l2 = 0; l2 < 32; ++l2) {
+      const int ii = c * 32 + l2;
+      const float pi = __shfl_sync(0xffffffffu, p, l2);
+      const float dsi = __shfl_sync(0xffffffffu, ds, l2);
+      if (ii < T) {
+        const uint32_t qq = *reinterpret_cast<const uint32_t*>(base + (long long)ii * ld + 2 * lane);
+        const uint32_t oo = *reinterpret_cast<const uint32_t*>(dctx + ((long long)b * T + ii) * H + h * 64 + 2 * lane);
+        dk0 = fmaf(dsi, bf16_lo(qq), dk0);
+        dk1 = fmaf(dsi, bf16_hi(qq), dk1);
+        dv0 = fmaf(pi, bf16_lo(oo), dv0);
+        dv1 = fmaf(pi, bf16_hi(oo), dv1);
+      }
+    }
+  }
+  __nv_bfloat16* orow = dqkv + ((long long)b * T + j) * ld + h * 64 + 2 * lane;
+  *reinterpret_cast<uint32_t*>(orow + H) = pack_bf16x2(dk0 * scale, dk1 * scale);
+  *reinterpret_cast<uint32_t*>(orow + 2 * H) = pack_bf16x2(dv0, dv1);
+}
+
+std::string launch_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx, int B, int T, int H, int heads, float scale,
+                            __nv_bfloat16* dqkv, float* stats, cudaStream_t s) {
+  if (H != heads * 64) return "attention backward: head_dim must be 64";
+  if (T > 32 * AB_MAXC) return "attention backward: more than 1024 frames are not supported yet";
+  const long long total = (long long)B * heads * T;
+  if (total == 0) return "";
+  attn_bwd_q_kernel<<<(unsigned)((total + 3) / 4), 128, 0, s>>>(qkv, dctx, B, T, H, heads, scale, dqkv, stats);
+  attn_bwd_kv_kernel<<<(unsigned)((total + 3) / 4), 128, 0, s>>>(qkv, dctx, B, T, H, heads, scale, dqkv, stats);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+// Strided conv, backward w.r.t. its input.  The contraction dcol[t_out, j C + c] = sum_o du[t_out, o] W[o][j C + c] ran on the
+// tensor cores; this gathers the <= ceil(kw / stride) taps that reach input frame t_in (t_in = stride t_out + j) and, when
+// `u_prev` is given, multiplies by gelu'(u_prev) -- the gradient w.r.t. the previous layer's pre-activation.
+__global__ void __launch_bounds__(256) conv_gather_kernel(const __nv_bfloat16* __restrict__ dcol, int T_in, int T_out, int C,
+                                                           int kw, int stride, const __nv_bfloat16* __restrict__ u_prev,
+                                                           __nv_bfloat16* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int C8 = C >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)T_in * C8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i / C8), c = (int)(i - (long long)t * C8) * 8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j = t % stride; j < kw; j += stride) {
+      const int to = (t - j) / stride;
+      if (t - j < 0 || to >= T_out) continue;
+      const uint4 v = *reinterpret_cast<const uint4*>(dcol + ((long long)b * T_out + to) * kw * C + (long long)j * C + c);
+      acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+      acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+    }
+    const long long o = ((long long)b * T_in + t) * C + c;
+    if (u_prev) {
+      const uint4 u = *reinterpret_cast<const uint4*>(u_prev + o);
+      acc[0] *= gelu_grad(bf16_lo(u.x)); acc[1] *= gelu_grad(bf16_hi(u.x));
+      acc[2] *= gelu_grad(bf16_lo(u.y)); acc[3] *= gelu_grad(bf16_hi(u.y));
+      acc[4] *= gelu_grad(bf16_lo(u.z)); acc[5] *= gelu_grad(bf16_hi(u.z));
+      acc[6] *= gelu_grad(bf16_lo(u.w)); acc[7] *= gelu_grad(bf16_hi(u.w));
+    }
+    uint4 r;
+    r.x = pack_bf16x2(acc[0], acc[1]); r.y = pack_bf16x2(acc[2], acc[3]);
+    r.z = pack_bf16x2(acc[4], acc[5]); r.w = pack_bf16x2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(out + o) = r;
+  }
+}
+std::string launch_conv_gather(const __nv_bfloat16* dcol, int n, int T_in, int T_out, int C, int kw, int stride,
+                               const __nv_bfloat16* u_prev, __nv_bfloat16* out, cudaStream_t s) {
+  if (C % 8) return "conv backward: channel count must be a multiple of 8";
+  if (n == 0) return "";
+  const long long per = (long long)T_in * (C / 8);
+  dim3 grid((unsigned)((per + 255) / 256 > 2048 ? 2048 : (per + 255) / 256), n);
+  conv_gather_kernel<<<grid, 256, 0, s>>>(dcol, T_in, T_out, C, kw, stride, u_prev, out);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+// conv0 + GroupNorm-over-time, backward to the waveform (HF wav2vec2/modeling_wav2vec2.py:302-323).  With
+// u = a_c (c0 - mean_c) + beta_c  (a_c = rstd_c gamma_c per (row, channel), c0 = conv0 output), du given:
+//   d c0[t, c] = a_c (du[t, c] - m1_c - xhat[t, c] m2_c),   m1_c = mean_t du,  m2_c = mean_t (du xhat),  xhat = (u - beta_c) / gamma_c
+//   d x[i]     = sum_c sum_{t, j: 5 t + j = i} w[c][j] d c0[t, c]
+// pass 1: per (row, channel) the two time means (one warp per 32 channels x a slab of frames, fp32 atomics-free: one CTA
+//         per (row, 64-channel group) walks all frames);  pass 2: per (row, frame) the 10 tap sums g[t][j] = sum_c w[c][j] d c0[t, c];
+// pass 3: gather d x[i] = g[i / 5][i % 5] + g[i / 5 - 1][i % 5 + 5].
+__global__ void __launch_bounds__(256) gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ du, const __nv_bfloat16* __restrict__ u,
+                                                            int T0, int C, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float* __restrict__ m12 /* [n, C, 2] */) {
+  // CTA = (64 channels, row); thread = (channel pair, frame lane): 32 channel pairs x 8 frame lanes
+  const int row = blockIdx.y, c0 = blockIdx.x * 64;
+  const int cp = threadIdx.x & 31, fl = threadIdx.x >> 5;
+  const int c = c0 + 2 * cp;
+  __shared__ float red[8][32][4];
+  float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+  if (c < C) {
+    const float ga = gamma[c], gb = gamma[c + 1], ba = beta[c], bb = beta[c + 1];
+    const float iga = 1.0f / ga, igb = 1.0f / gb;
+    for (int t = fl; t < T0; t += 8) {
+      const long long o = ((long long)row * T0 + t) * C + c;
+      const uint32_t dv = *reinterpret_cast<const uint32_t*>(du + o);
+      const uint32_t uv = *reinterpret_cast<const uint32_t*>(u + o);
+      const float da = bf16_lo(dv), db = bf16_hi(dv);
+      s1a += da;
+      s1b += db;
+      s2a = fmaf(da, (bf16_lo(uv) - ba) * iga, s2a);
+      s2b = fmaf(db, (bf16_hi(uv) - bb) * igb, s2b);
+    }
+  }
+  red[fl][cp][0] = s1a; red[fl][cp][1] = s1b; red[fl][cp][2] = s2a; red[fl][cp][3] = s2b;
+  __syncthreads();
+  if (fl == 0 && c < C) {
+    float r[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int f = 0; f < 8; ++f)
+      for (int q = 0; q < 4; ++q) r[q] += red[f][cp][q];
+    float* dst = m12 + ((long long)row * C + c) * 2;
+    const float invT = 1.0f / (float)T0;
+    dst[0] = r[0] * invT; dst[1] = r[2] * invT;   // channel c: (m1, m2)
+    dst[2] = r[1] * invT; dst[3] = r[3] * invT;   // channel c + 1
+  }
+}
+
+// pass 2: g[row, t, j] = sum_c w[c][j] a_c (du - m1_c - xhat m2_c); one warp per frame, lanes stride the channels
+template <int KW>
+__global__ void __launch_bounds__(256) conv0_bwd_taps_kernel(const __nv_bfloat16* __restrict__ du, const __nv_bfloat16* __restrict__ u,
+                                                              int T0, int C, const float* __restrict__ w /* [C][KW] */,
+                                                              const float* __restrict__ gn_a /* [n, C] */,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              const float* __restrict__ m12, float* __restrict__ g /* [n, T0, KW] */) {
+  const int row = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = blockIdx.x * 8 + warp; t < T0; t += gridDim.x * 8) {
+    float acc[KW];
+#pragma unroll
+    for (int j = 0; j < KW; ++j) acc[j] = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const long long o = ((long long)row * T0 + t) * C + c;
+      const float xh = (__bfloat162float(u[o]) - beta[c]) / gamma[c];
+      const float* mm = m12 + ((long long)row * C + c) * 2;
+      const float dc = gn_a[(long long)row * C + c] * (__bfloat162float(du[o]) - mm[0] - xh * mm[1]);
+#pragma unroll
+      for (int j = 0; j < KW; ++j) acc[j] = fmaf(__ldg(w + c * KW + j), dc, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < KW; ++j) acc[j] = warp_sum(acc[j]);
+    if (lane == 0) {
+      float* dst = g + ((long long)row * T0 + t) * KW;
+#pragma unroll
+      for (int j = 0; j < KW; ++j) dst[j] = acc[j];
+    }
+  }
+}
+
+// pass 3: d x[i] = sum over the frames t with 0 <= i - stride t < KW of g[t][i - stride t]
+__global__ void __launch_bounds__(256) conv0_bwd_gather_kernel(const float* __restrict__ g, int T0, int KW, int stride, long long L,
+                                                                float* __restrict__ dx, long long ld) {
+  const int row = blockIdx.y;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (long long)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    const long long thi = i / stride;
+    for (long long t = thi; t >= 0 && i - t * stride < KW; --t)
+      if (t < T0) acc += g[((long long)row * T0 + t) * KW + (i - t * stride)];
+    dx[(long long)row * ld + i] = acc;
+  }
+}
+
+std::string launch_conv0_bwd(const __nv_bfloat16* du, const __nv_bfloat16* u, int n, long long L, int T0, int C, int kw, int stride,
+                             const float* w, const float* gn_a, const float* gamma, const float* beta, float* m12, float* g,
+                             float* dx, long long ld, cudaStream_t s) {
+  if (kw != 10) return "conv0 backward: only kernel width 10 is implemented";
+  if (C % 64) return "conv0 backward: channel count must be a multiple of 64";
+  if (n == 0) return "";
+  gn_bwd_stats_kernel<<<dim3(C / 64, n), 256, 0, s>>>(du, u, T0, C, gamma, beta, m12);
+  conv0_bwd_taps_kernel<10><<<dim3((unsigned)((T0 + 7) / 8 > 1024 ? 1024 : (T0 + 7) / 8), n), 256, 0, s>>>(du, u, T0, C, w, gn_a, gamma,
+                                                                                                          beta, m12, g);
+  conv0_bwd_gather_kernel<<<dim3((unsigned)((L + 255) / 256 > 1024 ? 1024 : (L + 255) / 256), n), 256, 0, s>>>(g, T0, kw, stride, L, dx, ld);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+// ---- weight re-layout for the backward contractions (once, at first use) --------------------------------------
+// dst[c][r] = src[r][c]  (bf16, R x C -> C x R)
+__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R, int C) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? src[(long long)r * C + c] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < C) dst[(long long)c * R + r] = tile[threadIdx.x][i];
+  }
+}
+std::string launch_transpose_bf16(const __nv_bfloat16* src, __nv_bfloat16* dst, int R, int C, cudaStream_t s) {
+  transpose_bf16_kernel<<<dim3((C + 31) / 32, (R + 31) / 32), dim3(32, 8), 0, s>>>(src, dst, R, C);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+// positional conv, backward-data weights: w'[g][ci][j' * 64 + co] = w[g*cpg + co][ci][kw - 1 - j']  (zero for co >= cpg),
+// from the HF layout src[H][cpg][kw] (weight-norm already folded)
+__global__ void repack_posconv_bwd_kernel(const float* src, __nv_bfloat16* dst, int H, int G, int kw) {
+  const int cpg = H / G;
+  const long long n = (long long)H * kw * 64;   // [G][cpg (ci)][kw * 64 + co]
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i & 63);
+    const int jp = (int)((i >> 6) % kw);
+    const int row = (int)(i / ((long long)kw * 64));   // g * cpg + ci
+    const int g = row / cpg, ci = row - g * cpg;
+    float v = 0.f;
+    if (co < cpg) v = src[((long long)(g * cpg + co) * cpg + ci) * kw + (kw - 1 - jp)];
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+std::string launch_repack_posconv_bwd(const float* src, __nv_bfloat16* dst, int H, int G, int kw, cudaStream_t s) {
+  const long long n = (long long)H * kw * 64;
+  repack_posconv_bwd_kernel<<<(unsigned)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, s>>>(src, dst, H, G, kw);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+}  // namespace w2s

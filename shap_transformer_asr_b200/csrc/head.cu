@@ -122,8 +122,6 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadParams p) {
 
 // second stage of the tensor-core head: logits[rows, ldl] (fp32, bias included) -> reduction; one warp per work item
 __global__ void __launch_bounds__(256) head_reduce_kernel(const float* __restrict__ logits, const HeadParams p) {
-  pdl_trigger();
-  pdl_wait();
   const DynArgs d = *p.dyn;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool targeted = (d.mode == W2S_OUT_LOGIT || d.mode == W2S_OUT_LOGPROB);

@@ -68,13 +68,6 @@ std::string launch_layernorm(const void* in, int in_fp32, long long rows, int H,
                              const float* beta, float eps, int act, __nv_bfloat16* out, float* out_f32,
                              cudaStream_t s, const __nv_bfloat16* residual = nullptr);
 
-// ---- LayerNorm carried across two contractions (gemm.cuh: EpiParams) -----------------------------------------------
-// per-32-column partial (sum, sum of squares) [rows][N/32] -> per-row (mean, rstd)
-std::string launch_ln_stats_finalize(const float2* parts, long long rows, int N, float eps, float2* out, cudaStream_t s);
-// consumer weights with gamma folded in + the two correction vectors (once at create)
-std::string launch_fold_ln(const float* w, const float* gamma, const float* beta, const float* bias, int N, int K,
-                           __nv_bfloat16* w_out, float* c1, float* c0, cudaStream_t s);
-
 // ---- positional-conv input staging: [B, T, H] -> zero-padded [B, T + kpos, G*64] ------------------------
 std::string launch_pos_pad(const __nv_bfloat16* h, int B, int T, int H, int G, int kpos, __nv_bfloat16* out,
                            cudaStream_t s);

@@ -84,8 +84,6 @@ posconv_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   // TMEM columns: accumulator set a (alternating units) at 256 a; coalition u of the pair at + 128 u; row half at + 64 half
-  pdl_trigger();
-  pdl_wait();
 
   if (warp == 8) {
     if (elect_one()) {   // weight slices: one stream across units, never blocked by the windows

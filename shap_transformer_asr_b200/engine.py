@@ -36,8 +36,8 @@ class Engine:
     plain ``state_dict`` with HF parameter names plus an explicit :class:`ModelConfig`."""
 
     def __init__(self, model, config: Optional[ModelConfig] = None, device: int = 0, max_batch: int = 0,
-                 validate_gemm: bool = False, validate_attn: bool = False, preln_bf16: bool = False,
-                 pdl: bool = False, graphs: bool = True, fused_ln: bool = True):
+                 validate_gemm: bool = False, validate_attn: bool = False, preln_fp32: bool = False,
+                 graphs: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("no CUDA device: the masked-coalition path has no CPU fallback")
         self.lib = _lib.load()
@@ -88,8 +88,7 @@ class Engine:
         cfg.rotary_embedding_base = config.rotary_embedding_base
         cfg.max_batch = int(max_batch)
         cfg.flags = ((_lib.FLAG_VALIDATE_GEMM if validate_gemm else 0) | (_lib.FLAG_VALIDATE_ATTN if validate_attn else 0)
-                     | (_lib.FLAG_BF16_PRELN if preln_bf16 else 0) | (_lib.FLAG_PDL if pdl else 0)
-                     | (0 if graphs else _lib.FLAG_NO_GRAPH) | (0 if fused_ln else _lib.FLAG_UNFUSED_LN))
+                     | (_lib.FLAG_FP32_PRELN if preln_fp32 else 0) | (0 if graphs else _lib.FLAG_NO_GRAPH))
         names = list(keep.keys())
         n = len(names)
         c_names = (C.c_char_p * n)(*[s.encode() for s in names])

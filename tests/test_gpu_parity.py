@@ -34,12 +34,12 @@ def P():
 
 
 @pytest.mark.parametrize("name", IMPLEMENTED)
-@pytest.mark.parametrize("mode", ["validate", "tcgen05", "unfused_ln"])
+@pytest.mark.parametrize("mode", ["validate", "tcgen05", "fp32_preln"])
 def test_tiny_logits_match_golden(P, golden_dir, name, mode):
     g = np.load(os.path.join(golden_dir, f"{name}.npz"))
     cfg = VARIANTS[name]
     eng = P.Engine(build_model(cfg), cfg, max_batch=2, validate_gemm=mode == "validate", validate_attn=mode == "validate",
-                   fused_ln=mode != "unfused_ln")
+                   preln_fp32=mode == "fp32_preln")
     eng.set_targets("logits")
     x = torch.from_numpy(g["x"]).cuda()
     out = eng.eval_waveforms(x).view(g["logits"].shape).cpu().numpy()   # 3 rows, batch tile 2: ragged last tile
