@@ -113,6 +113,21 @@ int w2s_eval(w2s_handle* h, const uint32_t* z_bits_dev, int64_t K, float* out_de
 int w2s_eval_waveforms(w2s_handle* h, const float* x_dev, int64_t n, int64_t L, int64_t ld, float* out_dev,
                        void* stream);
 
+/* Expected-gradients path -- the reference's production explainer differentiates ModelWrapper's output
+ * (shap.GradientExplainer(wrapped_model, ...).shap_values, shap_calculation.py:133,162; per output index
+ * `outputs = self.model(*X); outputs[:, idx]` then autograd, conformer_test.ipynb:95).  For explicit waveform rows
+ * x[n, L] (fp32, device, row stride `ld`) and one output frame per row (host array): out[r] = max_v logits[r,
+ * frames[r], v] (shap_calculation.py:50) and grad[r, :] = d out[r] / d x[r, :] (fp32 [n, L], device).  Input
+ * gradients only -- no weight gradients.  First slice: Wav2Vec2ForCTC with the group-norm front end and a post-LN
+ * encoder (wav2vec2-base / -large); other configurations return an error. */
+int w2s_grad_waveforms(w2s_handle* h, const float* x_dev, int64_t n, int64_t L, int64_t ld,
+                       const int32_t* frames_host, float* grad_dev, float* out_dev, void* stream);
+/* Test hooks of the gradient path: keep snapshots of the gradient after every encoder layer / conv layer
+ * ("layer<l>", "h0", "conv<l>", "convu<l>") and copy one out (returns bytes copied, 0 = unknown name, < 0 = buffer
+ * too small by that many bytes). */
+int w2s_grad_debug(w2s_handle* h, int on);
+int64_t w2s_grad_peek(w2s_handle* h, const char* name, void* dst_dev, int64_t max_bytes, void* stream);
+
 /* Standalone masker (conformer_test.ipynb:138-141 semantics with keep-bits): materialise
  * out[K, L] = keep ? x : baseline for the clip set by w2s_set_clip. */
 int w2s_mask(w2s_handle* h, const uint32_t* z_bits_dev, int64_t K, float* out_dev, void* stream);

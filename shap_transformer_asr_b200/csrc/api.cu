@@ -5,6 +5,7 @@
 #include "gemm.cuh"
 #include "kernels.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -67,6 +68,12 @@ struct Plan {
 };
 
 __global__ void set_dyn_kernel(DynArgs* dst, const DynArgs v) { *dst = v; }
+
+// expected-gradients path: transposed dense weights of one encoder layer (dX = dY W runs as a contraction with W^T)
+struct GradW {
+  bf16 *wqkvT = nullptr, *woT = nullptr, *w1T = nullptr, *w2T = nullptr;
+};
+struct GradPlan;
 
 }  // namespace
 
@@ -131,6 +138,19 @@ struct w2s_handle {
   bool profiling = false;
   std::vector<ProfRec> prof;
 
+  // expected-gradients path (grad_plan.cuh): backward weights, plans per tile size, per-call pointers
+  bool grad_ready = false;
+  std::vector<GradW> gradw;
+  bf16* conv_wT[W2S_MAX_CONV_LAYERS] = {};
+  bf16* fp_wT = nullptr;
+  bf16* pos_w_bwd = nullptr;          // flipped / transposed positional-conv filters (built at create)
+  std::map<int, std::shared_ptr<GradPlan>> grad_plans;
+  long long grad_L = -1;
+  int grad_tile = 32;
+  bool grad_debug = false, grad_debug_built = false;
+  std::vector<int32_t> grad_frames_host;
+  float *grad_out = nullptr, *grad_out_val = nullptr;
+
   // per-call arguments of the plan's kernels (kernels.cuh: DynArgs), rewritten before every tile
   DynArgs* dyn_dev = nullptr;
   int head_ldl = 0;             // logits row stride: vocab rounded up to a multiple of 32
@@ -144,6 +164,7 @@ struct w2s_handle {
       cudaEventDestroy(r.e1);
     }
     plans.clear();
+    grad_plans.clear();
     if (cap_stream) cudaStreamDestroy(cap_stream);
     if (dyn_dev) cudaFree(dyn_dev);
     if (clip) cudaFree(clip);
@@ -255,6 +276,8 @@ std::string load_weights(w2s_handle* h, const WeightTable& wt) {
     W2S_TRY(wt.get(P + "encoder.pos_conv_embed.conv.weight", (int64_t)H * cpg * kp, &src));
     W2S_TRY(dalloc(h->allocs, &h->pos_w, (size_t)H * kp * 64));
     W2S_TRY(launch_repack_posconv(src, h->pos_w, H, G, kp, 0));
+    W2S_TRY(dalloc(h->allocs, &h->pos_w_bwd, (size_t)H * kp * 64));
+    W2S_TRY(launch_repack_posconv_bwd(src, h->pos_w_bwd, H, G, kp, 0));
     W2S_TRY(copy_f32(h, wt, P + "encoder.pos_conv_embed.conv.bias", H, &h->pos_b));
     for (int l = 0; l < c.num_hidden_layers; ++l) {
       LayerW& w = h->layers[l];
@@ -917,6 +940,8 @@ std::string check_targets(const w2s_handle* h) {
   return "";
 }
 
+#include "grad_plan.cuh"
+
 int fail(w2s_handle* h, const std::string& e) {
   h->err = e;
   return 1;
@@ -1094,6 +1119,33 @@ int w2s_eval_waveforms(w2s_handle* h, const float* x_dev, int64_t n, int64_t L, 
   if (e.empty()) e = check_targets(h);
   if (e.empty()) e = run_batches(h, nullptr, x_dev, ld, n, out_dev, (cudaStream_t)stream);
   return e.empty() ? 0 : fail(h, "eval_waveforms: " + e);
+}
+
+int w2s_grad_waveforms(w2s_handle* h, const float* x_dev, int64_t n, int64_t L, int64_t ld, const int32_t* frames_host,
+                       float* grad_dev, float* out_dev, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || !x_dev || !frames_host || !grad_dev) return fail(h, "grad_waveforms: null buffer");
+  if (ld < L) return fail(h, "grad_waveforms: row stride smaller than the row length");
+  std::string e = run_grad(h, x_dev, ld, L, n, frames_host, grad_dev, out_dev, (cudaStream_t)stream);
+  return e.empty() ? 0 : fail(h, "grad_waveforms: " + e);
+}
+
+int w2s_grad_debug(w2s_handle* h, int on) {
+  h->grad_debug = on != 0;
+  return 0;
+}
+
+int64_t w2s_grad_peek(w2s_handle* h, const char* name, void* dst_dev, int64_t max_bytes, void* stream) {
+  for (auto& kv : h->grad_plans) {
+    auto it = kv.second->peek.find(name);
+    if (it == kv.second->peek.end()) continue;
+    const int64_t bytes = (int64_t)it->second.second;
+    if (bytes > max_bytes) return -bytes;
+    if (cudaMemcpyAsync(dst_dev, it->second.first, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream) != cudaSuccess)
+      return 0;
+    return bytes;
+  }
+  return 0;
 }
 
 int w2s_mask(w2s_handle* h, const uint32_t* z_bits_dev, int64_t K, float* out_dev, void* stream) {

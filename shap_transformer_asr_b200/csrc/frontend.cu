@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(256, 2) conv0_kernel(const Conv0Params p, int 
 // conflict-free ldmatrix), each warp owns 64 channels whose B fragments stay in registers, and the channel
 // permutation inside a warp is chosen so that a thread ends up with 8 consecutive channels per (frame, half):
 // one 16-byte store, 64 contiguous bytes per quad.
-template <int KW>
+template <int KW, bool PRE>
 __global__ void __launch_bounds__(256, 2) conv0_mma_kernel(const Conv0Params p, int FT) {
   extern __shared__ __align__(16) uint8_t im2col[];
   constexpr int LDA = 80;
@@ -350,7 +350,8 @@ __global__ void __launch_bounds__(256, 2) conv0_mma_kernel(const Conv0Params p, 
           uint32_t pk[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float2 y = gelu_erf2(make_float2(c[4 * h + q][2 * r], c[4 * h + q][2 * r + 1]));
+            const float2 a = make_float2(c[4 * h + q][2 * r], c[4 * h + q][2 * r + 1]);
+            const float2 y = PRE ? a : gelu_erf2(a);
             pk[q] = pack_bf16x2(y.x, y.y);
           }
           *reinterpret_cast<uint4*>(out + (long long)f * p.C + h * 32) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -510,7 +511,8 @@ std::string launch_conv0(const Conv0Params& p, bool layer_norm, cudaStream_t s) 
   if (!layer_norm && p.gn_wb && p.C % 64 == 0 && p.C <= 512 && p.n > 0) {
     const int FT = 512;
     dim3 grid((p.T0 + FT - 1) / FT, p.n);
-    W2S_CUDA_OK(launch_pdl(conv0_mma_kernel<10>, grid, dim3(p.C / 2), (size_t)FT * 80, s, 1, p, FT));
+    if (p.pre_act) W2S_CUDA_OK(launch_pdl(conv0_mma_kernel<10, true>, grid, dim3(p.C / 2), (size_t)FT * 80, s, 1, p, FT));
+    else W2S_CUDA_OK(launch_pdl(conv0_mma_kernel<10, false>, grid, dim3(p.C / 2), (size_t)FT * 80, s, 1, p, FT));
     W2S_CUDA_OK(cudaGetLastError());
     return "";
   }
@@ -726,7 +728,7 @@ std::string launch_layernorm(const void* in, int in_fp32, long long rows, int H,
 // 128-byte-wide TMA box (HF wav2vec2/modeling_wav2vec2.py:326-379: padding = k/2 on both sides).
 // =================================================================================================
 __global__ void __launch_bounds__(256) pos_pad_kernel(const __nv_bfloat16* __restrict__ h, int T, int H, int G,
-                                                       int kpos, __nv_bfloat16* __restrict__ out) {
+                                                       int kpos, int left, __nv_bfloat16* __restrict__ out) {
   // one thread = 8 consecutive channels (16 bytes) of one padded row
   const int cpg = H / G;
   const int Tp = T + kpos;
@@ -737,7 +739,7 @@ __global__ void __launch_bounds__(256) pos_pad_kernel(const __nv_bfloat16* __res
     const int tp = (int)(i / W8);
     const int c8 = (int)(i - (long long)tp * W8);
     const int g = c8 >> 3, c = (c8 & 7) * 8;
-    const int t = tp - kpos / 2;
+    const int t = tp - left;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (t >= 0 && t < T && c < cpg) {
       const __nv_bfloat16* src = h + ((long long)b * T + t) * H + g * cpg + c;
@@ -754,12 +756,13 @@ __global__ void __launch_bounds__(256) pos_pad_kernel(const __nv_bfloat16* __res
   }
 }
 std::string launch_pos_pad(const __nv_bfloat16* h, int B, int T, int H, int G, int kpos, __nv_bfloat16* out,
-                           cudaStream_t s) {
+                           cudaStream_t s, int left) {
+  if (left < 0) left = kpos / 2;
   if (H % G || H / G > 64) return "pos_pad: channels per group must be <= 64";
   if (B == 0) return "";
   const long long per = (long long)(T + kpos) * G * 8;
   dim3 grid((unsigned)((per + 255) / 256 > 1024 ? 1024 : (per + 255) / 256), B);
-  W2S_CUDA_OK(launch_pdl(pos_pad_kernel, grid, dim3(256), 0, s, 1, h, T, H, G, kpos, out));
+  W2S_CUDA_OK(launch_pdl(pos_pad_kernel, grid, dim3(256), 0, s, 1, h, T, H, G, kpos, left, out));
   W2S_CUDA_OK(cudaGetLastError());
   return "";
 }

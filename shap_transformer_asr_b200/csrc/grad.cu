@@ -64,6 +64,19 @@ std::string launch_gelu_bwd(const __nv_bfloat16* u, __nv_bfloat16* d, long long 
   return "";
 }
 
+// pre0 = h0 + gelu(upos)   (positional-conv branch + residual of the gradient-path forward, fp32 out)
+__global__ void __launch_bounds__(256) add_gelu_kernel(const __nv_bfloat16* __restrict__ h0, const __nv_bfloat16* __restrict__ up,
+                                                        float* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __bfloat162float(h0[i]) + gelu_erf(__bfloat162float(up[i]));
+}
+std::string launch_add_gelu(const __nv_bfloat16* h0, const __nv_bfloat16* up, float* out, long long n, cudaStream_t s) {
+  if (n == 0) return "";
+  add_gelu_kernel<<<(unsigned)((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256), 256, 0, s>>>(h0, up, out, n);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
 // fp32 -> bf16 copy of a gradient (A operand of the next contraction), optionally scaled element-wise by gelu'(u)
 __global__ void __launch_bounds__(256) grad_cast_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ u,
                                                          __nv_bfloat16* __restrict__ out, long long n) {

@@ -1,0 +1,451 @@
+// Expected-gradients path (the reference's production explainer: shap.GradientExplainer over ModelWrapper,
+// shap_calculation.py:125-162): forward pass with saved activations + backward pass to the waveform, for one batch tile.
+// Included by api.cu inside its anonymous namespace (it needs w2s_handle / Step / PlanBuilder::plain).
+//
+// Scope of this first slice: Wav2Vec2ForCTC with feat_extract_norm = "group", no conv bias, post-LN encoder, GELU
+// (facebook/wav2vec2-base-960h -- the model the reference runs -- and wav2vec2-large-960h).  Only d(output)/d(input) is
+// computed: no weight gradients.  Every dense backward contraction dX = dY W runs on the tcgen05 contraction kernels of
+// the forward pass with pre-transposed weights; attention backward and the normalisation / activation / conv-gather
+// steps are CUDA-core kernels (grad.cu).
+#pragma once
+
+struct GradLayerBuf {
+  bf16* qkv = nullptr;    // [rows, 3H]   saved q | k | v
+  float* s1 = nullptr;    // [rows, H]    h + attention(h): input of layer_norm
+  bf16* u = nullptr;      // [rows, I]    pre-activation of the feed-forward
+  float* s2 = nullptr;    // [rows, H]    h1 + ffn(h1): input of final_layer_norm
+};
+
+struct GradPlan {
+  int n = 0;
+  std::vector<Step> steps;
+  std::vector<GemmLaunch*> gemms;
+  std::vector<PosConvPlan*> posconv;
+  std::vector<AttnFaPlan*> attn_fa;
+  std::vector<void*> allocs;
+  // buffers the entry point reads / snapshots
+  float* logits = nullptr;
+  float* dA = nullptr;
+  bf16* D[2] = {nullptr, nullptr};
+  int* frames = nullptr;
+  std::map<std::string, std::pair<const void*, size_t>> peek;   // debug: name -> (device buffer, bytes) snapshots
+  ~GradPlan() {
+    for (auto* f : attn_fa) attention_fa_free(f);
+    for (auto* pc : posconv) posconv_free(pc);
+    for (auto* g : gemms) delete g;
+    for (void* p : allocs) cudaFree(p);
+  }
+};
+
+std::string grad_supported(const w2s_handle* h) {
+  const w2s_config& c = h->cfg;
+  if (c.kind != 0) return "gradient path: only Wav2Vec2ForCTC is built (conformer: not yet)";
+  if (c.feat_extract_norm != 0 || c.conv_bias) return "gradient path: only the group-norm front end without conv bias is built";
+  if (c.do_stable_layer_norm) return "gradient path: only the post-LN encoder is built";
+  if (c.hidden_act != 0) return "gradient path: only GELU is built";
+  if (c.hidden_size != c.num_attention_heads * 64) return "gradient path: head_dim must be 64";
+  if (c.num_conv_pos_embeddings % 2) return "gradient path: odd positional-conv kernels are not built";
+  if (c.conv_kernel[0] != 10 || c.conv_dim[0] % 64 || c.conv_dim[0] > 512)
+    return "gradient path: conv0 must be k = 10 with 64..512 channels (a multiple of 64)";
+  return "";
+}
+
+// transposed copies of the dense weights for dX = dY W (once per handle)
+std::string grad_prepare_weights(w2s_handle* h) {
+  if (h->grad_ready) return "";
+  const w2s_config& c = h->cfg;
+  const int H = c.hidden_size, I = c.intermediate_size;
+  auto tr = [&](const bf16* src, int R, int C, bf16** dst) -> std::string {
+    W2S_TRY(dalloc(h->allocs, dst, (size_t)R * C));
+    return launch_transpose_bf16(src, *dst, R, C, 0);
+  };
+  h->gradw.resize(c.num_hidden_layers);
+  for (int l = 0; l < c.num_hidden_layers; ++l) {
+    const LayerW& w = h->layers[l];
+    GradW& g = h->gradw[l];
+    W2S_TRY(tr(w.wqkv, 3 * H, H, &g.wqkvT));   // [3H][H] -> [H][3H]
+    W2S_TRY(tr(w.wo, H, H, &g.woT));
+    W2S_TRY(tr(w.w1, I, H, &g.w1T));           // [I][H] -> [H][I]
+    W2S_TRY(tr(w.w2, H, I, &g.w2T));           // [H][I] -> [I][H]
+  }
+  for (int l = 1; l < c.num_conv_layers; ++l)
+    W2S_TRY(tr(h->conv_w[l], c.conv_dim[l], c.conv_kernel[l] * c.conv_dim[l - 1], &h->conv_wT[l]));   // [O][kw C] -> [kw C][O]
+  const int Cl = c.conv_dim[c.num_conv_layers - 1];
+  W2S_TRY(tr(h->fp_w, H, Cl, &h->fp_wT));      // [H][Cl] -> [Cl][H]
+  W2S_CUDA_OK(cudaDeviceSynchronize());
+  h->grad_ready = true;
+  return "";
+}
+
+struct GradBuilder {
+  w2s_handle* h;
+  GradPlan* plan;
+  int n;
+  long long L;
+  std::vector<int> Tl;
+  int T = 0;
+  bool debug = false;
+
+  template <typename TT>
+  std::string alloc(TT** out, size_t count, bool zero = false) { return dalloc(plan->allocs, out, count, zero); }
+  void add(const std::string& name, std::function<std::string(cudaStream_t)> f) {
+    plan->steps.push_back(Step{name, std::move(f)});
+  }
+  std::string add_gemm(const std::string& name, const GemmProblem& p) {
+    GemmLaunch* gl = new GemmLaunch();
+    plan->gemms.push_back(gl);
+    W2S_TRY(gemm_prepare(p, h->num_sms, gl));
+    add(name, [gl](cudaStream_t s) { return gemm_launch_tc(*gl, s); });
+    return "";
+  }
+  // debug snapshot of a gradient buffer right after the step that produced it
+  std::string snap(const std::string& name, const void* src, size_t bytes) {
+    if (!debug) return "";
+    uint8_t* dst = nullptr;
+    W2S_TRY(alloc(&dst, bytes));
+    add("snap." + name, [=](cudaStream_t s) -> std::string {
+      W2S_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
+      return "";
+    });
+    plan->peek[name] = {dst, bytes};
+    return "";
+  }
+
+  std::string build() {
+    const w2s_config& c = h->cfg;
+    const int H = c.hidden_size, I = c.intermediate_size, NL = c.num_hidden_layers, NC = c.num_conv_layers;
+    const int C0 = c.conv_dim[0];
+    T = (int)num_frames(c, L, &Tl);
+    if (T <= 0) return "clip shorter than the conv receptive field";
+    const long long rows = (long long)n * T;
+    const int nn = n;
+    w2s_handle* hh = h;
+
+    // ---- buffers ------------------------------------------------------------------------------------------------
+    std::vector<bf16*> u(NC), y(NC);
+    for (int l = 0; l < NC; ++l) {
+      W2S_TRY(alloc(&u[l], (size_t)n * Tl[l] * c.conv_dim[l]));
+      W2S_TRY(alloc(&y[l], (size_t)n * Tl[l] * c.conv_dim[l]));
+    }
+    float *gn_a = nullptr, *gn_b = nullptr;
+    bf16* gn_wb = nullptr;
+    W2S_TRY(alloc(&gn_a, (size_t)n * C0));
+    W2S_TRY(alloc(&gn_b, (size_t)n * C0));
+    W2S_TRY(alloc(&gn_wb, (size_t)n * C0 * 32));
+    const int Cl = c.conv_dim[NC - 1];
+    bf16 *fpn = nullptr, *h0 = nullptr, *hp = nullptr, *upos = nullptr, *hb = nullptr, *h1 = nullptr, *ctx = nullptr, *ffn = nullptr;
+    float* pre0 = nullptr;
+    const int G = c.num_conv_pos_embedding_groups, kp = c.num_conv_pos_embeddings, cpg = H / G;
+    W2S_TRY(alloc(&fpn, (size_t)rows * Cl));
+    W2S_TRY(alloc(&h0, (size_t)rows * H));
+    W2S_TRY(alloc(&hp, (size_t)n * (T + kp) * G * 64));
+    W2S_TRY(alloc(&upos, (size_t)rows * H));
+    W2S_TRY(alloc(&pre0, (size_t)rows * H));
+    W2S_TRY(alloc(&hb, (size_t)rows * H));
+    W2S_TRY(alloc(&h1, (size_t)rows * H));
+    W2S_TRY(alloc(&ctx, (size_t)rows * H));
+    W2S_TRY(alloc(&ffn, (size_t)rows * I));
+    W2S_TRY(alloc(&plan->logits, (size_t)rows * h->head_ldl));
+    std::vector<GradLayerBuf> lb(NL);
+    for (int l = 0; l < NL; ++l) {
+      W2S_TRY(alloc(&lb[l].qkv, (size_t)rows * 3 * H));
+      W2S_TRY(alloc(&lb[l].s1, (size_t)rows * H));
+      W2S_TRY(alloc(&lb[l].u, (size_t)rows * I));
+      W2S_TRY(alloc(&lb[l].s2, (size_t)rows * H));
+    }
+    // backward
+    float *dA = nullptr, *dS = nullptr, *attn_stats = nullptr, *dFp = nullptr, *m12 = nullptr, *gtap = nullptr;
+    bf16 *dS16 = nullptr, *dF = nullptr, *dC = nullptr, *dQKV = nullptr, *dcol = nullptr;
+    W2S_TRY(alloc(&dA, (size_t)rows * H));
+    W2S_TRY(alloc(&dS, (size_t)rows * H));
+    W2S_TRY(alloc(&dS16, (size_t)rows * H));
+    W2S_TRY(alloc(&dF, (size_t)rows * I));
+    W2S_TRY(alloc(&dC, (size_t)rows * H));
+    W2S_TRY(alloc(&dQKV, (size_t)rows * 3 * H));
+    W2S_TRY(alloc(&attn_stats, (size_t)rows * c.num_attention_heads * 3));
+    W2S_TRY(alloc(&dFp, (size_t)rows * Cl));
+    size_t dmax = 0, colmax = 0;
+    for (int l = 0; l < NC; ++l) {
+      dmax = std::max(dmax, (size_t)n * Tl[l] * c.conv_dim[l]);
+      if (l >= 1) colmax = std::max(colmax, (size_t)n * Tl[l] * c.conv_kernel[l] * c.conv_dim[l - 1]);
+    }
+    W2S_TRY(alloc(&plan->D[0], dmax));
+    W2S_TRY(alloc(&plan->D[1], dmax));
+    W2S_TRY(alloc(&dcol, colmax));
+    W2S_TRY(alloc(&m12, (size_t)n * C0 * 2));
+    W2S_TRY(alloc(&gtap, (size_t)n * Tl[0] * c.conv_kernel[0]));
+    W2S_TRY(alloc(&plan->frames, (size_t)n));
+    plan->dA = dA;
+
+    // ================================ forward, activations saved =================================================
+    {
+      Conv0Params cp{};
+      cp.dyn = h->dyn_dev;
+      cp.n = n; cp.L = (int)L; cp.T0 = Tl[0]; cp.C = C0; cp.kw = c.conv_kernel[0]; cp.stride = c.conv_stride[0];
+      cp.w = h->conv0_w; cp.bias = nullptr; cp.gamma = h->norm0_g; cp.beta = h->norm0_b;
+      cp.gn_a = gn_a; cp.gn_b = gn_b; cp.gn_wb = gn_wb;
+      cp.out = u[0];
+      cp.pre_act = 1;   // store the normalised pre-activation; GELU follows as its own step
+      add("conv0_stats", [=](cudaStream_t s) { return launch_conv0_stats(cp, s); });
+      add("conv0", [=](cudaStream_t s) { return launch_conv0(cp, false, s); });
+      const long long ne = (long long)n * Tl[0] * C0;
+      bf16 *uu = u[0], *yy = y[0];
+      add("conv0_gelu", [=](cudaStream_t s) { return launch_gelu_fwd(uu, yy, ne, s); });
+    }
+    for (int l = 1; l < NC; ++l) {
+      const int Cin = c.conv_dim[l - 1], Cout = c.conv_dim[l], kw = c.conv_kernel[l], st = c.conv_stride[l];
+      const int Tin = Tl[l - 1], Tout = Tl[l];
+      if ((st * Cin) % 64) return "conv layer " + std::to_string(l) + ": stride * in_channels must be a multiple of 64";
+      GemmProblem p;
+      p.a = y[l - 1]; p.a_cols = (long long)st * Cin; p.a_rows = (Tin + st - 1) / st; p.a_batches = n;
+      p.a_row_stride = (long long)st * Cin; p.a_batch_stride = (long long)Tin * Cin;
+      p.a_kb_per_row = st * Cin / 64; p.a_g_col = 0;
+      p.w = h->conv_w[l]; p.M = Tout; p.N = Cout; p.K = kw * Cin; p.Bz = n; p.G = 1;
+      p.epi.act = ACT_NONE;
+      p.epi.out = u[l]; p.epi.ldb = (long long)Tout * Cout; p.epi.ldm = Cout;
+      W2S_TRY(add_gemm("conv" + std::to_string(l), p));
+      const long long ne = (long long)n * Tout * Cout;
+      bf16 *uu = u[l], *yy = y[l];
+      add("conv" + std::to_string(l) + "_gelu", [=](cudaStream_t s) { return launch_gelu_fwd(uu, yy, ne, s); });
+    }
+    {
+      bf16* y6 = y[NC - 1];
+      const float *g = h->fp_ln_g, *b = h->fp_ln_b;
+      const float eps = c.layer_norm_eps;
+      add("featproj_ln", [=](cudaStream_t s) { return launch_layernorm(y6, 0, rows, Cl, g, b, eps, ACT_NONE, fpn, nullptr, s); });
+      GemmProblem p = PlanBuilder::plain(fpn, rows, Cl, h->fp_w, H);
+      p.epi.bias = h->fp_b; p.epi.out = h0;
+      W2S_TRY(add_gemm("featproj", p));
+    }
+    {
+      add("pos_pad", [=](cudaStream_t s) { return launch_pos_pad(h0, nn, T, H, G, kp, hp, s, kp / 2); });
+      EpiParams e;
+      e.bias = h->pos_b; e.act = ACT_NONE; e.out = upos; e.out_fp32 = 0;
+      e.ldg = cpg; e.ldb = (long long)T * H; e.ldm = H;
+      if (!posconv_supported(H, G, kp)) return "gradient path: positional conv shape not supported by the tcgen05 kernel";
+      PosConvPlan* pc = nullptr;
+      W2S_TRY(posconv_prepare(hp, h->pos_w, n, T, H, G, kp, e, h->num_sms, &pc));
+      plan->posconv.push_back(pc);
+      add("pos_conv", [=](cudaStream_t s) { return posconv_launch(pc, s); });
+      add("pos_add", [=](cudaStream_t s) { return launch_add_gelu(h0, upos, pre0, rows * H, s); });
+      const float *g = h->enc_ln_g, *b = h->enc_ln_b;
+      const float eps = c.layer_norm_eps;
+      add("encoder_ln", [=](cudaStream_t s) { return launch_layernorm(pre0, 1, rows, H, g, b, eps, ACT_NONE, hb, nullptr, s); });
+    }
+    AttnParams ap{};
+    ap.ctx = ctx; ap.B = n; ap.T = T; ap.Tp = (T + 63) / 64 * 64; ap.H = H;
+    ap.heads = c.num_attention_heads; ap.hd = 64;
+    ap.ld = 3 * H; ap.q_off = 0; ap.qv_off = 0; ap.k_off = H; ap.v_off = 2 * H;
+    ap.scale = 0.125f;
+    const float eps = c.layer_norm_eps;
+    for (int l = 0; l < NL; ++l) {
+      const LayerW& w = h->layers[l];
+      const GradLayerBuf B = lb[l];
+      const std::string ls = "L" + std::to_string(l) + ".";
+      {
+        GemmProblem p = PlanBuilder::plain(hb, rows, H, w.wqkv, 3 * H);
+        p.epi.bias = w.bqkv; p.epi.out = B.qkv;
+        W2S_TRY(add_gemm(ls + "qkv", p));
+      }
+      {
+        AttnParams lp = ap;
+        lp.qkv = B.qkv;
+        AttnFaPlan* afl = nullptr;
+        W2S_TRY(attention_fa_prepare(lp, h->num_sms, &afl));
+        plan->attn_fa.push_back(afl);
+        add(ls + "attention", [=](cudaStream_t s) { return attention_fa_launch(afl, s); });
+      }
+      {
+        GemmProblem p = PlanBuilder::plain(ctx, rows, H, w.wo, H);
+        p.epi.bias = w.bo; p.epi.residual = hb; p.epi.res_fp32 = 0;
+        p.epi.out = B.s1; p.epi.out_fp32 = 1;
+        W2S_TRY(add_gemm(ls + "out_proj", p));
+      }
+      {
+        const float *g = w.ln1_g, *b = w.ln1_b;
+        const float* in = B.s1;
+        add(ls + "ln1", [=](cudaStream_t s) { return launch_layernorm(in, 1, rows, H, g, b, eps, ACT_NONE, h1, nullptr, s); });
+      }
+      {
+        GemmProblem p = PlanBuilder::plain(h1, rows, H, w.w1, I);
+        p.epi.bias = w.b1; p.epi.act = ACT_NONE; p.epi.out = B.u;
+        W2S_TRY(add_gemm(ls + "ffn1", p));
+        bf16* uu = B.u;
+        add(ls + "ffn_gelu", [=](cudaStream_t s) { return launch_gelu_fwd(uu, ffn, rows * I, s); });
+      }
+      {
+        GemmProblem p = PlanBuilder::plain(ffn, rows, I, w.w2, H);
+        p.epi.bias = w.b2; p.epi.residual = h1; p.epi.res_fp32 = 0;
+        p.epi.out = B.s2; p.epi.out_fp32 = 1;
+        W2S_TRY(add_gemm(ls + "ffn2", p));
+      }
+      {
+        const float *g = w.ln2_g, *b = w.ln2_b;
+        const float* in = B.s2;
+        add(ls + "ln2", [=](cudaStream_t s) { return launch_layernorm(in, 1, rows, H, g, b, eps, ACT_NONE, hb, nullptr, s); });
+      }
+    }
+    {
+      GemmProblem p = PlanBuilder::plain(hb, rows, H, h->head_w, h->head_ldl);
+      p.epi.bias = h->head_b; p.epi.out = plan->logits; p.epi.out_fp32 = 1;
+      W2S_TRY(add_gemm("lm_head", p));
+    }
+
+    // ================================ backward to the waveform ===================================================
+    {
+      const float* lg = plan->logits;
+      const int ldl = h->head_ldl, V = c.vocab_size;
+      const bf16* hw = h->head_w;
+      const int* fr = plan->frames;
+      add("head_bwd", [=](cudaStream_t s) { return launch_head_bwd(lg, ldl, V, hw, nn, T, H, fr, dA, hh->grad_out_val, s); });
+      W2S_TRY(snap("layer" + std::to_string(NL), dA, sizeof(float) * rows * H));
+    }
+    for (int l = NL - 1; l >= 0; --l) {
+      const LayerW& w = h->layers[l];
+      const GradW& gw = h->gradw[l];
+      const GradLayerBuf B = lb[l];
+      const std::string ls = "B" + std::to_string(l) + ".";
+      {
+        const float* g = w.ln2_g;
+        const float* x = B.s2;
+        add(ls + "ln2_bwd", [=](cudaStream_t s) { return launch_ln_bwd(dA, x, 1, rows, H, g, eps, nullptr, dS, dS16, s); });
+      }
+      {
+        GemmProblem p = PlanBuilder::plain(dS16, rows, H, gw.w2T, I);
+        p.epi.out = dF;
+        W2S_TRY(add_gemm(ls + "ffn2_bwd", p));
+        const bf16* uu = B.u;
+        add(ls + "gelu_bwd", [=](cudaStream_t s) { return launch_gelu_bwd(uu, dF, rows * I, s); });
+      }
+      {
+        GemmProblem p = PlanBuilder::plain(dF, rows, I, gw.w1T, H);
+        p.epi.residual = dS; p.epi.res_fp32 = 1; p.epi.out = dA; p.epi.out_fp32 = 1;
+        W2S_TRY(add_gemm(ls + "ffn1_bwd", p));
+      }
+      {
+        const float* g = w.ln1_g;
+        const float* x = B.s1;
+        add(ls + "ln1_bwd", [=](cudaStream_t s) { return launch_ln_bwd(dA, x, 1, rows, H, g, eps, nullptr, dS, dS16, s); });
+      }
+      {
+        GemmProblem p = PlanBuilder::plain(dS16, rows, H, gw.woT, H);
+        p.epi.out = dC;
+        W2S_TRY(add_gemm(ls + "out_proj_bwd", p));
+      }
+      {
+        const bf16* q = B.qkv;
+        const int heads = c.num_attention_heads;
+        add(ls + "attention_bwd", [=](cudaStream_t s) { return launch_attn_bwd(q, dC, nn, T, H, heads, 0.125f, dQKV, attn_stats, s); });
+      }
+      {
+        GemmProblem p = PlanBuilder::plain(dQKV, rows, 3 * H, gw.wqkvT, H);
+        p.epi.residual = dS; p.epi.res_fp32 = 1; p.epi.out = dA; p.epi.out_fp32 = 1;
+        W2S_TRY(add_gemm(ls + "qkv_bwd", p));
+      }
+      W2S_TRY(snap("layer" + std::to_string(l), dA, sizeof(float) * rows * H));
+    }
+    {
+      // encoder input: hb0 = LN(pre0), pre0 = h0 + gelu(pos_conv(h0))
+      const float* g = h->enc_ln_g;
+      add("encoder_ln_bwd", [=](cudaStream_t s) { return launch_ln_bwd(dA, pre0, 1, rows, H, g, eps, nullptr, dS, nullptr, s); });
+      add("pos_gelu_bwd", [=](cudaStream_t s) { return launch_grad_cast(dS, upos, dS16, rows * H, s); });
+      add("pos_pad_bwd", [=](cudaStream_t s) { return launch_pos_pad(dS16, nn, T, H, G, kp, hp, s, kp / 2 - 1); });
+      EpiParams e;
+      e.act = ACT_NONE; e.residual = dS; e.res_fp32 = 1; e.out = dA; e.out_fp32 = 1;
+      e.ldg = cpg; e.ldb = (long long)T * H; e.ldm = H;
+      PosConvPlan* pc = nullptr;
+      W2S_TRY(posconv_prepare(hp, h->pos_w_bwd, n, T, H, G, kp, e, h->num_sms, &pc));
+      plan->posconv.push_back(pc);
+      add("pos_conv_bwd", [=](cudaStream_t s) { return posconv_launch(pc, s); });
+      W2S_TRY(snap("h0", dA, sizeof(float) * rows * H));
+      add("h0_cast", [=](cudaStream_t s) { return launch_grad_cast(dA, nullptr, dS16, rows * H, s); });
+      GemmProblem p = PlanBuilder::plain(dS16, rows, H, h->fp_wT, Cl);
+      p.epi.out = dFp; p.epi.out_fp32 = 1;
+      W2S_TRY(add_gemm("featproj_bwd", p));
+      const float* gl = h->fp_ln_g;
+      const bf16* y6 = y[NC - 1];
+      bf16* d6 = plan->D[(NC - 1) & 1];
+      add("featproj_ln_bwd", [=](cudaStream_t s) { return launch_ln_bwd(dFp, y6, 0, rows, Cl, gl, eps, nullptr, nullptr, d6, s); });
+      W2S_TRY(snap("conv" + std::to_string(NC - 1), d6, sizeof(bf16) * rows * Cl));
+      const bf16* u6 = u[NC - 1];
+      add("conv" + std::to_string(NC - 1) + "_gelu_bwd", [=](cudaStream_t s) { return launch_gelu_bwd(u6, d6, rows * Cl, s); });
+    }
+    for (int l = NC - 1; l >= 1; --l) {
+      // D[l & 1] holds d u_l [n, T_l, C_l]; contraction with the transposed filters, then gather to d u_(l-1)
+      const int Cin = c.conv_dim[l - 1], Cout = c.conv_dim[l], kw = c.conv_kernel[l], st = c.conv_stride[l];
+      const int Tin = Tl[l - 1], Tout = Tl[l];
+      bf16* dul = plan->D[l & 1];
+      bf16* dprev = plan->D[(l - 1) & 1];
+      GemmProblem p = PlanBuilder::plain(dul, (long long)n * Tout, Cout, h->conv_wT[l], kw * Cin);
+      p.epi.out = dcol;
+      W2S_TRY(add_gemm("conv" + std::to_string(l) + "_bwd", p));
+      const bf16* up = u[l - 1];
+      add("conv" + std::to_string(l) + "_gather",
+          [=](cudaStream_t s) { return launch_conv_gather(dcol, nn, Tin, Tout, Cin, kw, st, up, dprev, s); });
+      W2S_TRY(snap("convu" + std::to_string(l - 1), dprev, sizeof(bf16) * (size_t)n * Tin * Cin));
+    }
+    {
+      const bf16* du0 = plan->D[0];
+      const bf16* u0 = u[0];
+      const int T0 = Tl[0], kw = c.conv_kernel[0], st = c.conv_stride[0];
+      const float *w0 = h->conv0_w, *gam = h->norm0_g, *bet = h->norm0_b;
+      const long long LL = L;
+      add("conv0_bwd", [=](cudaStream_t s) {
+        return launch_conv0_bwd(du0, u0, nn, LL, T0, C0, kw, st, w0, gn_a, gam, bet, m12, gtap, hh->grad_out, LL, s);
+      });
+    }
+    return "";
+  }
+};
+
+std::string get_grad_plan(w2s_handle* h, int n, long long L, GradPlan** out) {
+  if (h->grad_L != L || h->grad_debug_built != h->grad_debug) {
+    cudaDeviceSynchronize();
+    h->grad_plans.clear();
+    h->grad_L = L;
+    h->grad_debug_built = h->grad_debug;
+  }
+  auto it = h->grad_plans.find(n);
+  if (it != h->grad_plans.end()) {
+    *out = it->second.get();
+    return "";
+  }
+  std::shared_ptr<GradPlan> pl(new GradPlan());
+  pl->n = n;
+  GradBuilder b{h, pl.get(), n, L};
+  b.debug = h->grad_debug;
+  W2S_TRY(b.build());
+  *out = pl.get();
+  h->grad_plans[n] = pl;
+  return "";
+}
+
+// rows in tiles of `tile`; per tile: argument block, target frames, forward + backward
+std::string run_grad(w2s_handle* h, const float* x, long long ld, long long L, int64_t n, const int32_t* frames_host,
+                     float* grad, float* out_val, cudaStream_t s) {
+  W2S_TRY(grad_supported(h));
+  W2S_TRY(grad_prepare_weights(h));
+  const int64_t T = num_frames(h->cfg, L, nullptr);
+  for (int64_t i = 0; i < n; ++i)
+    if (frames_host[i] < 0 || frames_host[i] >= T)
+      return "target frame " + std::to_string(frames_host[i]) + " outside the clip's " + std::to_string(T) + " frames";
+  const int tile = h->grad_tile;
+  h->grad_frames_host.assign(frames_host, frames_host + n);
+  for (int64_t k0 = 0; k0 < n; k0 += tile) {
+    const int nt = (int)((n - k0) < tile ? (n - k0) : tile);
+    GradPlan* pl = nullptr;
+    W2S_TRY(get_grad_plan(h, nt, L, &pl));
+    DynArgs d{};
+    d.x = x + k0 * ld; d.ld = ld;
+    set_dyn_kernel<<<1, 1, 0, s>>>(h->dyn_dev, d);
+    W2S_CUDA_OK(cudaMemcpyAsync(pl->frames, h->grad_frames_host.data() + k0, sizeof(int) * nt, cudaMemcpyHostToDevice, s));
+    h->grad_out = grad + k0 * L;
+    h->grad_out_val = out_val ? out_val + k0 : nullptr;
+    for (const Step& st : pl->steps) {
+      std::string e = st.run(s);
+      if (!e.empty()) return st.name + ": " + e;
+    }
+    h->launches += (long long)pl->steps.size() + 1;
+  }
+  return "";
+}

@@ -49,6 +49,7 @@ struct Conv0Params {
   const float* ln_gram;  // [kw][kw]   mean_c w[c][j] w[c][j']
   const float* ln_wb;    // [kw]       mean_c w[c][j] b[c]
   float ln_bmean, ln_b2mean;
+  int pre_act;           // 1: store the normalised pre-activation (no GELU) -- forward of the gradient path
   const __nv_bfloat16* ln_wb48;  // [C][48] (optional) B operand of conv0_ln_mma_kernel: filters, bias and affine terms
                                  // as bf16 hi/lo rows
   __nv_bfloat16* out;    // [n, T0, C] channels-last
@@ -69,8 +70,9 @@ std::string launch_layernorm(const void* in, int in_fp32, long long rows, int H,
                              cudaStream_t s, const __nv_bfloat16* residual = nullptr);
 
 // ---- positional-conv input staging: [B, T, H] -> zero-padded [B, T + kpos, G*64] ------------------------
+// `left` = zero rows in front of frame 0 (default kpos / 2, HF's padding; the backward-data conv uses kpos / 2 - 1)
 std::string launch_pos_pad(const __nv_bfloat16* h, int B, int T, int H, int G, int kpos, __nv_bfloat16* out,
-                           cudaStream_t s);
+                           cudaStream_t s, int left = -1);
 
 // ---- K4: positional conv on tcgen05 with a resident input window (posconv.cu) --------------------------------
 struct EpiParams;
@@ -137,6 +139,25 @@ std::string launch_head_reduce(const float* logits, const HeadParams& p, cudaStr
 std::string launch_wls(const uint32_t* zbits, int zwords, const double* w, const float* y, long long K, int M,
                        int D, const double* fx, const double* fnull, double* phi, int32_t* status,
                        double* work /* 2 * ((M-1)*(M-1) + (M-1)*D) doubles */, cudaStream_t s);
+
+// ---- backward (input-gradient) kernels of the expected-gradients path (grad.cu) -------------------------------------
+std::string launch_gelu_fwd(const __nv_bfloat16* u, __nv_bfloat16* y, long long n, cudaStream_t s);
+std::string launch_gelu_bwd(const __nv_bfloat16* u, __nv_bfloat16* d, long long n, cudaStream_t s);
+std::string launch_add_gelu(const __nv_bfloat16* h0, const __nv_bfloat16* up, float* out, long long n, cudaStream_t s);
+std::string launch_grad_cast(const float* g, const __nv_bfloat16* u, __nv_bfloat16* out, long long n, cudaStream_t s);
+std::string launch_ln_bwd(const float* dy, const void* x, int x_fp32, long long rows, int H, const float* gamma, float eps,
+                          const float* add, float* dx, __nv_bfloat16* dx16, cudaStream_t s);
+std::string launch_head_bwd(const float* logits, int ldl, int V, const __nv_bfloat16* w_head, int n, int T, int H,
+                            const int* frames, float* dh, float* out_val, cudaStream_t s);
+std::string launch_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx, int B, int T, int H, int heads, float scale,
+                            __nv_bfloat16* dqkv, float* stats, cudaStream_t s);
+std::string launch_conv_gather(const __nv_bfloat16* dcol, int n, int T_in, int T_out, int C, int kw, int stride,
+                               const __nv_bfloat16* u_prev, __nv_bfloat16* out, cudaStream_t s);
+std::string launch_conv0_bwd(const __nv_bfloat16* du, const __nv_bfloat16* u, int n, long long L, int T0, int C, int kw, int stride,
+                             const float* w, const float* gn_a, const float* gamma, const float* beta, float* m12, float* g,
+                             float* dx, long long ld, cudaStream_t s);
+std::string launch_transpose_bf16(const __nv_bfloat16* src, __nv_bfloat16* dst, int R, int C, cudaStream_t s);
+std::string launch_repack_posconv_bwd(const float* src, __nv_bfloat16* dst, int H, int G, int kw, cudaStream_t s);
 
 // ---- weight re-layout (run once at create) -------------------------------------------------------------------
 // y[i] += x[i]
