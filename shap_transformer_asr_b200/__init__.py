@@ -12,3 +12,4 @@ from .engine import Engine, debug_gemm  # noqa: F401
 from .metrics import eta_raw, greedy_ctc_decode, wer  # noqa: F401
 from .sweep import add_noise, explain_test_set, make_test_set  # noqa: F401
 from .modelzoo import build_random_init_model  # noqa: F401
+from .expected_gradients import ExpectedGradientsExplainer, make_background  # noqa: F401

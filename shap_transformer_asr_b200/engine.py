@@ -184,6 +184,33 @@ class Engine:
                                                 self._stream()), "w2s_eval_waveforms")
         return out
 
+    # -- input gradients (expected-gradients path) ----------------------------------------------------------
+    def grad_waveforms(self, x: torch.Tensor, frames):
+        """x: float32 device tensor [n, L]; frames: one output frame per row -> (grad [n, L] float32 device tensor of
+        d out[r] / d x[r], out [n]) with out[r] = max_v logits[r, frames[r], v] -- the scalar the reference's
+        GradientExplainer differentiates through ModelWrapper (shap_calculation.py:50, :133, :162)."""
+        if x.dim() != 2 or x.stride(1) != 1 or x.dtype != torch.float32 or not x.is_cuda:
+            raise ValueError("expected a float32 CUDA tensor [n, L] with contiguous rows")
+        n, L = x.shape
+        f = np.ascontiguousarray(np.broadcast_to(np.asarray(frames, dtype=np.int32), (n,)))
+        grad = torch.empty((n, L), dtype=torch.float32, device=self.device)
+        out = torch.empty((n,), dtype=torch.float32, device=self.device)
+        self._check(self.lib.w2s_grad_waveforms(self._h, x.data_ptr(), n, L, x.stride(0),
+                                                f.ctypes.data_as(C.POINTER(C.c_int32)), grad.data_ptr(), out.data_ptr(),
+                                                self._stream()), "w2s_grad_waveforms")
+        return grad, out
+
+    def grad_debug(self, on: bool = True):
+        self.lib.w2s_grad_debug(self._h, int(on))
+
+    def grad_peek(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
+        """Snapshot of an intermediate gradient of the last grad_waveforms call (tests; needs grad_debug(True))."""
+        out = torch.empty(shape, dtype=dtype, device=self.device)
+        got = self.lib.w2s_grad_peek(self._h, name.encode(), out.data_ptr(), out.numel() * out.element_size(), self._stream())
+        if got != out.numel() * out.element_size():
+            raise RuntimeError(f"w2s_grad_peek('{name}'): got {got} bytes for a buffer of {out.numel() * out.element_size()}")
+        return out
+
     def mask(self, zbits: torch.Tensor) -> torch.Tensor:
         K = zbits.shape[0]
         out = torch.empty((K, self.num_samples), dtype=torch.float32, device=self.device)

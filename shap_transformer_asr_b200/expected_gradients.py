@@ -1,0 +1,64 @@
+"""Expected gradients around the device input-gradient path -- the reference's production explainer.
+
+``shap_calculation.py:125-162`` builds ``shap.GradientExplainer(wrapped_model, background, batch_size=1)`` over five
+near-zero background clips and calls ``.shap_values(input_values)``; shap then loops over every output index (all T'
+frames: ``ranked_outputs=None``) and ``nsamples = 200`` random (background, alpha) pairs, one forward + backward pass at
+batch 1 each (traceback in ``feasability_tests/conformer_test.ipynb:95``): 114 600 passes for the recorded 11.5 s clip.
+
+This module restates that estimator (shap is not installable here: algorithm FROM MEMORY of shap's
+``_PyTorchGradient.shap_values``, as SURVEY.md Appendix A does for KernelExplainer -- parity with shap itself is
+UNPINNED; what is pinned is the gradient, against torch autograd on the ``transformers`` model) and batches the passes:
+
+    phi[:, j] = mean_s  d out_j / d x (x_s) * (x - bg_s),   x_s = bg_s + alpha_s (x - bg_s),  alpha_s ~ U(0, 1)
+
+with the per-sample gradient rows evaluated by ``Engine.grad_waveforms`` in tiles.  Samples are drawn once per output
+index from a seeded ``numpy`` generator, as shap reseeds per explained output.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+
+def make_background(num_samples: int, num_background: int = 5, seed: Optional[int] = None) -> np.ndarray:
+    """zeros + 0.01 * randn, the reference's background set (shap_calculation.py:125-127; unseeded there)."""
+    rng = np.random.default_rng(seed)
+    return (0.01 * rng.standard_normal((num_background, num_samples))).astype(np.float32)
+
+
+class ExpectedGradientsExplainer:
+    """phi[L, T'] for the ModelWrapper outputs (max logit per frame) of one clip."""
+
+    def __init__(self, engine, background: np.ndarray, nsamples: int = 200, seed: int = 0, batch: int = 64):
+        self.engine = engine
+        self.background = np.ascontiguousarray(background, dtype=np.float32)
+        self.nsamples = int(nsamples)
+        self.seed = seed
+        self.batch = int(batch)
+
+    def shap_values(self, x, frames=None) -> np.ndarray:
+        """x: normalised clip [L] -> attributions [1, L, D] (the reference's on-disk layout, D = T' when ``frames`` is
+        None: every output frame, as ``ranked_outputs=None``)."""
+        eng = self.engine
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float32).reshape(-1))
+        L = x.size
+        T = eng.num_frames(L)
+        frames = np.arange(T, dtype=np.int32) if frames is None else np.asarray(frames, dtype=np.int32)
+        bg = torch.from_numpy(self.background).to(eng.device)
+        xt = torch.from_numpy(x).to(eng.device)
+        phi = torch.zeros((len(frames), L), dtype=torch.float64, device=eng.device)
+        for d, j in enumerate(frames):
+            rng = np.random.default_rng([self.seed, int(j)])
+            rind = torch.from_numpy(rng.integers(0, bg.shape[0], self.nsamples)).to(eng.device)
+            alpha = torch.from_numpy(rng.uniform(size=self.nsamples).astype(np.float32)).to(eng.device)
+            for s0 in range(0, self.nsamples, self.batch):
+                b = bg[rind[s0:s0 + self.batch]]
+                a = alpha[s0:s0 + self.batch, None]
+                delta = xt[None] - b
+                xs = (b + a * delta).contiguous()
+                g, _ = eng.grad_waveforms(xs, int(j))
+                phi[d] += (g.double() * delta.double()).sum(0)
+        phi /= self.nsamples
+        return phi.t().contiguous()[None].cpu().numpy()

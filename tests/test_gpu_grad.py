@@ -1,0 +1,167 @@
+"""GPU: the input-gradient path (expected gradients, the reference's production explainer: shap_calculation.py:125-162)
+through the C ABI against torch autograd on the `transformers` model -- stage by stage, then end to end.
+
+Tolerance: gradients travel through ~60 bf16-rounded stages (bf16 operands, fp32 accumulation, fp32 LayerNorm / softmax
+arithmetic), so they are compared as max |g_gpu - g_ref| <= GRAD_TOL * max |g_ref| per row batch, plus a cosine similarity.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import VARIANTS, build_model
+from shap_transformer_asr_b200.config import MODELS
+
+pytestmark = pytest.mark.gpu
+
+GRAD_TOL = 0.06
+
+
+@pytest.fixture(scope="module")
+def P():
+    import shap_transformer_asr_b200 as pkg
+    assert torch.cuda.is_available()
+    return pkg
+
+
+def reference_grads(model, x, frames):
+    """torch autograd on the transformers model: d max_v logits[r, frames[r], v] / d (x and the intermediate activations)."""
+    grabs, hooks = {}, []
+
+    def keep(name):
+        def hook(mod, inp, out):
+            t = out[0] if isinstance(out, tuple) else out
+            t.retain_grad()
+            grabs[name] = t
+        return hook
+
+    w = model.wav2vec2
+    NL = len(w.encoder.layers)
+    hooks.append(w.encoder.layer_norm.register_forward_hook(keep("layer0")))
+    for l, layer in enumerate(w.encoder.layers):
+        hooks.append(layer.register_forward_hook(keep(f"layer{l + 1}")))
+    hooks.append(w.feature_projection.register_forward_hook(keep("h0")))
+    convs = w.feature_extractor.conv_layers
+    hooks.append(convs[0].layer_norm.register_forward_hook(keep("convu0")))
+    for l in range(1, len(convs)):
+        hooks.append(convs[l].conv.register_forward_hook(keep(f"convu{l}")))
+    hooks.append(convs[-1].register_forward_hook(keep(f"conv{len(convs) - 1}")))
+    xt = torch.tensor(x, requires_grad=True)
+    logits = model(xt).logits
+    out = logits.max(-1).values[torch.arange(len(x)), torch.as_tensor(frames, dtype=torch.long)]
+    out.sum().backward()
+    for h in hooks:
+        h.remove()
+    g = {k: v.grad.detach() for k, v in grabs.items()}
+    return xt.grad.detach().numpy(), g, out.detach().numpy(), NL
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def cosine(a, b):
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30))
+
+
+def test_gradient_stages_match_autograd_tiny(P):
+    """Every stage of the backward pass against autograd (tiny model): localises a wrong kernel to its stage."""
+    cfg = VARIANTS["tiny_group"]
+    model = build_model(cfg)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((3, 6000)).astype(np.float32)
+    T = cfg.num_frames(6000)
+    frames = np.array([0, 5, T - 1], dtype=np.int32)
+    gx, g, out, NL = reference_grads(model, x, frames)
+    eng = P.Engine(model, cfg, max_batch=4)
+    eng.grad_debug(True)
+    grad, val = eng.grad_waveforms(torch.from_numpy(x).cuda(), frames)
+    torch.cuda.synchronize()
+    assert np.abs(val.cpu().numpy() - out).max() < 0.025 * np.abs(out).max() + 1e-3
+    H = cfg.hidden_size
+    report = []
+    for l in range(NL, -1, -1):
+        mine = eng.grad_peek(f"layer{l}", (3, T, H)).cpu().numpy()
+        report.append((f"layer{l}", rel(mine, g[f"layer{l}"].numpy())))
+    report.append(("h0", rel(eng.grad_peek("h0", (3, T, H)).cpu().numpy(), g["h0"].numpy())))
+    lens = cfg.conv_lengths(6000)
+    NC = len(lens)
+    mine = eng.grad_peek(f"conv{NC - 1}", (3, lens[-1], cfg.conv_dim[-1]), torch.bfloat16).float().cpu().numpy()
+    report.append((f"conv{NC - 1}", rel(mine, g[f"conv{NC - 1}"].numpy().transpose(0, 2, 1))))
+    for l in range(NC - 2, -1, -1):
+        mine = eng.grad_peek(f"convu{l}", (3, lens[l], cfg.conv_dim[l]), torch.bfloat16).float().cpu().numpy()
+        report.append((f"convu{l}", rel(mine, g[f"convu{l}"].numpy().transpose(0, 2, 1))))
+    report.append(("x", rel(grad.cpu().numpy(), gx)))
+    print("gradient stages (max rel err vs autograd): " + "; ".join(f"{k} {v:.2e}" for k, v in report))
+    worst = max(v for _, v in report)
+    assert worst < GRAD_TOL, report
+    assert cosine(grad.cpu().numpy(), gx) > 0.999
+    eng.close()
+
+
+@pytest.mark.parametrize("name,n,L", [("tiny_group", 35, 9000), ("wav2vec2-base", 32, 16000)])
+def test_input_gradients_match_autograd_at_batch_32(P, name, n, L):
+    """d (max logit of frame j) / d waveform for >= 32 rows with different target frames (one ragged tile for the tiny
+    model: 32 + 3) against torch autograd on the transformers model."""
+    cfg = VARIANTS[name] if name in VARIANTS else MODELS[name]
+    model = build_model(cfg)
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((n, L)).astype(np.float32)
+    T = cfg.num_frames(L)
+    frames = rng.integers(0, T, size=n).astype(np.int32)
+    gx, _, out, _ = reference_grads(model, x, frames)
+    eng = P.Engine(model, cfg, max_batch=4)
+    grad, val = eng.grad_waveforms(torch.from_numpy(x).cuda(), frames)
+    grad = grad.cpu().numpy()
+    e, c = rel(grad, gx), cosine(grad, gx)
+    per_row = [cosine(grad[i], gx[i]) for i in range(n)]
+    print(f"{name} n={n} L={L}: input-gradient max rel err {e:.3e}; cosine {c:.5f}; worst row cosine {min(per_row):.5f}")
+    assert np.abs(val.cpu().numpy() - out).max() < 0.025 * np.abs(out).max() + 1e-3
+    assert e < GRAD_TOL and min(per_row) > 0.995
+    # the same rows, one at a time, give the same gradients (no dependence on the position in the batch)
+    g1, _ = eng.grad_waveforms(torch.from_numpy(x[5:6]).cuda(), frames[5:6])
+    assert np.abs(g1.cpu().numpy()[0] - grad[5]).max() <= 1e-6 * np.abs(grad[5]).max() + 1e-12
+    eng.close()
+
+
+def test_expected_gradients_explainer_properties(P):
+    """ExpectedGradientsExplainer on the tiny model: layout [1, L, D] (shap_calculation.py:200-210), agreement with the
+    same estimator evaluated with autograd gradients on the same (background, alpha) draws, and approximate
+    completeness (sum of attributions ~ f(x) - E f(background))."""
+    cfg = VARIANTS["tiny_group"]
+    model = build_model(cfg)
+    L = 4000
+    x = P.synthetic_clip(L)
+    bg = P.make_background(L, 5, seed=1)
+    eng = P.Engine(model, cfg, max_batch=8)
+    frames = np.array([2, 7], dtype=np.int32)
+    ex = P.ExpectedGradientsExplainer(eng, bg, nsamples=64, seed=3, batch=32)
+    phi = ex.shap_values(x, frames)
+    assert phi.shape == (1, L, 2)
+    # reference: identical draws, autograd gradients
+    ref = np.zeros((L, 2))
+    for d, j in enumerate(frames):
+        rng = np.random.default_rng([3, int(j)])
+        rind = rng.integers(0, 5, 64)
+        alpha = rng.uniform(size=64).astype(np.float32)
+        xs = bg[rind] + alpha[:, None] * (x[None] - bg[rind])
+        gx, _, _, _ = reference_grads(model, xs.astype(np.float32), np.full(64, j, np.int32))
+        ref[:, d] = (gx.astype(np.float64) * (x[None] - bg[rind])).mean(0)
+    e = rel(phi[0], ref)
+    print(f"expected gradients (64 samples, 2 outputs): max rel err vs autograd estimator {e:.3e}")
+    assert e < GRAD_TOL
+    with torch.no_grad():
+        fx = model(torch.from_numpy(x)[None]).logits.max(-1).values[0, frames].numpy()
+        fb = model(torch.from_numpy(bg)).logits.max(-1).values[:, frames].mean(0).numpy()
+    gap = np.abs(phi[0].sum(0) - (fx - fb)) / (np.abs(fx - fb) + 1e-6)
+    print(f"completeness gap (64 samples): {gap}")
+    eng.close()
+
+
+def test_gradient_path_rejects_unbuilt_configurations(P):
+    cfg = VARIANTS["tiny_layer_stable"]
+    eng = P.Engine(build_model(cfg), cfg, max_batch=2)
+    with pytest.raises(RuntimeError, match="gradient path"):
+        eng.grad_waveforms(torch.zeros((1, 4000), device="cuda"), [0])
+    eng.close()
