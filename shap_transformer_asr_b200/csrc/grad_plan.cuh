@@ -82,8 +82,6 @@ struct GradBuilder {
   GradPlan* plan;
   int n;
   long long L;
-  std::vector<int> Tl;
-  int T = 0;
   bool debug = false;
 
   template <typename TT>
@@ -115,7 +113,10 @@ struct GradBuilder {
     const w2s_config& c = h->cfg;
     const int H = c.hidden_size, I = c.intermediate_size, NL = c.num_hidden_layers, NC = c.num_conv_layers;
     const int C0 = c.conv_dim[0];
-    T = (int)num_frames(c, L, &Tl);
+    // NB: every value a step lambda uses must be a LOCAL of this function (captured by value): the builder itself is gone
+    // by the time the steps run
+    std::vector<int> Tl;
+    const int T = (int)num_frames(c, L, &Tl);
     if (T <= 0) return "clip shorter than the conv receptive field";
     const long long rows = (long long)n * T;
     const int nn = n;
@@ -191,6 +192,7 @@ struct GradBuilder {
       const long long ne = (long long)n * Tl[0] * C0;
       bf16 *uu = u[0], *yy = y[0];
       add("conv0_gelu", [=](cudaStream_t s) { return launch_gelu_fwd(uu, yy, ne, s); });
+      W2S_TRY(snap("f.convu0", u[0], sizeof(bf16) * (size_t)ne));
     }
     for (int l = 1; l < NC; ++l) {
       const int Cin = c.conv_dim[l - 1], Cout = c.conv_dim[l], kw = c.conv_kernel[l], st = c.conv_stride[l];
@@ -207,6 +209,7 @@ struct GradBuilder {
       const long long ne = (long long)n * Tout * Cout;
       bf16 *uu = u[l], *yy = y[l];
       add("conv" + std::to_string(l) + "_gelu", [=](cudaStream_t s) { return launch_gelu_fwd(uu, yy, ne, s); });
+      W2S_TRY(snap("f.convu" + std::to_string(l), u[l], sizeof(bf16) * (size_t)ne));
     }
     {
       bf16* y6 = y[NC - 1];
@@ -216,6 +219,8 @@ struct GradBuilder {
       GemmProblem p = PlanBuilder::plain(fpn, rows, Cl, h->fp_w, H);
       p.epi.bias = h->fp_b; p.epi.out = h0;
       W2S_TRY(add_gemm("featproj", p));
+      W2S_TRY(snap("f.conv" + std::to_string(NC - 1), y6, sizeof(bf16) * (size_t)rows * Cl));
+      W2S_TRY(snap("f.h0", h0, sizeof(bf16) * (size_t)rows * H));
     }
     {
       add("pos_pad", [=](cudaStream_t s) { return launch_pos_pad(h0, nn, T, H, G, kp, hp, s, kp / 2); });
@@ -231,6 +236,7 @@ struct GradBuilder {
       const float *g = h->enc_ln_g, *b = h->enc_ln_b;
       const float eps = c.layer_norm_eps;
       add("encoder_ln", [=](cudaStream_t s) { return launch_layernorm(pre0, 1, rows, H, g, b, eps, ACT_NONE, hb, nullptr, s); });
+      W2S_TRY(snap("f.layer0", hb, sizeof(bf16) * (size_t)rows * H));
     }
     AttnParams ap{};
     ap.ctx = ctx; ap.B = n; ap.T = T; ap.Tp = (T + 63) / 64 * 64; ap.H = H;
@@ -284,11 +290,13 @@ struct GradBuilder {
         const float* in = B.s2;
         add(ls + "ln2", [=](cudaStream_t s) { return launch_layernorm(in, 1, rows, H, g, b, eps, ACT_NONE, hb, nullptr, s); });
       }
+      W2S_TRY(snap("f.layer" + std::to_string(l + 1), hb, sizeof(bf16) * (size_t)rows * H));
     }
     {
       GemmProblem p = PlanBuilder::plain(hb, rows, H, h->head_w, h->head_ldl);
       p.epi.bias = h->head_b; p.epi.out = plan->logits; p.epi.out_fp32 = 1;
       W2S_TRY(add_gemm("lm_head", p));
+      W2S_TRY(snap("f.logits", plan->logits, sizeof(float) * (size_t)rows * h->head_ldl));
     }
 
     // ================================ backward to the waveform ===================================================
