@@ -122,8 +122,9 @@ int w2s_eval_waveforms(w2s_handle* h, const float* x_dev, int64_t n, int64_t L, 
  * encoder (wav2vec2-base / -large); other configurations return an error. */
 int w2s_grad_waveforms(w2s_handle* h, const float* x_dev, int64_t n, int64_t L, int64_t ld,
                        const int32_t* frames_host, float* grad_dev, float* out_dev, void* stream);
-/* Test hooks of the gradient path: keep snapshots of the gradient after every encoder layer / conv layer
- * ("layer<l>", "h0", "conv<l>", "convu<l>") and copy one out (returns bytes copied, 0 = unknown name, < 0 = buffer
+/* Test hooks of the gradient path.  `on` bit 0: keep snapshots of the gradient after every encoder layer / conv layer
+ * ("layer<l>", "h0", "conv<l>", "convu<l>", forward activations "f.*"); bit 1: run attention backward on the CUDA-core
+ * cross-check kernels instead of the tensor-core contractions.  w2s_grad_peek copies a snapshot out (returns bytes copied, 0 = unknown name, < 0 = buffer
  * too small by that many bytes). */
 int w2s_grad_debug(w2s_handle* h, int on);
 int64_t w2s_grad_peek(w2s_handle* h, const char* name, void* dst_dev, int64_t max_bytes, void* stream);

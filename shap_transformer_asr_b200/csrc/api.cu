@@ -148,6 +148,7 @@ struct w2s_handle {
   long long grad_L = -1;
   int grad_tile = 32;
   bool grad_debug = false, grad_debug_built = false;
+  bool grad_attn_simt = false;        // cross-check: attention backward on the CUDA-core kernels (w2s_grad_debug bit 1)
   std::vector<int32_t> grad_frames_host;
   float *grad_out = nullptr, *grad_out_val = nullptr;
 
@@ -1131,7 +1132,10 @@ int w2s_grad_waveforms(w2s_handle* h, const float* x_dev, int64_t n, int64_t L, 
 }
 
 int w2s_grad_debug(w2s_handle* h, int on) {
-  h->grad_debug = on != 0;
+  const bool snaps = (on & 1) != 0, simt = (on & 2) != 0;
+  if (simt != h->grad_attn_simt) h->grad_L = -1;   // rebuild the plans
+  h->grad_debug = snaps;
+  h->grad_attn_simt = simt;
   return 0;
 }
 
@@ -1214,7 +1218,13 @@ int64_t w2s_profile_read(w2s_handle* h, char* names, int64_t names_cap, double* 
   std::vector<int64_t> cnt;
   for (auto& r : h->prof) {
     std::string k = r.name;
-    if (k.size() > 1 && k[0] == 'L' && isdigit((unsigned char)k[1])) k = k.substr(k.find('.') + 1);
+    std::string pre;
+    if (k.compare(0, 5, "grad.") == 0) {   // gradient path: "grad.L3.qkv" / "grad.B3.qkv_bwd" -> "grad.qkv" / "grad.qkv_bwd"
+      pre = "grad.";
+      k = k.substr(5);
+    }
+    if (k.size() > 1 && (k[0] == 'L' || k[0] == 'B') && isdigit((unsigned char)k[1])) k = k.substr(k.find('.') + 1);
+    k = pre + k;
     size_t i = 0;
     for (; i < keys.size(); ++i)
       if (keys[i] == k) break;

@@ -112,8 +112,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const int krow = kb / p.a_kb_per_row;
           const int kcol = kb - krow * p.a_kb_per_row;
           const uint32_t sa = tiles + stage * C::STAGE_BYTES;
-          tma_load_3d(sa, &mapA, full_bar(stage), tc.g * p.a_g_col + kcol * 64, tc.m0 + krow, tc.b);
-          tma_load_3d(sa + C::A_BYTES, &mapW, full_bar(stage), kb * 64, tc.n0, tc.g);
+          tma_load_3d(sa, &mapA, full_bar(stage), tc.g * p.a_g_col + kcol * 64, tc.g * p.a_g_row + tc.m0 + krow, tc.b);
+          tma_load_4d(sa + C::A_BYTES, &mapW, full_bar(stage), kb * 64, tc.n0, tc.g, p.w_batched ? tc.b : 0);
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmDev p) {
       const int k = k0 + kk;
       float av = 0.f, wv = 0.f;
       if (k < p.K) {
-        const long long row = (long long)m0 + r + k / rowlen;
+        const long long row = (long long)g * p.a_g_row + m0 + r + k / rowlen;
         const long long col = (long long)g * p.a_g_col + k % rowlen;
         if (row < p.a_rows && col < p.a_cols)
           av = __bfloat162float(p.a[(long long)b * p.a_batch_stride + row * p.a_row_stride + col]);
@@ -336,6 +336,8 @@ std::string gemm_prepare(const GemmProblem& p, int num_sms, GemmLaunch* out) {
   d.num_units = d.units_m * d.tiles_n * p.Bz * p.G;
   d.a_kb_per_row = p.a_kb_per_row;
   d.a_g_col = p.a_g_col;
+  d.a_g_row = p.a_g_row;
+  d.w_batched = p.w_batch_stride != 0;
   d.a = p.a; d.w = p.w;
   d.a_cols = p.a_cols; d.a_rows = p.a_rows; d.a_row_stride = p.a_row_stride; d.a_batch_stride = p.a_batch_stride;
   d.epi = p.epi;
@@ -357,10 +359,14 @@ std::string gemm_prepare(const GemmProblem& p, int num_sms, GemmLaunch* out) {
     W2S_TRY(make_tensor_map_bf16(&out->mapA, p.a, 3, dims, str, box));
   }
   {
-    uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)p.N, (uint64_t)p.G};
-    uint64_t str[2] = {(uint64_t)p.K * 2, (uint64_t)p.K * p.N * 2};
-    uint32_t box[3] = {64, (uint32_t)(out->mc ? bn / 2 : bn), 1};
-    W2S_TRY(make_tensor_map_bf16(&out->mapW, p.w, 3, dims, str, box));
+    const uint64_t rs = (uint64_t)(p.w_row_stride ? p.w_row_stride : p.K);
+    const uint64_t wr = (uint64_t)(p.w_rows ? p.w_rows : p.N);
+    const uint64_t gs = (uint64_t)(p.w_g_stride ? p.w_g_stride : (long long)p.K * p.N);
+    const uint64_t bs = p.w_batch_stride ? (uint64_t)p.w_batch_stride : gs * (uint64_t)p.G;
+    uint64_t dims[4] = {(uint64_t)p.K, wr, (uint64_t)p.G, (uint64_t)(p.w_batch_stride ? p.Bz : 1)};
+    uint64_t str[3] = {rs * 2, gs * 2, bs * 2};
+    uint32_t box[4] = {64, (uint32_t)(out->mc ? bn / 2 : bn), 1, 1};
+    W2S_TRY(make_tensor_map_bf16(&out->mapW, p.w, 4, dims, str, box));
   }
   // pair kernel: TMA-store epilogue (not for the GLU epilogue, whose output width differs from the tile width)
   out->tma_out = 0;

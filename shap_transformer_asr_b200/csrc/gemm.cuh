@@ -26,12 +26,17 @@ struct EpiParams {
 //   plain GEMM      : a_kb_per_row = K/64
 //   strided conv    : view = [ceil(T_in/stride), stride*C]  ("stride-rows"), a_kb_per_row = stride*C/64
 //   positional conv : view = [T+pad, G*64], a_kb_per_row = 1 (one tap per block), a_g_col = 64
+//   per-(batch, head) operands (attention backward): a_g_col = 64 selects a head's columns of a [rows, n_heads*64]
+//   buffer, a_g_row = T its row block of a [batch][head][T][K] buffer; W may be batched as well (w_batch_stride != 0)
+//   with its own row / group strides, and may hold fewer than N rows (w_rows; the tiles past them are zero-filled)
 struct GemmProblem {
   const __nv_bfloat16* a = nullptr;
   long long a_cols = 0, a_rows = 0, a_batches = 1;
   long long a_row_stride = 0, a_batch_stride = 0;  // elements
-  int a_kb_per_row = 1, a_g_col = 0;
-  const __nv_bfloat16* w = nullptr;  // [G][N][K]
+  int a_kb_per_row = 1, a_g_col = 0, a_g_row = 0;
+  const __nv_bfloat16* w = nullptr;  // [G][N][K] unless the strides below say otherwise
+  long long w_row_stride = 0, w_g_stride = 0, w_batch_stride = 0;   // elements; 0 = K, N*K, "shared by all batches"
+  int w_rows = 0;                                                   // rows present per (group, batch); 0 = N
   int M = 0, N = 0, K = 0, Bz = 1, G = 1;
   EpiParams epi;
 };
@@ -40,7 +45,8 @@ struct GemmDev {
   int M, N, K, Bz, G;
   int tiles_m, tiles_n, num_tiles, num_kb;
   int units_m, num_units;  // scheduling units: tiles, or M-pairs of tiles for the CTA-pair kernel
-  int a_kb_per_row, a_g_col;
+  int a_kb_per_row, a_g_col, a_g_row;
+  int w_batched;   // W has a batch dimension (4th TMA coordinate = batch index)
   // validation-kernel addressing
   const __nv_bfloat16* a;
   const __nv_bfloat16* w;

@@ -97,8 +97,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           const int krow = kb / p.a_kb_per_row;
           const int kcol = kb - krow * p.a_kb_per_row;
           const uint32_t sa = tiles + stage * C::STAGE_BYTES;
-          tma_load_3d_2sm(sa, &mapA, full_leader, g * p.a_g_col + kcol * 64, m0 + krow, b);
-          tma_load_3d_2sm(sa + C::A_BYTES, &mapW, full_leader, kb * 64, n0 + (int)rank * (BN / 2), g);
+          tma_load_3d_2sm(sa, &mapA, full_leader, g * p.a_g_col + kcol * 64, g * p.a_g_row + m0 + krow, b);
+          tma_load_4d_2sm(sa + C::A_BYTES, &mapW, full_leader, kb * 64, n0 + (int)rank * (BN / 2), g, p.w_batched ? b : 0);
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1u;

@@ -370,6 +370,132 @@ std::string launch_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx,
   return "";
 }
 
+// ---- attention backward on the tensor cores: the five contractions (S = Q K^T, dP = dO V^T, dV = P^T dO, dQ = dS K,
+// dK = dS^T Q) run as batched GEMMs per (coalition, head) on the contraction kernels; what is left are the two row-wise
+// passes below and the transposes that give every GEMM a K-major operand.  All [.., T, Tp] buffers are zero in their
+// padding (columns T..Tp; cleared once when the plan is built, never written).
+
+// rows of S (already scaled) -> P = softmax(S) as bf16, row-major and transposed.  CTA = 32 query rows of one (b, h).
+__global__ void __launch_bounds__(256) attn_softmax_t_kernel(const float* __restrict__ S, int T, int Tp,
+                                                              __nv_bfloat16* __restrict__ P, __nv_bfloat16* __restrict__ PT) {
+  __shared__ float tile[32][33];
+  __shared__ float s_m[32], s_inv[32];
+  const long long bh = blockIdx.y;
+  const int i0 = blockIdx.x * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* Sb = S + bh * (long long)T * Tp;
+  for (int r = warp; r < 32; r += 8) {
+    const int i = i0 + r;
+    float mx = -INFINITY, l = 0.f;
+    if (i < T) {
+      for (int j = lane; j < T; j += 32) mx = fmaxf(mx, Sb[(long long)i * Tp + j]);
+      mx = warp_max(mx);
+      for (int j = lane; j < T; j += 32) l += __expf(Sb[(long long)i * Tp + j] - mx);
+      l = warp_sum(l);
+    }
+    if (lane == 0) {
+      s_m[r] = mx;
+      s_inv[r] = i < T ? 1.0f / l : 0.f;
+    }
+  }
+  __syncthreads();
+  for (int j0 = 0; j0 < T; j0 += 32) {
+    for (int r = warp; r < 32; r += 8) {
+      const int i = i0 + r, j = j0 + lane;
+      float pv = 0.f;
+      if (i < T && j < T) {
+        pv = __expf(Sb[(long long)i * Tp + j] - s_m[r]) * s_inv[r];
+        P[(bh * T + i) * (long long)Tp + j] = __float2bfloat16_rn(pv);
+      }
+      tile[r][lane] = pv;
+    }
+    __syncthreads();
+    for (int c = warp; c < 32; c += 8) {
+      const int j = j0 + c, i = i0 + lane;
+      if (j < T && i < T) PT[(bh * T + j) * (long long)Tp + i] = __float2bfloat16_rn(tile[lane][c]);
+    }
+    __syncthreads();
+  }
+}
+
+// dS = P (dP - D), D_i = sum_j P_ij dP_ij, as bf16, row-major and transposed
+__global__ void __launch_bounds__(256) attn_ds_t_kernel(const __nv_bfloat16* __restrict__ P, const float* __restrict__ dP, int T,
+                                                         int Tp, __nv_bfloat16* __restrict__ dS, __nv_bfloat16* __restrict__ dST) {
+  __shared__ float tile[32][33];
+  __shared__ float s_D[32];
+  const long long bh = blockIdx.y;
+  const int i0 = blockIdx.x * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const __nv_bfloat16* Pb = P + bh * (long long)T * Tp;
+  const float* dPb = dP + bh * (long long)T * Tp;
+  for (int r = warp; r < 32; r += 8) {
+    const int i = i0 + r;
+    float D = 0.f;
+    if (i < T)
+      for (int j = lane; j < T; j += 32) D = fmaf(__bfloat162float(Pb[(long long)i * Tp + j]), dPb[(long long)i * Tp + j], D);
+    D = warp_sum(D);
+    if (lane == 0) s_D[r] = D;
+  }
+  __syncthreads();
+  for (int j0 = 0; j0 < T; j0 += 32) {
+    for (int r = warp; r < 32; r += 8) {
+      const int i = i0 + r, j = j0 + lane;
+      float v = 0.f;
+      if (i < T && j < T) {
+        v = __bfloat162float(Pb[(long long)i * Tp + j]) * (dPb[(long long)i * Tp + j] - s_D[r]);
+        dS[(bh * T + i) * (long long)Tp + j] = __float2bfloat16_rn(v);
+      }
+      tile[r][lane] = v;
+    }
+    __syncthreads();
+    for (int c = warp; c < 32; c += 8) {
+      const int j = j0 + c, i = i0 + lane;
+      if (j < T && i < T) dST[(bh * T + j) * (long long)Tp + i] = __float2bfloat16_rn(tile[lane][c]);
+    }
+    __syncthreads();
+  }
+}
+
+std::string launch_attn_softmax_t(const float* S, int BH, int T, int Tp, __nv_bfloat16* P, __nv_bfloat16* PT, cudaStream_t s) {
+  if (BH == 0) return "";
+  attn_softmax_t_kernel<<<dim3((T + 31) / 32, BH), 256, 0, s>>>(S, T, Tp, P, PT);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+std::string launch_attn_ds_t(const __nv_bfloat16* P, const float* dP, int BH, int T, int Tp, __nv_bfloat16* dS,
+                             __nv_bfloat16* dST, cudaStream_t s) {
+  if (BH == 0) return "";
+  attn_ds_t_kernel<<<dim3((T + 31) / 32, BH), 256, 0, s>>>(P, dP, T, Tp, dS, dST);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+// per-head transpose: src[(b T + t) ld + off + h 64 + c] -> dst[((b heads + h) 64 + c) Tp + t]   (t < T; padding untouched)
+__global__ void __launch_bounds__(256) head_transpose_kernel(const __nv_bfloat16* __restrict__ src, int ld, int off, int T, int Tp,
+                                                              int heads, __nv_bfloat16* __restrict__ dst) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int bh = blockIdx.y, b = bh / heads, h = bh - b * heads;
+  const int t0 = blockIdx.x * 64;
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+    const int r = i >> 6, c = i & 63;   // r: frame, c: channel
+    const int t = t0 + r;
+    tile[r][c] = t < T ? src[((long long)b * T + t) * ld + off + h * 64 + c] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+    const int c = i >> 6, r = i & 63;
+    const int t = t0 + r;
+    if (t < T) dst[((long long)bh * 64 + c) * Tp + t] = tile[r][c];
+  }
+}
+std::string launch_head_transpose(const __nv_bfloat16* src, int ld, int off, int B, int T, int Tp, int heads, __nv_bfloat16* dst,
+                                  cudaStream_t s) {
+  if (B == 0) return "";
+  head_transpose_kernel<<<dim3((T + 63) / 64, B * heads), 256, 0, s>>>(src, ld, off, T, Tp, heads, dst);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
 // Strided conv, backward w.r.t. its input.  The contraction dcol[t_out, j C + c] = sum_o du[t_out, o] W[o][j C + c] ran on the
 // tensor cores; this gathers the <= ceil(kw / stride) taps that reach input frame t_in (t_in = stride t_out + j) and, when
 // `u_prev` is given, multiplies by gelu'(u_prev) -- the gradient w.r.t. the previous layer's pre-activation.

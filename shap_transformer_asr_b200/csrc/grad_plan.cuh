@@ -94,6 +94,7 @@ struct GradBuilder {
     plan->gemms.push_back(gl);
     W2S_TRY(gemm_prepare(p, h->num_sms, gl));
     add(name, [gl](cudaStream_t s) { return gemm_launch_tc(*gl, s); });
+    plan->steps.back().flops = 2.0 * p.M * (double)p.N * p.K * p.Bz * p.G;
     return "";
   }
   // debug snapshot of a gradient buffer right after the step that produced it
@@ -164,6 +165,24 @@ struct GradBuilder {
     W2S_TRY(alloc(&dC, (size_t)rows * H));
     W2S_TRY(alloc(&dQKV, (size_t)rows * 3 * H));
     W2S_TRY(alloc(&attn_stats, (size_t)rows * c.num_attention_heads * 3));
+    // attention backward on the tensor cores: [n, heads, T, Tp] score-shaped buffers and per-head transposes, zero padding
+    const int heads = c.num_attention_heads;
+    const int Tp = (T + 63) / 64 * 64;
+    const size_t nsc = (size_t)n * heads * T * Tp, ntr = (size_t)n * heads * 64 * Tp;
+    float *aS = nullptr, *adP = nullptr;
+    bf16 *aP = nullptr, *aPT = nullptr, *adS = nullptr, *adST = nullptr, *aQT = nullptr, *aKT = nullptr, *adOT = nullptr;
+    const bool attn_tc = !h->grad_attn_simt;
+    if (attn_tc) {
+      W2S_TRY(alloc(&aS, nsc));
+      W2S_TRY(alloc(&adP, nsc));
+      W2S_TRY(alloc(&aP, nsc, true));
+      W2S_TRY(alloc(&aPT, nsc, true));
+      W2S_TRY(alloc(&adS, nsc, true));
+      W2S_TRY(alloc(&adST, nsc, true));
+      W2S_TRY(alloc(&aQT, ntr, true));
+      W2S_TRY(alloc(&aKT, ntr, true));
+      W2S_TRY(alloc(&adOT, ntr, true));
+    }
     W2S_TRY(alloc(&dFp, (size_t)rows * Cl));
     size_t dmax = 0, colmax = 0;
     for (int l = 0; l < NC; ++l) {
@@ -340,10 +359,77 @@ struct GradBuilder {
         p.epi.out = dC;
         W2S_TRY(add_gemm(ls + "out_proj_bwd", p));
       }
-      {
+      if (!attn_tc) {
         const bf16* q = B.qkv;
-        const int heads = c.num_attention_heads;
         add(ls + "attention_bwd", [=](cudaStream_t s) { return launch_attn_bwd(q, dC, nn, T, H, heads, 0.125f, dQKV, attn_stats, s); });
+      } else {
+        const bf16* qkv = B.qkv;
+        // operands per (coalition b, head g): columns g*64 of a [rows, ld] buffer, or row block g*T of a [n, heads, T, Tp] one
+        auto from_rows = [&](const bf16* base, int ld) {   // A = 64 columns of head g, K = 64
+          GemmProblem p;
+          p.a = base; p.a_cols = ld; p.a_rows = T; p.a_batches = n; p.a_row_stride = ld; p.a_batch_stride = (long long)T * ld;
+          p.a_kb_per_row = 1; p.a_g_col = 64;
+          p.M = T; p.K = 64; p.Bz = n; p.G = heads;
+          return p;
+        };
+        auto from_scores = [&](const bf16* base) {        // A = [T, Tp] block of (b, g), K = Tp
+          GemmProblem p;
+          p.a = base; p.a_cols = Tp; p.a_rows = (long long)heads * T; p.a_batches = n; p.a_row_stride = Tp;
+          p.a_batch_stride = (long long)heads * T * Tp; p.a_kb_per_row = Tp / 64; p.a_g_col = 0; p.a_g_row = T;
+          p.M = T; p.K = Tp; p.Bz = n; p.G = heads;
+          return p;
+        };
+        auto w_rows_of = [&](GemmProblem& p, const bf16* base, int ld) {   // W = the T rows of head g in a [rows, ld] buffer
+          p.w = base; p.w_row_stride = ld; p.w_g_stride = 64; p.w_batch_stride = (long long)T * ld; p.w_rows = T; p.N = Tp;
+        };
+        auto w_transposed = [&](GemmProblem& p, const bf16* base) {        // W = [64, Tp] block of (b, g)
+          p.w = base; p.w_row_stride = Tp; p.w_g_stride = 64LL * Tp; p.w_batch_stride = (long long)heads * 64 * Tp; p.N = 64;
+        };
+        auto score_out = [&](GemmProblem& p, float* out, float alpha) {
+          p.epi.out = out; p.epi.out_fp32 = 1; p.epi.alpha = alpha;
+          p.epi.ldg = (long long)T * Tp; p.epi.ldb = (long long)heads * T * Tp; p.epi.ldm = Tp;
+        };
+        auto qkv_out = [&](GemmProblem& p, bf16* out, float alpha) {
+          p.epi.out = out; p.epi.out_fp32 = 0; p.epi.alpha = alpha;
+          p.epi.ldg = 64; p.epi.ldb = (long long)T * 3 * H; p.epi.ldm = 3 * H;
+        };
+        {
+          GemmProblem p = from_rows(qkv, 3 * H);                 // S = scale Q K^T
+          w_rows_of(p, qkv + H, 3 * H);
+          score_out(p, aS, 0.125f);
+          W2S_TRY(add_gemm(ls + "attn_scores", p));
+        }
+        add(ls + "attn_softmax", [=](cudaStream_t s) { return launch_attn_softmax_t(aS, nn * heads, T, Tp, aP, aPT, s); });
+        {
+          GemmProblem p = from_rows(dC, H);                      // dP = dO V^T
+          w_rows_of(p, qkv + 2 * H, 3 * H);
+          score_out(p, adP, 1.0f);
+          W2S_TRY(add_gemm(ls + "attn_dp", p));
+        }
+        add(ls + "attn_ds", [=](cudaStream_t s) { return launch_attn_ds_t(aP, adP, nn * heads, T, Tp, adS, adST, s); });
+        add(ls + "attn_transposes", [=](cudaStream_t s) -> std::string {
+          W2S_TRY(launch_head_transpose(qkv, 3 * H, 0, nn, T, Tp, heads, aQT, s));
+          W2S_TRY(launch_head_transpose(qkv, 3 * H, H, nn, T, Tp, heads, aKT, s));
+          return launch_head_transpose(dC, H, 0, nn, T, Tp, heads, adOT, s);
+        });
+        {
+          GemmProblem p = from_scores(adS);                      // dQ = scale dS K
+          w_transposed(p, aKT);
+          qkv_out(p, dQKV, 0.125f);
+          W2S_TRY(add_gemm(ls + "attn_dq", p));
+        }
+        {
+          GemmProblem p = from_scores(adST);                     // dK = scale dS^T Q
+          w_transposed(p, aQT);
+          qkv_out(p, dQKV + H, 0.125f);
+          W2S_TRY(add_gemm(ls + "attn_dk", p));
+        }
+        {
+          GemmProblem p = from_scores(aPT);                      // dV = P^T dO
+          w_transposed(p, adOT);
+          qkv_out(p, dQKV + 2 * H, 1.0f);
+          W2S_TRY(add_gemm(ls + "attn_dv", p));
+        }
       }
       {
         GemmProblem p = PlanBuilder::plain(dQKV, rows, 3 * H, gw.wqkvT, H);
@@ -450,7 +536,20 @@ std::string run_grad(w2s_handle* h, const float* x, long long ld, long long L, i
     h->grad_out = grad + k0 * L;
     h->grad_out_val = out_val ? out_val + k0 : nullptr;
     for (const Step& st : pl->steps) {
+      ProfRec rec;
+      if (h->profiling) {
+        rec.name = "grad." + st.name;
+        rec.flops = st.flops;
+        rec.bytes = st.bytes;
+        cudaEventCreate(&rec.e0);
+        cudaEventCreate(&rec.e1);
+        cudaEventRecord(rec.e0, s);
+      }
       std::string e = st.run(s);
+      if (h->profiling) {
+        cudaEventRecord(rec.e1, s);
+        h->prof.push_back(rec);
+      }
       if (!e.empty()) return st.name + ": " + e;
     }
     h->launches += (long long)pl->steps.size() + 1;

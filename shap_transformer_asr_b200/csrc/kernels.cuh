@@ -151,6 +151,11 @@ std::string launch_head_bwd(const float* logits, int ldl, int V, const __nv_bflo
                             const int* frames, float* dh, float* out_val, cudaStream_t s);
 std::string launch_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx, int B, int T, int H, int heads, float scale,
                             __nv_bfloat16* dqkv, float* stats, cudaStream_t s);
+std::string launch_attn_softmax_t(const float* S, int BH, int T, int Tp, __nv_bfloat16* P, __nv_bfloat16* PT, cudaStream_t s);
+std::string launch_attn_ds_t(const __nv_bfloat16* P, const float* dP, int BH, int T, int Tp, __nv_bfloat16* dS,
+                             __nv_bfloat16* dST, cudaStream_t s);
+std::string launch_head_transpose(const __nv_bfloat16* src, int ld, int off, int B, int T, int Tp, int heads, __nv_bfloat16* dst,
+                                  cudaStream_t s);
 std::string launch_conv_gather(const __nv_bfloat16* dcol, int n, int T_in, int T_out, int C, int kw, int stride,
                                const __nv_bfloat16* u_prev, __nv_bfloat16* out, cudaStream_t s);
 std::string launch_conv0_bwd(const __nv_bfloat16* du, const __nv_bfloat16* u, int n, long long L, int T0, int C, int kw, int stride,

@@ -67,8 +67,10 @@ def cosine(a, b):
     return float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30))
 
 
-def test_gradient_stages_match_autograd_tiny(P):
-    """Every stage of the backward pass against autograd (tiny model): localises a wrong kernel to its stage."""
+@pytest.mark.parametrize("attn", ["tensor_core", "cuda_core"])
+def test_gradient_stages_match_autograd_tiny(P, attn):
+    """Every stage of the backward pass against autograd (tiny model): localises a wrong kernel to its stage.  Attention
+    backward both as batched tensor-core contractions (the product path) and on the CUDA-core cross-check kernels."""
     cfg = VARIANTS["tiny_group"]
     model = build_model(cfg)
     rng = np.random.default_rng(0)
@@ -77,7 +79,7 @@ def test_gradient_stages_match_autograd_tiny(P):
     frames = np.array([0, 5, T - 1], dtype=np.int32)
     gx, g, out, NL = reference_grads(model, x, frames)
     eng = P.Engine(model, cfg, max_batch=4)
-    eng.grad_debug(True)
+    eng.grad_debug(True, simt_attention=attn == "cuda_core")
     grad, val = eng.grad_waveforms(torch.from_numpy(x).cuda(), frames)
     torch.cuda.synchronize()
     H = cfg.hidden_size
@@ -115,7 +117,7 @@ def test_gradient_stages_match_autograd_tiny(P):
     eng.close()
 
 
-@pytest.mark.parametrize("name,n,L", [("tiny_group", 35, 9000), ("wav2vec2-base", 32, 16000)])
+@pytest.mark.parametrize("name,n,L", [("tiny_group", 35, 9000), ("wav2vec2-base", 32, 16000), ("tiny_group", 3, 183600)])
 def test_input_gradients_match_autograd_at_batch_32(P, name, n, L):
     """d (max logit of frame j) / d waveform for >= 32 rows with different target frames (one ragged tile for the tiny
     model: 32 + 3) against torch autograd on the transformers model."""

@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Expected-gradients path: forward + backward passes per second (the unit the reference's recorded run is quoted in:
+114 600 passes in 5586 s for the 11.5 s clip, evaluation.ipynb:463,513 -> 20.5 passes/s at batch 1 on their GPU).
+
+    python tools/bench_grad.py [--model wav2vec2-base] [--samples 183600] [--rows 64] [--steps 3]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from shap_transformer_asr_b200 import MODELS, Engine, synthetic_clip
+from shap_transformer_asr_b200.modelzoo import build_random_init_model
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default="wav2vec2-base")
+    ap.add_argument("--samples", type=int, default=183600)
+    ap.add_argument("--rows", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--simt-attention", action="store_true", help="attention backward on the CUDA-core cross-check kernels")
+    args = ap.parse_args()
+    cfg = MODELS[args.model]
+    eng = Engine(build_random_init_model(cfg, seed=0), cfg, max_batch=4)
+    eng.grad_debug(False, simt_attention=args.simt_attention)
+    L = args.samples
+    T = eng.num_frames(L)
+    x = torch.from_numpy(np.stack([synthetic_clip(L, seed=s) for s in range(4)])).cuda()
+    x = x[torch.arange(args.rows) % 4].contiguous()
+    frames = (np.arange(args.rows) * 7) % T
+    eng.grad_waveforms(x, frames)                                  # plans, transposed weights
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        g, out = eng.grad_waveforms(x, frames)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    eng.profile(True)
+    eng.grad_waveforms(x, frames)
+    torch.cuda.synchronize()
+    prof = eng.profile_read()
+    eng.profile(False)
+    tot = sum(v["ms"] for v in prof.values())
+    top = {k: round(v["ms"], 2) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:14]}
+    fwd = sum(v["ms"] for k, v in prof.items() if not k.endswith("_bwd") and "bwd" not in k and "gather" not in k and "cast" not in k)
+    print(json.dumps({"metric": "expected_gradient_passes_per_sec", "value": args.rows / (ms / 1e3), "unit": "fwd+bwd passes/s",
+                      "model": args.model, "attention_backward": "cuda_core" if args.simt_attention else "tensor_core", "num_samples": L, "frames": T, "rows_per_call": args.rows, "ms_per_call": ms,
+                      "reference_recorded": {"passes_per_s": 114600 / 5586.0, "source": "evaluation.ipynb:463,513 (batch 1, GPU model not recorded)"},
+                      "profiled_ms": tot, "forward_share": fwd / tot, "top_steps_ms": top,
+                      "clip_estimate_s": {"passes": T * 200, "seconds": T * 200 / (args.rows / (ms / 1e3))}}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
