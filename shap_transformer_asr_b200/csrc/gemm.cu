@@ -330,8 +330,9 @@ std::string gemm_prepare(const GemmProblem& p, int num_sms, GemmLaunch* out) {
   d.tiles_n = p.N / bn;
   d.num_tiles = d.tiles_m * d.tiles_n * p.Bz * p.G;
   d.num_kb = p.K / 64;
-  // CTA pairs (tcgen05 cta_group::2, 256-row tiles) when there are enough tiles to keep all pairs busy
-  out->mc = (bn >= 128 && d.tiles_m >= 2 && d.num_tiles >= 2 * num_sms) ? 2 : 0;
+  // CTA pairs (tcgen05 cta_group::2, 256-row tiles) when there are enough tiles to give every pair one: below that the
+  // single-CTA kernel keeps more SMs busy
+  out->mc = (bn >= 128 && d.tiles_m >= 2 && d.num_tiles >= num_sms) ? 2 : 0;
   d.units_m = out->mc ? (d.tiles_m + 1) / 2 : d.tiles_m;
   d.num_units = d.units_m * d.tiles_n * p.Bz * p.G;
   d.a_kb_per_row = p.a_kb_per_row;

@@ -137,8 +137,9 @@ def test_input_gradients_match_autograd_at_batch_32(P, name, n, L):
     assert np.abs(val.cpu().numpy() - out).max() < 0.025 * np.abs(out).max() + 1e-3
     assert e < GRAD_TOL and min(per_row) > 0.995
     # the same rows, one at a time, give the same gradients (no dependence on the position in the batch)
-    g1, _ = eng.grad_waveforms(torch.from_numpy(x[5:6]).cuda(), frames[5:6])
-    assert np.abs(g1.cpu().numpy()[0] - grad[5]).max() <= 1e-6 * np.abs(grad[5]).max() + 1e-12
+    r = min(5, n - 1)
+    g1, _ = eng.grad_waveforms(torch.from_numpy(x[r:r + 1]).cuda(), frames[r:r + 1])
+    assert np.abs(g1.cpu().numpy()[0] - grad[r]).max() <= 1e-6 * np.abs(grad[r]).max() + 1e-12
     eng.close()
 
 

@@ -49,7 +49,10 @@ def main():
     eng.profile(False)
     tot = sum(v["ms"] for v in prof.values())
     top = {k: round(v["ms"], 2) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:14]}
-    fwd = sum(v["ms"] for k, v in prof.items() if not k.endswith("_bwd") and "bwd" not in k and "gather" not in k and "cast" not in k)
+    fwd_names = {"conv0_stats", "conv0", "featproj_ln", "featproj", "pos_pad", "pos_conv", "pos_add", "encoder_ln", "qkv",
+                 "attention", "out_proj", "ln1", "ffn1", "ffn_gelu", "ffn2", "ln2", "lm_head"}
+    fwd_names |= {f"conv{l}" for l in range(1, 8)} | {f"conv{l}_gelu" for l in range(0, 8)}
+    fwd = sum(v["ms"] for k, v in prof.items() if k.replace("grad.", "") in fwd_names)
     print(json.dumps({"metric": "expected_gradient_passes_per_sec", "value": args.rows / (ms / 1e3), "unit": "fwd+bwd passes/s",
                       "model": args.model, "attention_backward": "cuda_core" if args.simt_attention else "tensor_core", "num_samples": L, "frames": T, "rows_per_call": args.rows, "ms_per_call": ms,
                       "reference_recorded": {"passes_per_s": 114600 / 5586.0, "source": "evaluation.ipynb:463,513 (batch 1, GPU model not recorded)"},
