@@ -375,97 +375,95 @@ std::string launch_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx,
 // passes below and the transposes that give every GEMM a K-major operand.  All [.., T, Tp] buffers are zero in their
 // padding (columns T..Tp; cleared once when the plan is built, never written).
 
-// rows of S (already scaled) -> P = softmax(S) as bf16, row-major and transposed.  CTA = 32 query rows of one (b, h).
-__global__ void __launch_bounds__(256) attn_softmax_t_kernel(const float* __restrict__ S, int T, int Tp,
-                                                              __nv_bfloat16* __restrict__ P, __nv_bfloat16* __restrict__ PT) {
-  __shared__ float tile[32][33];
-  __shared__ float s_m[32], s_inv[32];
-  const long long bh = blockIdx.y;
-  const int i0 = blockIdx.x * 32;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* Sb = S + bh * (long long)T * Tp;
-  for (int r = warp; r < 32; r += 8) {
-    const int i = i0 + r;
-    float mx = -INFINITY, l = 0.f;
-    if (i < T) {
-      for (int j = lane; j < T; j += 32) mx = fmaxf(mx, Sb[(long long)i * Tp + j]);
-      mx = warp_max(mx);
-      for (int j = lane; j < T; j += 32) l += __expf(Sb[(long long)i * Tp + j] - mx);
-      l = warp_sum(l);
-    }
-    if (lane == 0) {
-      s_m[r] = mx;
-      s_inv[r] = i < T ? 1.0f / l : 0.f;
-    }
-  }
-  __syncthreads();
-  for (int j0 = 0; j0 < T; j0 += 32) {
-    for (int r = warp; r < 32; r += 8) {
-      const int i = i0 + r, j = j0 + lane;
-      float pv = 0.f;
-      if (i < T && j < T) {
-        pv = __expf(Sb[(long long)i * Tp + j] - s_m[r]) * s_inv[r];
-        P[(bh * T + i) * (long long)Tp + j] = __float2bfloat16_rn(pv);
-      }
-      tile[r][lane] = pv;
-    }
-    __syncthreads();
-    for (int c = warp; c < 32; c += 8) {
-      const int j = j0 + c, i = i0 + lane;
-      if (j < T && i < T) PT[(bh * T + j) * (long long)Tp + i] = __float2bfloat16_rn(tile[lane][c]);
-    }
-    __syncthreads();
-  }
-}
+// rows of S (already scaled) -> P = softmax(S) as bf16, row-major and transposed.  CTA = 32 query rows of one (b, h):
+// a warp holds a whole row in registers (one read of S), the CTA's 32 x T tile of P is staged in shared memory (row pitch
+// an odd number of words: conflict-free column reads) and written out a second time as 64-byte runs of P^T.
+constexpr int AT_MAXV = 32;   // T <= 1024
 
-// dS = P (dP - D), D_i = sum_j P_ij dP_ij, as bf16, row-major and transposed
-__global__ void __launch_bounds__(256) attn_ds_t_kernel(const __nv_bfloat16* __restrict__ P, const float* __restrict__ dP, int T,
-                                                         int Tp, __nv_bfloat16* __restrict__ dS, __nv_bfloat16* __restrict__ dST) {
-  __shared__ float tile[32][33];
-  __shared__ float s_D[32];
+template <bool DS>   // false: P = softmax(S);  true: dS = P (dP - sum_j P dP), with `in16` = P and `in32` = dP
+__global__ void __launch_bounds__(256) attn_rows_t_kernel(const float* __restrict__ in32, const __nv_bfloat16* __restrict__ in16,
+                                                           int T, int Tp, __nv_bfloat16* __restrict__ out,
+                                                           __nv_bfloat16* __restrict__ outT) {
+  extern __shared__ __nv_bfloat16 tile[];   // [32][Tp + 2]
+  const int pitch = Tp + 2;
   const long long bh = blockIdx.y;
   const int i0 = blockIdx.x * 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const __nv_bfloat16* Pb = P + bh * (long long)T * Tp;
-  const float* dPb = dP + bh * (long long)T * Tp;
+  const long long base = bh * (long long)T * Tp;
   for (int r = warp; r < 32; r += 8) {
     const int i = i0 + r;
-    float D = 0.f;
-    if (i < T)
-      for (int j = lane; j < T; j += 32) D = fmaf(__bfloat162float(Pb[(long long)i * Tp + j]), dPb[(long long)i * Tp + j], D);
-    D = warp_sum(D);
-    if (lane == 0) s_D[r] = D;
+    if (i >= T) continue;   // warp-uniform
+    const float* row32 = in32 + base + (long long)i * Tp;
+    float v[AT_MAXV];
+    if constexpr (!DS) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < AT_MAXV; ++c) {
+        const int j = c * 32 + lane;
+        v[c] = j < T ? row32[j] : -INFINITY;
+        mx = fmaxf(mx, v[c]);
+      }
+      mx = warp_max(mx);
+      float l = 0.f;
+#pragma unroll
+      for (int c = 0; c < AT_MAXV; ++c) {
+        v[c] = (c * 32 + lane < T) ? __expf(v[c] - mx) : 0.f;
+        l += v[c];
+      }
+      const float inv = 1.0f / warp_sum(l);
+#pragma unroll
+      for (int c = 0; c < AT_MAXV; ++c) v[c] *= inv;
+    } else {
+      const __nv_bfloat16* row16 = in16 + base + (long long)i * Tp;
+      float pv[AT_MAXV];
+      float D = 0.f;
+#pragma unroll
+      for (int c = 0; c < AT_MAXV; ++c) {
+        const int j = c * 32 + lane;
+        pv[c] = j < T ? __bfloat162float(row16[j]) : 0.f;
+        v[c] = j < T ? row32[j] : 0.f;
+        D = fmaf(pv[c], v[c], D);
+      }
+      D = warp_sum(D);
+#pragma unroll
+      for (int c = 0; c < AT_MAXV; ++c) v[c] = pv[c] * (v[c] - D);
+    }
+#pragma unroll
+    for (int c = 0; c < AT_MAXV; ++c) {
+      const int j = c * 32 + lane;
+      if (j < T) {
+        const __nv_bfloat16 q = __float2bfloat16_rn(v[c]);
+        out[base + (long long)i * Tp + j] = q;
+        tile[r * pitch + j] = q;
+      }
+    }
   }
   __syncthreads();
-  for (int j0 = 0; j0 < T; j0 += 32) {
-    for (int r = warp; r < 32; r += 8) {
-      const int i = i0 + r, j = j0 + lane;
-      float v = 0.f;
-      if (i < T && j < T) {
-        v = __bfloat162float(Pb[(long long)i * Tp + j]) * (dPb[(long long)i * Tp + j] - s_D[r]);
-        dS[(bh * T + i) * (long long)Tp + j] = __float2bfloat16_rn(v);
-      }
-      tile[r][lane] = v;
-    }
-    __syncthreads();
-    for (int c = warp; c < 32; c += 8) {
-      const int j = j0 + c, i = i0 + lane;
-      if (j < T && i < T) dST[(bh * T + j) * (long long)Tp + i] = __float2bfloat16_rn(tile[lane][c]);
-    }
-    __syncthreads();
-  }
+  const int nrow = min(32, T - i0);   // valid query rows of this CTA
+  for (int j = warp; j < T; j += 8)
+    if (lane < nrow) outT[base + (long long)j * Tp + i0 + lane] = tile[lane * pitch + j];
 }
 
 std::string launch_attn_softmax_t(const float* S, int BH, int T, int Tp, __nv_bfloat16* P, __nv_bfloat16* PT, cudaStream_t s) {
   if (BH == 0) return "";
-  attn_softmax_t_kernel<<<dim3((T + 31) / 32, BH), 256, 0, s>>>(S, T, Tp, P, PT);
+  if (T > 32 * AT_MAXV) return "attention backward: more than 1024 frames are not supported yet";
+  const size_t smem = (size_t)32 * (Tp + 2) * sizeof(__nv_bfloat16);
+  static bool attr = false;
+  if (!attr) {
+    W2S_CUDA_OK(cudaFuncSetAttribute(attn_rows_t_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    W2S_CUDA_OK(cudaFuncSetAttribute(attn_rows_t_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    attr = true;
+  }
+  attn_rows_t_kernel<false><<<dim3((T + 31) / 32, BH), 256, smem, s>>>(S, nullptr, T, Tp, P, PT);
   W2S_CUDA_OK(cudaGetLastError());
   return "";
 }
 std::string launch_attn_ds_t(const __nv_bfloat16* P, const float* dP, int BH, int T, int Tp, __nv_bfloat16* dS,
                              __nv_bfloat16* dST, cudaStream_t s) {
   if (BH == 0) return "";
-  attn_ds_t_kernel<<<dim3((T + 31) / 32, BH), 256, 0, s>>>(P, dP, T, Tp, dS, dST);
+  if (T > 32 * AT_MAXV) return "attention backward: more than 1024 frames are not supported yet";
+  const size_t smem = (size_t)32 * (Tp + 2) * sizeof(__nv_bfloat16);
+  attn_rows_t_kernel<true><<<dim3((T + 31) / 32, BH), 256, smem, s>>>(dP, P, T, Tp, dS, dST);
   W2S_CUDA_OK(cudaGetLastError());
   return "";
 }

@@ -48,6 +48,16 @@ def eta_raw(clean_audio, noise_audio, shap_matrix, sr: int, segment_ms: float = 
     return float((relevant * itm).sum() / den)
 
 
+def eta_raw_segments(clean_audio, noise_audio, phi, bounds, sr: int, **kw) -> float:
+    """``eta_raw`` for attributions that are constant inside a waveform segment (what KernelSHAP over segment coalitions
+    produces): ``phi`` is ``[M, D]``, ``bounds`` the ``M + 1`` segment boundaries.  The per-sample total ``sum_d |phi|`` is
+    formed per SEGMENT and repeated, instead of reducing the expanded ``[L, T']`` array (130 MB for a 6.4 s clip) -- the
+    same numbers summed in the same order, so the result is bit-identical to ``eta_raw`` on the expanded matrix."""
+    phi = np.asarray(phi)
+    total = np.repeat(np.abs(phi).sum(axis=1), np.diff(np.asarray(bounds)))
+    return eta_raw(clean_audio, noise_audio, total[:, None], sr, **kw)
+
+
 def greedy_ctc_decode(ids, vocab=VOCAB, pad_id: int = 0, space_id: int = 4) -> str:
     """Collapse repeats, drop blanks, map '|' to a space (what processor.batch_decode does for this vocabulary;
     visualization.py:305-309, nraw_vs_wer.py:75-79)."""

@@ -48,7 +48,8 @@ def explain_test_set(engine, test_set: List[Dict], out_dir: str = "data", num_se
 
     Every item is explained on THIS rank's GPU (clip-level sharding: the caller hands each rank its items).
     ``save_limit``: write the files of the first N items only (a 6.4 s item is 130 MB of float32 attributions);
-    ``on_item(index, item, shap_values, result)`` is called with the in-memory array of every item, saved or not."""
+    ``on_item(index, item, phi, bounds, result)`` is called for every item, saved or not, with the segment-level
+    attributions ``phi [M, T']`` (the ``[1, L, T']`` expansion is only materialised for the items that are written)."""
     os.makedirs(out_dir, exist_ok=True)
     explainer = KernelShapExplainer(engine, nsamples=nsamples, seed=seed, shard_coalitions=False)
     results, clean_text = [], None
@@ -66,16 +67,17 @@ def explain_test_set(engine, test_set: List[Dict], out_dir: str = "data", num_se
         targets = None if mode == "max" else (np.arange(T, dtype=np.int32), logits.argmax(-1).astype(np.int32))
         res = explainer.explain(x, num_segments=num_segments, mode=mode, targets=targets if mode != "max" else ((), ()))
         phi = res["phi"].cpu().numpy()
-        shap_values = expand_to_samples(phi, engine.bounds).astype(np.float32)      # [1, L, T']
         tag = f"sample_{i + 1}_{item['type']}_{item['snr']}"
         saved = save_limit is None or i < save_limit
+        shape = (1, int(engine.bounds[-1]), phi.shape[1])
         if saved:
+            shap_values = expand_to_samples(phi, engine.bounds).astype(np.float32)      # [1, L, T']
             np.save(os.path.join(out_dir, f"shap_values_{tag}"), shap_values)
             np.save(os.path.join(out_dir, f"audio_{tag}"), item["audio"])
             np.save(os.path.join(out_dir, f"noise_{tag}"), item["noise"])
             np.save(os.path.join(out_dir, f"text_{tag}.npy"), text)
-        results.append(dict(tag=tag, hypothesis=hyp, text=text, shap_shape=shap_values.shape, saved=saved,
+        results.append(dict(tag=tag, hypothesis=hyp, text=text, shap_shape=shape, saved=saved,
                             status=int(res["status"].item())))
         if on_item is not None:
-            on_item(i, item, shap_values, results[-1])
+            on_item(i, item, phi, np.asarray(engine.bounds), results[-1])
     return results

@@ -117,7 +117,8 @@ def test_gradient_stages_match_autograd_tiny(P, attn):
     eng.close()
 
 
-@pytest.mark.parametrize("name,n,L", [("tiny_group", 35, 9000), ("wav2vec2-base", 32, 16000), ("tiny_group", 3, 183600)])
+@pytest.mark.parametrize("name,n,L", [("tiny_group", 35, 9000), ("wav2vec2-base", 32, 16000), ("tiny_group", 3, 183600),
+                                      ("wav2vec2-large", 4, 16000)])
 def test_input_gradients_match_autograd_at_batch_32(P, name, n, L):
     """d (max logit of frame j) / d waveform for >= 32 rows with different target frames (one ragged tile for the tiny
     model: 32 + 3) against torch autograd on the transformers model."""

@@ -192,3 +192,37 @@ def test_native_sampler_continues_numpys_global_generator():
         words, w3, _ = sample_coalitions(M, K, seed=5, packed=True)
         Z3, _, _ = sample_coalitions(M, K, seed=5)
         assert np.array_equal(words, pack_coalitions(Z3)) and np.array_equal(unpack_coalitions(words, M), Z3)
+
+
+def test_expected_gradients_estimator_on_a_mock_engine():
+    """ExpectedGradientsExplainer (the reference's GradientExplainer loop, shap_calculation.py:125-162) on a quadratic
+    toy model whose input gradients are known in closed form: layout [1, L, D], and for f_j(x) = 0.5 a_j |x|^2 the
+    expected-gradients attribution of sample i is E[a_j (bg + alpha (x - bg))_i (x - bg)_i]."""
+    import types
+    from shap_transformer_asr_b200.expected_gradients import ExpectedGradientsExplainer, make_background
+
+    L, T = 50, 4
+    a = np.array([1.0, -2.0, 0.5, 3.0])
+
+    class Mock:
+        device = torch.device("cpu")
+
+        def num_frames(self, n):
+            return T
+
+        def grad_waveforms(self, xs, frame):
+            j = int(np.atleast_1d(frame)[0])
+            return a[j] * xs, (0.5 * a[j] * (xs ** 2).sum(1))
+
+    x = np.random.default_rng(0).standard_normal(L).astype(np.float32)
+    bg = make_background(L, 5, seed=2)
+    ex = ExpectedGradientsExplainer(Mock(), bg, nsamples=4000, seed=1, batch=512)
+    phi = ex.shap_values(x)
+    assert phi.shape == (1, L, T)
+    # E over alpha ~ U(0,1) and the 5 backgrounds of a_j (bg + alpha d) d,  d = x - bg
+    d = x[None] - bg
+    expect = np.stack([a[j] * ((bg + 0.5 * d) * d).mean(0) for j in range(T)], 1)
+    assert np.abs(phi[0] - expect).max() < 0.05 * np.abs(expect).max()
+    # completeness: sum_i phi_ij = f_j(x) - E f_j(bg) for this model, up to sampling noise
+    gap = phi[0].sum(0) - (0.5 * a * (x ** 2).sum() - 0.5 * a * (bg ** 2).sum(1).mean())
+    assert np.abs(gap).max() < 0.05 * np.abs(0.5 * a * (x ** 2).sum()).max()

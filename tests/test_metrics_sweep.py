@@ -73,3 +73,17 @@ def test_saved_layout_is_what_the_reference_consumers_expect(tmp_path):
     np.save(p, arr)
     back = np.load(p).squeeze()
     assert back.shape == (83, 5) and np.allclose(back[25], phi[2], atol=1e-6)
+
+
+def test_eta_raw_on_segment_level_attributions_is_bit_identical():
+    """eta_raw_segments (no [L, T'] expansion) against eta_raw on the expanded matrix, both ITM thresholds."""
+    from shap_transformer_asr_b200 import eta_raw, eta_raw_segments, expand_to_samples, segment_bounds
+    rng = np.random.default_rng(3)
+    L, M, D = 102400, 128, 40
+    clean = rng.standard_normal(L) * (1 + np.sin(np.arange(L) / 3000.0))
+    noise = 0.8 * rng.standard_normal(L)
+    phi = rng.standard_normal((M, D)) * rng.random((M, 1))
+    b = segment_bounds(L, M)
+    full = expand_to_samples(phi, b)[0]
+    for ratio in (0.5, 1.0):
+        assert eta_raw_segments(clean, noise, phi, b, 16000, itm_ratio=ratio) == eta_raw(clean, noise, full, 16000, itm_ratio=ratio)

@@ -19,7 +19,7 @@ import torch
 import torch.distributed as td
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from shap_transformer_asr_b200 import MODELS, Engine, dist as wdist, eta_raw, explain_test_set, make_test_set, wer
+from shap_transformer_asr_b200 import MODELS, Engine, dist as wdist, eta_raw_segments, explain_test_set, make_test_set, wer
 from shap_transformer_asr_b200.modelzoo import build_random_init_model
 
 
@@ -48,9 +48,9 @@ def main():
     t0 = time.perf_counter()
     rows = []
 
-    def consume(k, item, shap_values, r):      # the downstream metrics of every item, from the in-memory attributions
+    def consume(k, item, phi, bounds, r):      # the downstream metrics of every item, from the segment-level attributions
         rows.append(dict(item=mine[k], type=item["type"], snr=item["snr"], status=r["status"],
-                         eta_raw=eta_raw(item["audio"] - item["noise"], item["noise"], shap_values.squeeze(), 16000),
+                         eta_raw=eta_raw_segments(item["audio"] - item["noise"], item["noise"], phi, bounds, 16000),
                          wer=wer(r["text"], r["hypothesis"])))
 
     explain_test_set(eng, [test_set[i] for i in mine], out_dir=os.path.join(args.out, f"rank{rank}"),
