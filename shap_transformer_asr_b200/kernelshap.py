@@ -137,6 +137,27 @@ class KernelShapExplainer:
         self.nsamples = nsamples
         self.seed = seed
         self.shard_coalitions = shard_coalitions
+        self._cache = {}
+
+    def _coalitions(self, M: int):
+        """The sampled coalition matrix depends on (M, nsamples, seed) only -- not on the clip -- so with a fixed seed a
+        sweep over many clips draws it once: later calls reuse the packed rows, their device copy and the kernel weights,
+        and leave numpy's global generator in the state the draw would have left it in (exactly what re-sampling does)."""
+        key = (int(M), self.nsamples, self.seed)
+        hit = self._cache.get(key) if self.seed is not None else None
+        if hit is None:
+            words, kw, info = sample_coalitions(M, self.nsamples, seed=self.seed, packed=True)
+            head = np.zeros((2, words.shape[1]), dtype=np.uint32)      # rows 0 / 1: the empty and the full coalition
+            head[1] = 0xFFFFFFFF
+            if M % 32:
+                head[1, -1] = (1 << (M % 32)) - 1
+            hit = dict(words=words, kw=kw, info=info, state=np.random.get_state(), all_words=np.concatenate([head, words]),
+                       bits_dev=None, w_dev=None)
+            if self.seed is not None:
+                self._cache = {key: hit}
+        else:
+            np.random.set_state(hit["state"])
+        return hit
 
     def select_targets(self, mode: str = "logprob"):
         eng = self.engine
@@ -167,7 +188,7 @@ class KernelShapExplainer:
             eng.set_targets("logits")
             ones = eng.bits_to_device(np.ones((1, M), dtype=np.uint8))
             logits_dev = eng.eval_bits(ones)
-            sampled = sample_coalitions(M, self.nsamples, seed=self.seed, packed=True)
+            sampled = self._coalitions(M)
             logits = logits_dev.view(-1, eng.config.vocab_size).cpu().numpy()
             frames, tokens = char_targets(logits)
             eng.set_targets(mode, frames, tokens)
@@ -175,24 +196,22 @@ class KernelShapExplainer:
             frames, tokens = targets
             eng.set_targets(mode, frames, tokens)
         if sampled is None:
-            sampled = sample_coalitions(M, self.nsamples, seed=self.seed, packed=True)
-        words, kw, info = sampled
+            sampled = self._coalitions(M)
+        words, kw, info = sampled["words"], sampled["kw"], sampled["info"]
         K = words.shape[0]
         # rows 0 / 1 of the evaluated matrix are the empty and the full coalition (fnull, fx): fx comes from the same
         # reduction kernel as every y row, so the efficiency constraint is consistent to the last bit
-        head = np.zeros((2, words.shape[1]), dtype=np.uint32)
-        head[1] = 0xFFFFFFFF
-        if M % 32:
-            head[1, -1] = (1 << (M % 32)) - 1
         rank, world = wdist.rank_world() if self.shard_coalitions else (0, 1)
         lo, hi = wdist.shard_range(K + 2, rank, world)
-        bits_all = eng.bits_to_device(np.concatenate([head, words]))
+        if sampled["bits_dev"] is None or sampled["bits_dev"].device != eng.device:
+            sampled["bits_dev"] = eng.bits_to_device(sampled["all_words"]).clone()     # own copy: survives later uploads
+            sampled["w_dev"] = torch.from_numpy(kw).to(eng.device)
+        bits_all = sampled["bits_dev"]
         y_local = eng.eval_bits(bits_all[lo:hi]) if hi > lo else torch.empty((0, eng.out_width()), device=eng.device)
         y_all = wdist.all_gather_rows(y_local, K + 2, rank, world)
         fnull = y_all[0].double()
         fx = y_all[1].double()
-        w_dev = torch.from_numpy(kw).to(eng.device, non_blocking=True)
-        phi, status = eng.wls(bits_all[2:], w_dev, y_all[2:], fx, fnull, M)
+        phi, status = eng.wls(bits_all[2:], sampled["w_dev"], y_all[2:], fx, fnull, M)
         if check:
             st = int(status.item())
             if st == 1:
