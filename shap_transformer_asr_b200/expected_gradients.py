@@ -40,25 +40,36 @@ class ExpectedGradientsExplainer:
 
     def shap_values(self, x, frames=None) -> np.ndarray:
         """x: normalised clip [L] -> attributions [1, L, D] (the reference's on-disk layout, D = T' when ``frames`` is
-        None: every output frame, as ``ranked_outputs=None``)."""
+        None: every output frame, as ``ranked_outputs=None``).
+
+        The (output frame, sample) passes of ALL outputs form one list that is cut into device calls of ``batch`` rows
+        (every row carries its own target frame), so no call is ragged except the last."""
         eng = self.engine
         x = np.ascontiguousarray(np.asarray(x, dtype=np.float32).reshape(-1))
         L = x.size
         T = eng.num_frames(L)
         frames = np.arange(T, dtype=np.int32) if frames is None else np.asarray(frames, dtype=np.int32)
+        D, S = len(frames), self.nsamples
         bg = torch.from_numpy(self.background).to(eng.device)
         xt = torch.from_numpy(x).to(eng.device)
-        phi = torch.zeros((len(frames), L), dtype=torch.float64, device=eng.device)
+        # per output frame its own seeded draws (background index, alpha), as shap reseeds per explained output
+        rind = np.empty((D, S), dtype=np.int64)
+        alpha = np.empty((D, S), dtype=np.float32)
         for d, j in enumerate(frames):
             rng = np.random.default_rng([self.seed, int(j)])
-            rind = torch.from_numpy(rng.integers(0, bg.shape[0], self.nsamples)).to(eng.device)
-            alpha = torch.from_numpy(rng.uniform(size=self.nsamples).astype(np.float32)).to(eng.device)
-            for s0 in range(0, self.nsamples, self.batch):
-                b = bg[rind[s0:s0 + self.batch]]
-                a = alpha[s0:s0 + self.batch, None]
-                delta = xt[None] - b
-                xs = (b + a * delta).contiguous()
-                g, _ = eng.grad_waveforms(xs, int(j))
-                phi[d] += (g.double() * delta.double()).sum(0)
-        phi /= self.nsamples
+            rind[d] = rng.integers(0, bg.shape[0], S)
+            alpha[d] = rng.uniform(size=S).astype(np.float32)
+        rind_t = torch.from_numpy(rind.reshape(-1)).to(eng.device)
+        alpha_t = torch.from_numpy(alpha.reshape(-1)).to(eng.device)
+        out_of = torch.arange(D, device=eng.device).repeat_interleave(S)       # row -> output slot
+        row_frames = np.repeat(frames, S)
+        phi = torch.zeros((D, L), dtype=torch.float32, device=eng.device)
+        for r0 in range(0, D * S, self.batch):
+            r1 = min(r0 + self.batch, D * S)
+            b = bg[rind_t[r0:r1]]
+            delta = xt[None] - b
+            xs = torch.addcmul(b, alpha_t[r0:r1, None], delta)
+            g, _ = eng.grad_waveforms(xs, row_frames[r0:r1])
+            phi.index_add_(0, out_of[r0:r1], g * delta)
+        phi /= S
         return phi.t().contiguous()[None].cpu().numpy()

@@ -210,9 +210,9 @@ def test_expected_gradients_estimator_on_a_mock_engine():
         def num_frames(self, n):
             return T
 
-        def grad_waveforms(self, xs, frame):
-            j = int(np.atleast_1d(frame)[0])
-            return a[j] * xs, (0.5 * a[j] * (xs ** 2).sum(1))
+        def grad_waveforms(self, xs, frames):          # one target frame per row
+            aj = torch.from_numpy(a[np.broadcast_to(np.asarray(frames), (xs.shape[0],))]).float()
+            return aj[:, None] * xs, 0.5 * aj * (xs ** 2).sum(1)
 
     x = np.random.default_rng(0).standard_normal(L).astype(np.float32)
     bg = make_background(L, 5, seed=2)

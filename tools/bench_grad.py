@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--rows", type=int, default=64)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--simt-attention", action="store_true", help="attention backward on the CUDA-core cross-check kernels")
+    ap.add_argument("--explain-frames", type=int, default=0, help="also time ExpectedGradientsExplainer.shap_values over the "
+                    "first N output frames (-1 = all T' frames: the reference's full job) with 200 samples and 5 backgrounds")
     args = ap.parse_args()
     cfg = MODELS[args.model]
     eng = Engine(build_random_init_model(cfg, seed=0), cfg, max_batch=4)
@@ -48,6 +50,20 @@ def main():
     prof = eng.profile_read()
     eng.profile(False)
     tot = sum(v["ms"] for v in prof.values())
+    explain = None
+    if args.explain_frames:
+        import time
+        from shap_transformer_asr_b200 import ExpectedGradientsExplainer, make_background
+        nf = T if args.explain_frames < 0 else min(T, args.explain_frames)
+        ex = ExpectedGradientsExplainer(eng, make_background(L, 5, seed=0), nsamples=200, seed=0, batch=args.rows)
+        clip = synthetic_clip(L)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        phi = ex.shap_values(clip, np.arange(nf, dtype=np.int32))
+        dt = time.perf_counter() - t0
+        explain = {"frames": nf, "samples_per_frame": 200, "passes": nf * 200, "seconds": dt, "passes_per_s": nf * 200 / dt,
+                   "shap_shape": list(phi.shape), "finite": bool(np.isfinite(phi).all()),
+                   "reference_recorded_seconds_all_frames": 5586.0 if L == 183600 else None}
     top = {k: round(v["ms"], 2) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:14]}
     fwd_names = {"conv0_stats", "conv0", "featproj_ln", "featproj", "pos_pad", "pos_conv", "pos_add", "encoder_ln", "qkv",
                  "attention", "out_proj", "ln1", "ffn1", "ffn_gelu", "ffn2", "ln2", "lm_head"}
@@ -56,7 +72,7 @@ def main():
     print(json.dumps({"metric": "expected_gradient_passes_per_sec", "value": args.rows / (ms / 1e3), "unit": "fwd+bwd passes/s",
                       "model": args.model, "attention_backward": "cuda_core" if args.simt_attention else "tensor_core", "num_samples": L, "frames": T, "rows_per_call": args.rows, "ms_per_call": ms,
                       "reference_recorded": {"passes_per_s": 114600 / 5586.0, "source": "evaluation.ipynb:463,513 (batch 1, GPU model not recorded)"},
-                      "profiled_ms": tot, "forward_share": fwd / tot, "top_steps_ms": top,
+                      "explain": explain, "profiled_ms": tot, "forward_share": fwd / tot, "top_steps_ms": top,
                       "clip_estimate_s": {"passes": T * 200, "seconds": T * 200 / (args.rows / (ms / 1e3))}}), flush=True)
 
 
