@@ -122,6 +122,12 @@ int w2s_eval_waveforms(w2s_handle* h, const float* x_dev, int64_t n, int64_t L, 
  * encoder (wav2vec2-base / -large); other configurations return an error. */
 int w2s_grad_waveforms(w2s_handle* h, const float* x_dev, int64_t n, int64_t L, int64_t ld,
                        const int32_t* frames_host, float* grad_dev, float* out_dev, void* stream);
+/* The same backward pass seeded with an upstream gradient over ALL output frames -- the vector-Jacobian product autograd
+ * asks of ModelWrapper.forward (B1 in SURVEY.md 8b: "autograd graph required"): gout[n, T'] (fp32, device) ->
+ * grad[r, :] = sum_t gout[r, t] d out[r, t] / d x[r, :], out[n, T'] = the max logits (may be NULL).  With it the
+ * reference's shap.GradientExplainer(wrapped_model, ...) runs unmodified on callbacks.ModelWrapper. */
+int w2s_vjp_waveforms(w2s_handle* h, const float* x_dev, int64_t n, int64_t L, int64_t ld, const float* gout_dev,
+                      float* grad_dev, float* out_dev, void* stream);
 /* Test hooks of the gradient path.  `on` bit 0: keep snapshots of the gradient after every encoder layer / conv layer
  * ("layer<l>", "h0", "conv<l>", "convu<l>", forward activations "f.*"); bit 1: run attention backward on the CUDA-core
  * cross-check kernels instead of the tensor-core contractions.  w2s_grad_peek copies a snapshot out (returns bytes copied, 0 = unknown name, < 0 = buffer

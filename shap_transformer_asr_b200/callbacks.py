@@ -19,11 +19,31 @@ import torch
 from .preprocess import pack_coalitions
 
 
+class _MaxLogitFunction(torch.autograd.Function):
+    """ModelWrapper's output as an autograd node: forward = the evaluation path, backward = the device
+    vector-Jacobian product (w2s_vjp_waveforms), so `outputs[:, idx]` can be differentiated w.r.t. the waveform exactly
+    as shap.GradientExplainer does (traceback in conformer_test.ipynb:95: `autograd.grad(selected, x)`)."""
+
+    @staticmethod
+    def forward(ctx, x, engine):
+        ctx.engine = engine
+        ctx.save_for_backward(x)
+        engine.set_targets("max")
+        return engine.eval_waveforms(x)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (x,) = ctx.saved_tensors
+        return ctx.engine.vjp_waveforms(x, gout), None
+
+
 class ModelWrapper(torch.nn.Module):
     """forward(x[B, L] | [B, 1, L] | [B, 1, 1, L]) -> max logit per frame [B, T'] (shap_calculation.py:31-50).
 
     The all-ones attention mask of the reference (:39) is a no-op in HF and is not modelled; the
-    DEBUG statistics of :45-47 (three device syncs per call) are deliberately not reproduced."""
+    DEBUG statistics of :45-47 (three device syncs per call) are deliberately not reproduced.  When the input
+    requires grad the output carries an autograd node whose backward is the device input-gradient path (configurations
+    it does not cover yet raise at backward time)."""
 
     def __init__(self, engine):
         super().__init__()
@@ -37,6 +57,8 @@ class ModelWrapper(torch.nn.Module):
         x = x.to(device=self.engine.device, dtype=torch.float32)
         if x.stride(-1) != 1:
             x = x.contiguous()
+        if torch.is_grad_enabled() and x.requires_grad:
+            return _MaxLogitFunction.apply(x, self.engine)
         self.engine.set_targets("max")
         return self.engine.eval_waveforms(x)
 

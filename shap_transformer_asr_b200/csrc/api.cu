@@ -151,6 +151,7 @@ struct w2s_handle {
   bool grad_attn_simt = false;        // cross-check: attention backward on the CUDA-core kernels (w2s_grad_debug bit 1)
   std::vector<int32_t> grad_frames_host;
   float *grad_out = nullptr, *grad_out_val = nullptr;
+  const float* grad_gout = nullptr;
 
   // per-call arguments of the plan's kernels (kernels.cuh: DynArgs), rewritten before every tile
   DynArgs* dyn_dev = nullptr;
@@ -1127,8 +1128,17 @@ int w2s_grad_waveforms(w2s_handle* h, const float* x_dev, int64_t n, int64_t L, 
   if (n == 0) return 0;
   if (n < 0 || !x_dev || !frames_host || !grad_dev) return fail(h, "grad_waveforms: null buffer");
   if (ld < L) return fail(h, "grad_waveforms: row stride smaller than the row length");
-  std::string e = run_grad(h, x_dev, ld, L, n, frames_host, grad_dev, out_dev, (cudaStream_t)stream);
+  std::string e = run_grad(h, x_dev, ld, L, n, frames_host, nullptr, grad_dev, out_dev, (cudaStream_t)stream);
   return e.empty() ? 0 : fail(h, "grad_waveforms: " + e);
+}
+
+int w2s_vjp_waveforms(w2s_handle* h, const float* x_dev, int64_t n, int64_t L, int64_t ld, const float* gout_dev,
+                      float* grad_dev, float* out_dev, void* stream) {
+  if (n == 0) return 0;
+  if (n < 0 || !x_dev || !gout_dev || !grad_dev) return fail(h, "vjp_waveforms: null buffer");
+  if (ld < L) return fail(h, "vjp_waveforms: row stride smaller than the row length");
+  std::string e = run_grad(h, x_dev, ld, L, n, nullptr, gout_dev, grad_dev, out_dev, (cudaStream_t)stream);
+  return e.empty() ? 0 : fail(h, "vjp_waveforms: " + e);
 }
 
 int w2s_grad_debug(w2s_handle* h, int on) {

@@ -205,6 +205,50 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
     dst[i] = tt == t ? __bfloat162float(w_head[(long long)arg * H + k]) : 0.f;
   }
 }
+// General vector-Jacobian seed for the same output: out[b, t] = max_v logits[b, t, v] for EVERY frame and an upstream
+// gradient gout[b, t] (what autograd hands to ModelWrapper's backward): d h[b, t, :] = gout[b, t] W_head[argmax(b, t), :].
+// One warp per (row, frame).
+__global__ void __launch_bounds__(256) head_vjp_kernel(const float* __restrict__ logits, int ldl, int V,
+                                                        const __nv_bfloat16* __restrict__ w_head, long long items, int H,
+                                                        const float* __restrict__ gout, float* __restrict__ dh,
+                                                        float* __restrict__ out_all) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long it = (long long)blockIdx.x * 8 + warp; it < items; it += (long long)gridDim.x * 8) {
+    const float* row = logits + it * ldl;
+    float best = -INFINITY;
+    int arg = 0;
+    for (int v = lane; v < V; v += 32) {
+      const float x = row[v];
+      if (x > best) {
+        best = x;
+        arg = v;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (ob > best || (ob == best && oa < arg)) {
+        best = ob;
+        arg = oa;
+      }
+    }
+    if (lane == 0 && out_all) out_all[it] = best;
+    const float g = gout[it];
+    for (int k = lane; k < H; k += 32) dh[it * H + k] = g * __bfloat162float(w_head[(long long)arg * H + k]);
+  }
+}
+std::string launch_head_vjp(const float* logits, int ldl, int V, const __nv_bfloat16* w_head, int n, int T, int H,
+                            const float* gout, float* dh, float* out_all, cudaStream_t s) {
+  const long long items = (long long)n * T;
+  if (items == 0) return "";
+  long long blocks = (items + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  head_vjp_kernel<<<(unsigned)blocks, 256, 0, s>>>(logits, ldl, V, w_head, items, H, gout, dh, out_all);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
 std::string launch_head_bwd(const float* logits, int ldl, int V, const __nv_bfloat16* w_head, int n, int T, int H,
                             const int* frames, float* dh, float* out_val, cudaStream_t s) {
   if (n == 0) return "";

@@ -324,7 +324,11 @@ struct GradBuilder {
       const int ldl = h->head_ldl, V = c.vocab_size;
       const bf16* hw = h->head_w;
       const int* fr = plan->frames;
-      add("head_bwd", [=](cudaStream_t s) { return launch_head_bwd(lg, ldl, V, hw, nn, T, H, fr, dA, hh->grad_out_val, s); });
+      // per-row target frame (w2s_grad_waveforms), or an upstream gradient over all frames (w2s_vjp_waveforms)
+      add("head_bwd", [=](cudaStream_t s) {
+        if (hh->grad_gout) return launch_head_vjp(lg, ldl, V, hw, nn, T, H, hh->grad_gout, dA, hh->grad_out_val, s);
+        return launch_head_bwd(lg, ldl, V, hw, nn, T, H, fr, dA, hh->grad_out_val, s);
+      });
       W2S_TRY(snap("layer" + std::to_string(NL), dA, sizeof(float) * rows * H));
     }
     for (int l = NL - 1; l >= 0; --l) {
@@ -516,15 +520,18 @@ std::string get_grad_plan(w2s_handle* h, int n, long long L, GradPlan** out) {
 
 // rows in tiles of `tile`; per tile: argument block, target frames, forward + backward
 std::string run_grad(w2s_handle* h, const float* x, long long ld, long long L, int64_t n, const int32_t* frames_host,
-                     float* grad, float* out_val, cudaStream_t s) {
+                     const float* gout, float* grad, float* out_val, cudaStream_t s) {
   W2S_TRY(grad_supported(h));
   W2S_TRY(grad_prepare_weights(h));
   const int64_t T = num_frames(h->cfg, L, nullptr);
-  for (int64_t i = 0; i < n; ++i)
-    if (frames_host[i] < 0 || frames_host[i] >= T)
-      return "target frame " + std::to_string(frames_host[i]) + " outside the clip's " + std::to_string(T) + " frames";
+  if (T <= 0) return "clip shorter than the conv receptive field";
+  if (frames_host) {
+    for (int64_t i = 0; i < n; ++i)
+      if (frames_host[i] < 0 || frames_host[i] >= T)
+        return "target frame " + std::to_string(frames_host[i]) + " outside the clip's " + std::to_string(T) + " frames";
+    h->grad_frames_host.assign(frames_host, frames_host + n);
+  }
   const int tile = h->grad_tile;
-  h->grad_frames_host.assign(frames_host, frames_host + n);
   for (int64_t k0 = 0; k0 < n; k0 += tile) {
     const int nt = (int)((n - k0) < tile ? (n - k0) : tile);
     GradPlan* pl = nullptr;
@@ -532,9 +539,11 @@ std::string run_grad(w2s_handle* h, const float* x, long long ld, long long L, i
     DynArgs d{};
     d.x = x + k0 * ld; d.ld = ld;
     set_dyn_kernel<<<1, 1, 0, s>>>(h->dyn_dev, d);
-    W2S_CUDA_OK(cudaMemcpyAsync(pl->frames, h->grad_frames_host.data() + k0, sizeof(int) * nt, cudaMemcpyHostToDevice, s));
+    if (frames_host)
+      W2S_CUDA_OK(cudaMemcpyAsync(pl->frames, h->grad_frames_host.data() + k0, sizeof(int) * nt, cudaMemcpyHostToDevice, s));
     h->grad_out = grad + k0 * L;
-    h->grad_out_val = out_val ? out_val + k0 : nullptr;
+    h->grad_gout = gout ? gout + k0 * T : nullptr;
+    h->grad_out_val = out_val ? out_val + k0 * (gout ? T : 1) : nullptr;
     for (const Step& st : pl->steps) {
       ProfRec rec;
       if (h->profiling) {

@@ -149,6 +149,8 @@ std::string launch_ln_bwd(const float* dy, const void* x, int x_fp32, long long 
                           const float* add, float* dx, __nv_bfloat16* dx16, cudaStream_t s);
 std::string launch_head_bwd(const float* logits, int ldl, int V, const __nv_bfloat16* w_head, int n, int T, int H,
                             const int* frames, float* dh, float* out_val, cudaStream_t s);
+std::string launch_head_vjp(const float* logits, int ldl, int V, const __nv_bfloat16* w_head, int n, int T, int H,
+                            const float* gout, float* dh, float* out_all, cudaStream_t s);
 std::string launch_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx, int B, int T, int H, int heads, float scale,
                             __nv_bfloat16* dqkv, float* stats, cudaStream_t s);
 std::string launch_attn_softmax_t(const float* S, int BH, int T, int Tp, __nv_bfloat16* P, __nv_bfloat16* PT, cudaStream_t s);

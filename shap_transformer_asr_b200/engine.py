@@ -200,6 +200,20 @@ class Engine:
                                                 self._stream()), "w2s_grad_waveforms")
         return grad, out
 
+    def vjp_waveforms(self, x: torch.Tensor, gout: torch.Tensor) -> torch.Tensor:
+        """Vector-Jacobian product of ModelWrapper's output [n, T'] (max logit per frame) w.r.t. the waveforms:
+        gout [n, T'] float32 device tensor -> grad [n, L]."""
+        if x.dim() != 2 or x.stride(1) != 1 or x.dtype != torch.float32 or not x.is_cuda:
+            raise ValueError("expected a float32 CUDA tensor [n, L] with contiguous rows")
+        n, L = x.shape
+        gout = gout.to(device=self.device, dtype=torch.float32).contiguous()
+        if tuple(gout.shape) != (n, self.num_frames(L)):
+            raise ValueError(f"upstream gradient must be [n, T'] = {(n, self.num_frames(L))}, got {tuple(gout.shape)}")
+        grad = torch.empty((n, L), dtype=torch.float32, device=self.device)
+        self._check(self.lib.w2s_vjp_waveforms(self._h, x.data_ptr(), n, L, x.stride(0), gout.data_ptr(), grad.data_ptr(),
+                                               None, self._stream()), "w2s_vjp_waveforms")
+        return grad
+
     def grad_debug(self, snapshots: bool = True, simt_attention: bool = False):
         """Test hooks: keep per-stage snapshots (grad_peek); run attention backward on the CUDA-core cross-check kernels."""
         self.lib.w2s_grad_debug(self._h, int(bool(snapshots)) | (2 if simt_attention else 0))

@@ -187,3 +187,35 @@ def test_gradient_path_rejects_unbuilt_configurations(P):
     with pytest.raises(RuntimeError, match="gradient path"):
         eng.grad_waveforms(torch.zeros((1, 4000), device="cuda"), [0])
     eng.close()
+
+
+def test_model_wrapper_output_is_differentiable_as_in_the_reference(P):
+    """B1 of SURVEY.md 8b: shap.GradientExplainer calls `outputs = self.model(*X); selected = outputs[:, idx]` and then
+    autograd.grad(selected, X) (conformer_test.ipynb:95).  callbacks.ModelWrapper serves exactly that: its output carries
+    an autograd node whose backward is the device vector-Jacobian product -- one-hot (one output index) and general
+    (a weighted sum over frames) upstream gradients against torch autograd on the transformers model."""
+    cfg = VARIANTS["tiny_group"]
+    model = build_model(cfg)
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((5, 7000)).astype(np.float32)
+    T = cfg.num_frames(7000)
+    eng = P.Engine(model, cfg, max_batch=8)
+    wrap = P.ModelWrapper(eng)
+    xg = torch.from_numpy(x).cuda().requires_grad_(True)
+    out = wrap(xg[:, None, :])                                   # [B, 1, L] as shap hands it over (shap_calculation.py:33-36)
+    assert out.shape == (5, T) and out.requires_grad
+    idx = 9
+    (g_one,) = torch.autograd.grad(out[:, idx].sum(), xg, retain_graph=True)
+    w = torch.from_numpy(rng.standard_normal((5, T)).astype(np.float32)).cuda()
+    (g_gen,) = torch.autograd.grad((out * w).sum(), xg)
+    xr = torch.tensor(x, requires_grad=True)
+    ref_out = model(xr).logits.max(-1).values
+    (r_one,) = torch.autograd.grad(ref_out[:, idx].sum(), xr, retain_graph=True)
+    (r_gen,) = torch.autograd.grad((ref_out * w.cpu()).sum(), xr)
+    e1, e2 = rel(g_one.cpu().numpy(), r_one.numpy()), rel(g_gen.cpu().numpy(), r_gen.numpy())
+    print(f"ModelWrapper autograd: one-hot max rel err {e1:.3e}; weighted-sum max rel err {e2:.3e}")
+    assert np.abs(out.detach().cpu().numpy() - ref_out.detach().numpy()).max() < 0.025 * ref_out.abs().max().item()
+    assert e1 < GRAD_TOL and e2 < GRAD_TOL
+    # without requires_grad the wrapper stays on the evaluation path (no autograd node, no saved activations)
+    assert not wrap(torch.from_numpy(x).cuda()).requires_grad
+    eng.close()
