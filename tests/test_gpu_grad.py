@@ -206,10 +206,16 @@ def test_model_wrapper_output_is_differentiable_as_in_the_reference(P):
     assert out.shape == (5, T) and out.requires_grad
     idx = 9
     (g_one,) = torch.autograd.grad(out[:, idx].sum(), xg, retain_graph=True)
-    w = torch.from_numpy(rng.standard_normal((5, T)).astype(np.float32)).cuda()
-    (g_gen,) = torch.autograd.grad((out * w).sum(), xg)
     xr = torch.tensor(x, requires_grad=True)
-    ref_out = model(xr).logits.max(-1).values
+    ref_logits = model(xr).logits
+    ref_out = ref_logits.max(-1).values
+    # max over the vocabulary is not differentiable across a tie: weight only the frames whose top-2 margin is clear of
+    # the bf16 logit error (random-init logits are nearly flat, so several frames are within it)
+    top2 = ref_logits.detach().topk(2, -1).values
+    clear = ((top2[..., 0] - top2[..., 1]) > 0.05).float()
+    assert clear.sum() >= 10
+    w = (torch.from_numpy(rng.standard_normal((5, T)).astype(np.float32)) * clear).cuda()
+    (g_gen,) = torch.autograd.grad((out * w).sum(), xg)
     (r_one,) = torch.autograd.grad(ref_out[:, idx].sum(), xr, retain_graph=True)
     (r_gen,) = torch.autograd.grad((ref_out * w.cpu()).sum(), xr)
     e1, e2 = rel(g_one.cpu().numpy(), r_one.numpy()), rel(g_gen.cpu().numpy(), r_gen.numpy())
