@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(256, 2) conv0_mma_kernel(const Conv0Params p, 
 // window through the Gram matrix of the filter bank, as in the CUDA-core kernel this replaces.
 constexpr int C0L_K = 48, C0L_LDA = 112;   // 112-byte row pitch: 7 x 16 B, conflict-free ldmatrix
 
-template <int KW>
+template <int KW, bool PRE>
 __global__ void __launch_bounds__(256, 2) conv0_ln_mma_kernel(const Conv0Params p, int FT) {
   extern __shared__ __align__(16) uint8_t smem_ln[];
   __shared__ uint32_t zs[64];
@@ -409,6 +409,7 @@ __global__ void __launch_bounds__(256, 2) conv0_ln_mma_kernel(const Conv0Params 
       ex2 = fmaf(gj, xv[j], ex2);
     }
     const float rstd = rsqrtf(fmaxf(ex2 - mean * mean, 0.f) + 1e-5f);
+    if (PRE && p.ln_rstd_out) p.ln_rstd_out[(long long)row * p.T0 + f0 + f] = rstd;   // kept for the backward pass
     auto split3 = [&](float v, int at) {   // (hi, lo, hi): pairs with (hi, hi, lo) on the B side
       const __nv_bfloat16 hi = __float2bfloat16_rn(v);
       ar[at] = hi;
@@ -467,7 +468,8 @@ __global__ void __launch_bounds__(256, 2) conv0_ln_mma_kernel(const Conv0Params 
           uint32_t pk[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float2 y = gelu_erf2(make_float2(c[4 * h + q][2 * r], c[4 * h + q][2 * r + 1]));
+            const float2 a = make_float2(c[4 * h + q][2 * r], c[4 * h + q][2 * r + 1]);
+            const float2 y = PRE ? a : gelu_erf2(a);
             pk[q] = pack_bf16x2(y.x, y.y);
           }
           *reinterpret_cast<uint4*>(out + (long long)f * p.C + h * 32) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -521,12 +523,14 @@ std::string launch_conv0(const Conv0Params& p, bool layer_norm, cudaStream_t s) 
     const size_t smem = (size_t)FT * C0L_LDA + (size_t)(FT * p.stride + p.kw + 4) * sizeof(float);
     static bool attr = false;
     if (!attr) {
-      W2S_CUDA_OK(cudaFuncSetAttribute(conv0_ln_mma_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      W2S_CUDA_OK(cudaFuncSetAttribute(conv0_ln_mma_kernel<10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      W2S_CUDA_OK(cudaFuncSetAttribute(conv0_ln_mma_kernel<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       attr = true;
     }
     if (smem > 100 * 1024) return "conv0 (layer norm): stride too large for the staged window";
     dim3 grid((p.T0 + FT - 1) / FT, p.n);
-    W2S_CUDA_OK(launch_pdl(conv0_ln_mma_kernel<10>, grid, dim3(p.C / 2), smem, s, 1, p, FT));
+    if (p.pre_act) W2S_CUDA_OK(launch_pdl(conv0_ln_mma_kernel<10, true>, grid, dim3(p.C / 2), smem, s, 1, p, FT));
+    else W2S_CUDA_OK(launch_pdl(conv0_ln_mma_kernel<10, false>, grid, dim3(p.C / 2), smem, s, 1, p, FT));
     W2S_CUDA_OK(cudaGetLastError());
     return "";
   }

@@ -96,8 +96,8 @@ std::string launch_grad_cast(const float* g, const __nv_bfloat16* u, __nv_bfloat
 // LayerNorm backward w.r.t. its input, one warp per row:
 //   xhat = (x - mean) rstd,  g = dy gamma,  dx = rstd (g - mean(g) - xhat mean(g xhat))  (+ add)
 // x is the saved LayerNorm INPUT (fp32 or bf16); statistics are recomputed from it (two-pass, fp32).
-template <bool X_F32>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const void* __restrict__ x, long long rows,
+template <bool X_F32, bool DY_F32>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const void* dy, const void* __restrict__ x, long long rows,
                                                       int H, const float* __restrict__ gamma, float eps,
                                                       const float* __restrict__ add, float* __restrict__ dx,
                                                       __nv_bfloat16* __restrict__ dx16) {
@@ -131,7 +131,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
   for (int i = 0; i < MAXV; ++i) {
     const int idx = lane + 32 * i;
     float g = 0.f;
-    if (idx < H) g = dy[row * H + idx] * __ldg(gamma + idx);
+    if (idx < H) {
+      if constexpr (DY_F32) g = reinterpret_cast<const float*>(dy)[row * H + idx];
+      else g = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(dy)[row * H + idx]);
+      g *= __ldg(gamma + idx);
+    }
     gv[i] = g;
     xv[i] = (xv[i] - mean) * rstd;   // xhat
     if (idx < H) {
@@ -151,13 +155,15 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
     }
   }
 }
-std::string launch_ln_bwd(const float* dy, const void* x, int x_fp32, long long rows, int H, const float* gamma, float eps,
-                          const float* add, float* dx, __nv_bfloat16* dx16, cudaStream_t s) {
+std::string launch_ln_bwd(const void* dy, const void* x, int x_fp32, long long rows, int H, const float* gamma, float eps,
+                          const float* add, float* dx, __nv_bfloat16* dx16, cudaStream_t s, int dy_fp32) {
   if (H > 1024) return "ln_bwd: H > 1024 not supported";
   if (rows == 0) return "";
   const unsigned grid = (unsigned)((rows + 7) / 8);
-  if (x_fp32) ln_bwd_kernel<true><<<grid, 256, 0, s>>>(dy, x, rows, H, gamma, eps, add, dx, dx16);
-  else ln_bwd_kernel<false><<<grid, 256, 0, s>>>(dy, x, rows, H, gamma, eps, add, dx, dx16);
+  if (x_fp32 && dy_fp32) ln_bwd_kernel<true, true><<<grid, 256, 0, s>>>(dy, x, rows, H, gamma, eps, add, dx, dx16);
+  else if (x_fp32) ln_bwd_kernel<true, false><<<grid, 256, 0, s>>>(dy, x, rows, H, gamma, eps, add, dx, dx16);
+  else if (dy_fp32) ln_bwd_kernel<false, true><<<grid, 256, 0, s>>>(dy, x, rows, H, gamma, eps, add, dx, dx16);
+  else ln_bwd_kernel<false, false><<<grid, 256, 0, s>>>(dy, x, rows, H, gamma, eps, add, dx, dx16);
   W2S_CUDA_OK(cudaGetLastError());
   return "";
 }
@@ -678,6 +684,58 @@ std::string launch_conv0_bwd(const __nv_bfloat16* du, const __nv_bfloat16* u, in
   gn_bwd_stats_kernel<<<dim3(C / 64, n), 256, 0, s>>>(du, u, T0, C, gamma, beta, m12);
   conv0_bwd_taps_kernel<10><<<dim3((unsigned)((T0 + 7) / 8 > 1024 ? 1024 : (T0 + 7) / 8), n), 256, 0, s>>>(du, u, T0, C, w, gn_a, gamma,
                                                                                                           beta, m12, g);
+  conv0_bwd_gather_kernel<<<dim3((unsigned)((L + 255) / 256 > 1024 ? 1024 : (L + 255) / 256), n), 256, 0, s>>>(g, T0, kw, stride, L, dx, ld);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+// conv0 + LayerNorm over channels (feat_extract_norm = "layer", HF wav2vec2/modeling_wav2vec2.py:275-299), backward to the
+// waveform.  u = gamma xhat + beta with xhat = (c0 - mean_f) rstd_f per frame f; du given, rstd_f saved by the forward pass:
+//   d c0[f, c] = rstd_f (g - mean_c g - xhat mean_c (g xhat)),  g = du gamma,  xhat = (u - beta) / gamma
+//   taps[f][j] = sum_c w[c][j] d c0[f, c];  d x[i] = sum of the taps that reach sample i (conv0_bwd_gather_kernel)
+template <int KW>
+__global__ void __launch_bounds__(256) conv0_ln_bwd_taps_kernel(const __nv_bfloat16* __restrict__ du, const __nv_bfloat16* __restrict__ u,
+                                                                 const float* __restrict__ rstd, int T0, int C,
+                                                                 const float* __restrict__ w, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, float* __restrict__ g) {
+  const int row = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = blockIdx.x * 8 + warp; t < T0; t += gridDim.x * 8) {
+    const long long o0 = ((long long)row * T0 + t) * C;
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float gc = __bfloat162float(du[o0 + c]) * gamma[c];
+      const float xh = (__bfloat162float(u[o0 + c]) - beta[c]) / gamma[c];
+      s1 += gc;
+      s2 = fmaf(gc, xh, s2);
+    }
+    const float m1 = warp_sum(s1) / (float)C, m2 = warp_sum(s2) / (float)C;
+    const float rs = rstd[(long long)row * T0 + t];
+    float acc[KW];
+#pragma unroll
+    for (int j = 0; j < KW; ++j) acc[j] = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float gc = __bfloat162float(du[o0 + c]) * gamma[c];
+      const float xh = (__bfloat162float(u[o0 + c]) - beta[c]) / gamma[c];
+      const float dc = rs * (gc - m1 - xh * m2);
+#pragma unroll
+      for (int j = 0; j < KW; ++j) acc[j] = fmaf(__ldg(w + c * KW + j), dc, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < KW; ++j) acc[j] = warp_sum(acc[j]);
+    if (lane == 0) {
+      float* dst = g + ((long long)row * T0 + t) * KW;
+#pragma unroll
+      for (int j = 0; j < KW; ++j) dst[j] = acc[j];
+    }
+  }
+}
+std::string launch_conv0_ln_bwd(const __nv_bfloat16* du, const __nv_bfloat16* u, const float* rstd, int n, long long L, int T0, int C,
+                                int kw, int stride, const float* w, const float* gamma, const float* beta, float* g, float* dx,
+                                long long ld, cudaStream_t s) {
+  if (kw != 10) return "conv0 backward: only kernel width 10 is implemented";
+  if (n == 0) return "";
+  conv0_ln_bwd_taps_kernel<10><<<dim3((unsigned)((T0 + 7) / 8 > 1024 ? 1024 : (T0 + 7) / 8), n), 256, 0, s>>>(du, u, rstd, T0, C, w, gamma, beta, g);
   conv0_bwd_gather_kernel<<<dim3((unsigned)((L + 255) / 256 > 1024 ? 1024 : (L + 255) / 256), n), 256, 0, s>>>(g, T0, kw, stride, L, dx, ld);
   W2S_CUDA_OK(cudaGetLastError());
   return "";

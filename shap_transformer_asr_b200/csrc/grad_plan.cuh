@@ -2,8 +2,9 @@
 // shap_calculation.py:125-162): forward pass with saved activations + backward pass to the waveform, for one batch tile.
 // Included by api.cu inside its anonymous namespace (it needs w2s_handle / Step / PlanBuilder::plain).
 //
-// Scope of this first slice: Wav2Vec2ForCTC with feat_extract_norm = "group", no conv bias, post-LN encoder, GELU
-// (facebook/wav2vec2-base-960h -- the model the reference runs -- and wav2vec2-large-960h).  Only d(output)/d(input) is
+// Scope of this slice: Wav2Vec2ForCTC -- both front ends (feat_extract_norm = "group" / "layer") and both encoder orders
+// (post-LN: facebook/wav2vec2-base-960h, the model the reference runs, and wav2vec2-large-960h; stable-LN: the
+// wav2vec2-large-lv60 family), GELU.  The conformer encoder is not built.  Only d(output)/d(input) is
 // computed: no weight gradients.  Every dense backward contraction dX = dY W runs on the tcgen05 contraction kernels of
 // the forward pass with pre-transposed weights; attention backward and the normalisation / activation / conv-gather
 // steps are CUDA-core kernels (grad.cu).
@@ -40,8 +41,6 @@ struct GradPlan {
 std::string grad_supported(const w2s_handle* h) {
   const w2s_config& c = h->cfg;
   if (c.kind != 0) return "gradient path: only Wav2Vec2ForCTC is built (conformer: not yet)";
-  if (c.feat_extract_norm != 0 || c.conv_bias) return "gradient path: only the group-norm front end without conv bias is built";
-  if (c.do_stable_layer_norm) return "gradient path: only the post-LN encoder is built";
   if (c.hidden_act != 0) return "gradient path: only GELU is built";
   if (c.hidden_size != c.num_attention_heads * 64) return "gradient path: head_dim must be 64";
   if (c.num_conv_pos_embeddings % 2) return "gradient path: odd positional-conv kernels are not built";
@@ -129,6 +128,13 @@ struct GradBuilder {
       W2S_TRY(alloc(&u[l], (size_t)n * Tl[l] * c.conv_dim[l]));
       W2S_TRY(alloc(&y[l], (size_t)n * Tl[l] * c.conv_dim[l]));
     }
+    const bool layer = c.feat_extract_norm == 1, stable = c.do_stable_layer_norm != 0;
+    std::vector<bf16*> cpre(NC, nullptr);   // layer-norm front end: conv + bias, the input of the per-frame LayerNorm
+    float* ln_rstd0 = nullptr;              // and conv0's per-frame rstd
+    if (layer) {
+      for (int l = 1; l < NC; ++l) W2S_TRY(alloc(&cpre[l], (size_t)n * Tl[l] * c.conv_dim[l]));
+      W2S_TRY(alloc(&ln_rstd0, (size_t)n * Tl[0]));
+    }
     float *gn_a = nullptr, *gn_b = nullptr;
     bf16* gn_wb = nullptr;
     W2S_TRY(alloc(&gn_a, (size_t)n * C0));
@@ -156,10 +162,11 @@ struct GradBuilder {
       W2S_TRY(alloc(&lb[l].s2, (size_t)rows * H));
     }
     // backward
-    float *dA = nullptr, *dS = nullptr, *attn_stats = nullptr, *dFp = nullptr, *m12 = nullptr, *gtap = nullptr;
+    float *dA = nullptr, *dS = nullptr, *dT = nullptr, *attn_stats = nullptr, *dFp = nullptr, *m12 = nullptr, *gtap = nullptr;
     bf16 *dS16 = nullptr, *dF = nullptr, *dC = nullptr, *dQKV = nullptr, *dcol = nullptr;
     W2S_TRY(alloc(&dA, (size_t)rows * H));
     W2S_TRY(alloc(&dS, (size_t)rows * H));
+    if (stable) W2S_TRY(alloc(&dT, (size_t)rows * H));
     W2S_TRY(alloc(&dS16, (size_t)rows * H));
     W2S_TRY(alloc(&dF, (size_t)rows * I));
     W2S_TRY(alloc(&dC, (size_t)rows * H));
@@ -202,12 +209,15 @@ struct GradBuilder {
       Conv0Params cp{};
       cp.dyn = h->dyn_dev;
       cp.n = n; cp.L = (int)L; cp.T0 = Tl[0]; cp.C = C0; cp.kw = c.conv_kernel[0]; cp.stride = c.conv_stride[0];
-      cp.w = h->conv0_w; cp.bias = nullptr; cp.gamma = h->norm0_g; cp.beta = h->norm0_b;
+      cp.w = h->conv0_w; cp.bias = layer ? h->conv0_b : nullptr; cp.gamma = h->norm0_g; cp.beta = h->norm0_b;
       cp.gn_a = gn_a; cp.gn_b = gn_b; cp.gn_wb = gn_wb;
+      cp.ln_wbar = h->ln0_wbar; cp.ln_gram = h->ln0_gram; cp.ln_wb = h->ln0_wb;
+      cp.ln_bmean = h->ln0_bmean; cp.ln_b2mean = h->ln0_b2mean; cp.ln_wb48 = h->ln0_wb48; cp.ln_rstd_out = ln_rstd0;
       cp.out = u[0];
       cp.pre_act = 1;   // store the normalised pre-activation; GELU follows as its own step
-      add("conv0_stats", [=](cudaStream_t s) { return launch_conv0_stats(cp, s); });
-      add("conv0", [=](cudaStream_t s) { return launch_conv0(cp, false, s); });
+      if (layer && !h->ln0_wb48) return "gradient path: the layer-norm conv0 needs the tensor-core form (64..512 channels)";
+      if (!layer) add("conv0_stats", [=](cudaStream_t s) { return launch_conv0_stats(cp, s); });
+      add("conv0", [=](cudaStream_t s) { return launch_conv0(cp, layer, s); });
       const long long ne = (long long)n * Tl[0] * C0;
       bf16 *uu = u[0], *yy = y[0];
       add("conv0_gelu", [=](cudaStream_t s) { return launch_gelu_fwd(uu, yy, ne, s); });
@@ -222,11 +232,19 @@ struct GradBuilder {
       p.a_row_stride = (long long)st * Cin; p.a_batch_stride = (long long)Tin * Cin;
       p.a_kb_per_row = st * Cin / 64; p.a_g_col = 0;
       p.w = h->conv_w[l]; p.M = Tout; p.N = Cout; p.K = kw * Cin; p.Bz = n; p.G = 1;
+      p.epi.bias = h->conv_b[l];
       p.epi.act = ACT_NONE;
-      p.epi.out = u[l]; p.epi.ldb = (long long)Tout * Cout; p.epi.ldm = Cout;
+      p.epi.out = layer ? cpre[l] : u[l]; p.epi.ldb = (long long)Tout * Cout; p.epi.ldm = Cout;
       W2S_TRY(add_gemm("conv" + std::to_string(l), p));
       const long long ne = (long long)n * Tout * Cout;
       bf16 *uu = u[l], *yy = y[l];
+      if (layer) {
+        const bf16* cc = cpre[l];
+        const float *lg = h->conv_ln_g[l], *lb2 = h->conv_ln_b[l];
+        const long long lrows = (long long)n * Tout;
+        add("conv" + std::to_string(l) + "_ln",
+            [=](cudaStream_t s) { return launch_layernorm(cc, 0, lrows, Cout, lg, lb2, 1e-5f, ACT_NONE, uu, nullptr, s); });
+      }
       add("conv" + std::to_string(l) + "_gelu", [=](cudaStream_t s) { return launch_gelu_fwd(uu, yy, ne, s); });
       W2S_TRY(snap("f.convu" + std::to_string(l), u[l], sizeof(bf16) * (size_t)ne));
     }
@@ -254,8 +272,10 @@ struct GradBuilder {
       add("pos_add", [=](cudaStream_t s) { return launch_add_gelu(h0, upos, pre0, rows * H, s); });
       const float *g = h->enc_ln_g, *b = h->enc_ln_b;
       const float eps = c.layer_norm_eps;
-      add("encoder_ln", [=](cudaStream_t s) { return launch_layernorm(pre0, 1, rows, H, g, b, eps, ACT_NONE, hb, nullptr, s); });
-      W2S_TRY(snap("f.layer0", hb, sizeof(bf16) * (size_t)rows * H));
+      if (!stable) {
+        add("encoder_ln", [=](cudaStream_t s) { return launch_layernorm(pre0, 1, rows, H, g, b, eps, ACT_NONE, hb, nullptr, s); });
+        W2S_TRY(snap("f.layer0", hb, sizeof(bf16) * (size_t)rows * H));
+      }
     }
     AttnParams ap{};
     ap.ctx = ctx; ap.B = n; ap.T = T; ap.Tp = (T + 63) / 64 * 64; ap.H = H;
@@ -267,6 +287,13 @@ struct GradBuilder {
       const LayerW& w = h->layers[l];
       const GradLayerBuf B = lb[l];
       const std::string ls = "L" + std::to_string(l) + ".";
+      // stable-LN (pre-LN) layers: r1 = residual stream entering the layer (fp32), s1 = r1 + attention(LN1(r1)),
+      // s2 = s1 + ffn(LN2(s1)); post-LN layers: s1 = hb + attention(hb), h1 = LN1(s1), s2 = h1 + ffn(h1), hb' = LN2(s2)
+      const float* r1 = l == 0 ? pre0 : lb[l - 1].s2;
+      if (stable) {
+        const float *g = w.ln1_g, *b = w.ln1_b;
+        add(ls + "ln1", [=](cudaStream_t s) { return launch_layernorm(r1, 1, rows, H, g, b, eps, ACT_NONE, hb, nullptr, s); });
+      }
       {
         GemmProblem p = PlanBuilder::plain(hb, rows, H, w.wqkv, 3 * H);
         p.epi.bias = w.bqkv; p.epi.out = B.qkv;
@@ -282,14 +309,20 @@ struct GradBuilder {
       }
       {
         GemmProblem p = PlanBuilder::plain(ctx, rows, H, w.wo, H);
-        p.epi.bias = w.bo; p.epi.residual = hb; p.epi.res_fp32 = 0;
+        p.epi.bias = w.bo;
+        if (stable) {
+          p.epi.residual = r1; p.epi.res_fp32 = 1;
+        } else {
+          p.epi.residual = hb; p.epi.res_fp32 = 0;
+        }
         p.epi.out = B.s1; p.epi.out_fp32 = 1;
         W2S_TRY(add_gemm(ls + "out_proj", p));
       }
       {
-        const float *g = w.ln1_g, *b = w.ln1_b;
+        const float *g = stable ? w.ln2_g : w.ln1_g, *b = stable ? w.ln2_b : w.ln1_b;
         const float* in = B.s1;
-        add(ls + "ln1", [=](cudaStream_t s) { return launch_layernorm(in, 1, rows, H, g, b, eps, ACT_NONE, h1, nullptr, s); });
+        add(ls + (stable ? "ln2" : "ln1"),
+            [=](cudaStream_t s) { return launch_layernorm(in, 1, rows, H, g, b, eps, ACT_NONE, h1, nullptr, s); });
       }
       {
         GemmProblem p = PlanBuilder::plain(h1, rows, H, w.w1, I);
@@ -300,16 +333,26 @@ struct GradBuilder {
       }
       {
         GemmProblem p = PlanBuilder::plain(ffn, rows, I, w.w2, H);
-        p.epi.bias = w.b2; p.epi.residual = h1; p.epi.res_fp32 = 0;
+        p.epi.bias = w.b2;
+        if (stable) {
+          p.epi.residual = B.s1; p.epi.res_fp32 = 1;
+        } else {
+          p.epi.residual = h1; p.epi.res_fp32 = 0;
+        }
         p.epi.out = B.s2; p.epi.out_fp32 = 1;
         W2S_TRY(add_gemm(ls + "ffn2", p));
       }
-      {
+      if (!stable) {
         const float *g = w.ln2_g, *b = w.ln2_b;
         const float* in = B.s2;
         add(ls + "ln2", [=](cudaStream_t s) { return launch_layernorm(in, 1, rows, H, g, b, eps, ACT_NONE, hb, nullptr, s); });
+        W2S_TRY(snap("f.layer" + std::to_string(l + 1), hb, sizeof(bf16) * (size_t)rows * H));
       }
-      W2S_TRY(snap("f.layer" + std::to_string(l + 1), hb, sizeof(bf16) * (size_t)rows * H));
+    }
+    if (stable) {   // the encoder's LayerNorm comes last (HF wav2vec2/modeling_wav2vec2.py: Wav2Vec2EncoderStableLayerNorm)
+      const float *g = h->enc_ln_g, *b = h->enc_ln_b;
+      const float* in = lb[NL - 1].s2;
+      add("encoder_ln", [=](cudaStream_t s) { return launch_layernorm(in, 1, rows, H, g, b, eps, ACT_NONE, hb, nullptr, s); });
     }
     {
       GemmProblem p = PlanBuilder::plain(hb, rows, H, h->head_w, h->head_ldl);
@@ -319,50 +362,8 @@ struct GradBuilder {
     }
 
     // ================================ backward to the waveform ===================================================
-    {
-      const float* lg = plan->logits;
-      const int ldl = h->head_ldl, V = c.vocab_size;
-      const bf16* hw = h->head_w;
-      const int* fr = plan->frames;
-      // per-row target frame (w2s_grad_waveforms), or an upstream gradient over all frames (w2s_vjp_waveforms)
-      add("head_bwd", [=](cudaStream_t s) {
-        if (hh->grad_gout) return launch_head_vjp(lg, ldl, V, hw, nn, T, H, hh->grad_gout, dA, hh->grad_out_val, s);
-        return launch_head_bwd(lg, ldl, V, hw, nn, T, H, fr, dA, hh->grad_out_val, s);
-      });
-      W2S_TRY(snap("layer" + std::to_string(NL), dA, sizeof(float) * rows * H));
-    }
-    for (int l = NL - 1; l >= 0; --l) {
-      const LayerW& w = h->layers[l];
-      const GradW& gw = h->gradw[l];
-      const GradLayerBuf B = lb[l];
-      const std::string ls = "B" + std::to_string(l) + ".";
-      {
-        const float* g = w.ln2_g;
-        const float* x = B.s2;
-        add(ls + "ln2_bwd", [=](cudaStream_t s) { return launch_ln_bwd(dA, x, 1, rows, H, g, eps, nullptr, dS, dS16, s); });
-      }
-      {
-        GemmProblem p = PlanBuilder::plain(dS16, rows, H, gw.w2T, I);
-        p.epi.out = dF;
-        W2S_TRY(add_gemm(ls + "ffn2_bwd", p));
-        const bf16* uu = B.u;
-        add(ls + "gelu_bwd", [=](cudaStream_t s) { return launch_gelu_bwd(uu, dF, rows * I, s); });
-      }
-      {
-        GemmProblem p = PlanBuilder::plain(dF, rows, I, gw.w1T, H);
-        p.epi.residual = dS; p.epi.res_fp32 = 1; p.epi.out = dA; p.epi.out_fp32 = 1;
-        W2S_TRY(add_gemm(ls + "ffn1_bwd", p));
-      }
-      {
-        const float* g = w.ln1_g;
-        const float* x = B.s1;
-        add(ls + "ln1_bwd", [=](cudaStream_t s) { return launch_ln_bwd(dA, x, 1, rows, H, g, eps, nullptr, dS, dS16, s); });
-      }
-      {
-        GemmProblem p = PlanBuilder::plain(dS16, rows, H, gw.woT, H);
-        p.epi.out = dC;
-        W2S_TRY(add_gemm(ls + "out_proj_bwd", p));
-      }
+    // attention backward of one layer: (saved q | k | v, dC = d ctx) -> dQKV; shared by both encoder orders
+    auto add_attention_bwd = [&](const std::string& ls, const GradLayerBuf& B) -> std::string {
       if (!attn_tc) {
         const bf16* q = B.qkv;
         add(ls + "attention_bwd", [=](cudaStream_t s) { return launch_attn_bwd(q, dC, nn, T, H, heads, 0.125f, dQKV, attn_stats, s); });
@@ -435,6 +436,101 @@ struct GradBuilder {
           W2S_TRY(add_gemm(ls + "attn_dv", p));
         }
       }
+      return "";
+    };
+    {
+      const float* lg = plan->logits;
+      const int ldl = h->head_ldl, V = c.vocab_size;
+      const bf16* hw = h->head_w;
+      const int* fr = plan->frames;
+      float* seed = stable ? dT : dA;
+      // per-row target frame (w2s_grad_waveforms), or an upstream gradient over all frames (w2s_vjp_waveforms)
+      add("head_bwd", [=](cudaStream_t s) {
+        if (hh->grad_gout) return launch_head_vjp(lg, ldl, V, hw, nn, T, H, hh->grad_gout, seed, hh->grad_out_val, s);
+        return launch_head_bwd(lg, ldl, V, hw, nn, T, H, fr, seed, hh->grad_out_val, s);
+      });
+      if (stable) {   // final encoder LayerNorm: dA = d (residual stream after the last layer)
+        const float* g = h->enc_ln_g;
+        const float* x = lb[NL - 1].s2;
+        add("encoder_ln_bwd", [=](cudaStream_t s) { return launch_ln_bwd(dT, x, 1, rows, H, g, eps, nullptr, dA, nullptr, s); });
+      }
+      W2S_TRY(snap("layer" + std::to_string(NL), dA, sizeof(float) * rows * H));
+    }
+    for (int l = NL - 1; l >= 0 && stable; --l) {
+      // invariant: dA = d s2_l (gradient of the residual stream leaving layer l)
+      const LayerW& w = h->layers[l];
+      const GradW& gw = h->gradw[l];
+      const GradLayerBuf B = lb[l];
+      const std::string ls = "B" + std::to_string(l) + ".";
+      const float* r1 = l == 0 ? pre0 : lb[l - 1].s2;
+      add(ls + "cast", [=](cudaStream_t s) { return launch_grad_cast(dA, nullptr, dS16, rows * H, s); });
+      {
+        GemmProblem p = PlanBuilder::plain(dS16, rows, H, gw.w2T, I);
+        p.epi.out = dF;
+        W2S_TRY(add_gemm(ls + "ffn2_bwd", p));
+        const bf16* uu = B.u;
+        add(ls + "gelu_bwd", [=](cudaStream_t s) { return launch_gelu_bwd(uu, dF, rows * I, s); });
+      }
+      {
+        GemmProblem p = PlanBuilder::plain(dF, rows, I, gw.w1T, H);
+        p.epi.out = dT; p.epi.out_fp32 = 1;
+        W2S_TRY(add_gemm(ls + "ffn1_bwd", p));
+      }
+      {   // d s1 = d s2 + LN2^T (d h1)
+        const float* g = w.ln2_g;
+        const float* x = B.s1;
+        add(ls + "ln2_bwd", [=](cudaStream_t s) { return launch_ln_bwd(dT, x, 1, rows, H, g, eps, dA, dS, dS16, s); });
+      }
+      {
+        GemmProblem p = PlanBuilder::plain(dS16, rows, H, gw.woT, H);
+        p.epi.out = dC;
+        W2S_TRY(add_gemm(ls + "out_proj_bwd", p));
+      }
+      W2S_TRY(add_attention_bwd(ls, B));
+      {
+        GemmProblem p = PlanBuilder::plain(dQKV, rows, 3 * H, gw.wqkvT, H);
+        p.epi.out = dT; p.epi.out_fp32 = 1;
+        W2S_TRY(add_gemm(ls + "qkv_bwd", p));
+      }
+      {   // d r1 = d s1 + LN1^T (d hb)
+        const float* g = w.ln1_g;
+        add(ls + "ln1_bwd", [=](cudaStream_t s) { return launch_ln_bwd(dT, r1, 1, rows, H, g, eps, dS, dA, nullptr, s); });
+      }
+      W2S_TRY(snap("layer" + std::to_string(l), dA, sizeof(float) * rows * H));
+    }
+    for (int l = NL - 1; l >= 0 && !stable; --l) {
+      const LayerW& w = h->layers[l];
+      const GradW& gw = h->gradw[l];
+      const GradLayerBuf B = lb[l];
+      const std::string ls = "B" + std::to_string(l) + ".";
+      {
+        const float* g = w.ln2_g;
+        const float* x = B.s2;
+        add(ls + "ln2_bwd", [=](cudaStream_t s) { return launch_ln_bwd(dA, x, 1, rows, H, g, eps, nullptr, dS, dS16, s); });
+      }
+      {
+        GemmProblem p = PlanBuilder::plain(dS16, rows, H, gw.w2T, I);
+        p.epi.out = dF;
+        W2S_TRY(add_gemm(ls + "ffn2_bwd", p));
+        const bf16* uu = B.u;
+        add(ls + "gelu_bwd", [=](cudaStream_t s) { return launch_gelu_bwd(uu, dF, rows * I, s); });
+      }
+      {
+        GemmProblem p = PlanBuilder::plain(dF, rows, I, gw.w1T, H);
+        p.epi.residual = dS; p.epi.res_fp32 = 1; p.epi.out = dA; p.epi.out_fp32 = 1;
+        W2S_TRY(add_gemm(ls + "ffn1_bwd", p));
+      }
+      {
+        const float* g = w.ln1_g;
+        const float* x = B.s1;
+        add(ls + "ln1_bwd", [=](cudaStream_t s) { return launch_ln_bwd(dA, x, 1, rows, H, g, eps, nullptr, dS, dS16, s); });
+      }
+      {
+        GemmProblem p = PlanBuilder::plain(dS16, rows, H, gw.woT, H);
+        p.epi.out = dC;
+        W2S_TRY(add_gemm(ls + "out_proj_bwd", p));
+      }
+      W2S_TRY(add_attention_bwd(ls, B));
       {
         GemmProblem p = PlanBuilder::plain(dQKV, rows, 3 * H, gw.wqkvT, H);
         p.epi.residual = dS; p.epi.res_fp32 = 1; p.epi.out = dA; p.epi.out_fp32 = 1;
@@ -445,7 +541,13 @@ struct GradBuilder {
     {
       // encoder input: hb0 = LN(pre0), pre0 = h0 + gelu(pos_conv(h0))
       const float* g = h->enc_ln_g;
-      add("encoder_ln_bwd", [=](cudaStream_t s) { return launch_ln_bwd(dA, pre0, 1, rows, H, g, eps, nullptr, dS, nullptr, s); });
+      if (stable)   // the residual stream enters the first layer un-normalised: d pre0 = dA
+        add("pre0_copy", [=](cudaStream_t s) -> std::string {
+          W2S_CUDA_OK(cudaMemcpyAsync(dS, dA, sizeof(float) * rows * H, cudaMemcpyDeviceToDevice, s));
+          return "";
+        });
+      else
+        add("encoder_ln_bwd", [=](cudaStream_t s) { return launch_ln_bwd(dA, pre0, 1, rows, H, g, eps, nullptr, dS, nullptr, s); });
       add("pos_gelu_bwd", [=](cudaStream_t s) { return launch_grad_cast(dS, upos, dS16, rows * H, s); });
       add("pos_pad_bwd", [=](cudaStream_t s) { return launch_pos_pad(dS16, nn, T, H, G, kp, hp, s, kp / 2 - 1); });
       EpiParams e;
@@ -474,6 +576,13 @@ struct GradBuilder {
       const int Tin = Tl[l - 1], Tout = Tl[l];
       bf16* dul = plan->D[l & 1];
       bf16* dprev = plan->D[(l - 1) & 1];
+      if (layer) {   // through the per-frame LayerNorm: d (conv + bias) from d u_l, in place
+        const bf16* cc = cpre[l];
+        const float* lg = h->conv_ln_g[l];
+        const long long lrows = (long long)n * Tout;
+        add("conv" + std::to_string(l) + "_ln_bwd",
+            [=](cudaStream_t s) { return launch_ln_bwd(dul, cc, 0, lrows, Cout, lg, 1e-5f, nullptr, nullptr, dul, s, 0); });
+      }
       GemmProblem p = PlanBuilder::plain(dul, (long long)n * Tout, Cout, h->conv_wT[l], kw * Cin);
       p.epi.out = dcol;
       W2S_TRY(add_gemm("conv" + std::to_string(l) + "_bwd", p));
@@ -489,6 +598,7 @@ struct GradBuilder {
       const float *w0 = h->conv0_w, *gam = h->norm0_g, *bet = h->norm0_b;
       const long long LL = L;
       add("conv0_bwd", [=](cudaStream_t s) {
+        if (layer) return launch_conv0_ln_bwd(du0, u0, ln_rstd0, nn, LL, T0, C0, kw, st, w0, gam, bet, gtap, hh->grad_out, LL, s);
         return launch_conv0_bwd(du0, u0, nn, LL, T0, C0, kw, st, w0, gn_a, gam, bet, m12, gtap, hh->grad_out, LL, s);
       });
     }

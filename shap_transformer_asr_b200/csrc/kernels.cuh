@@ -50,6 +50,7 @@ struct Conv0Params {
   const float* ln_wb;    // [kw]       mean_c w[c][j] b[c]
   float ln_bmean, ln_b2mean;
   int pre_act;           // 1: store the normalised pre-activation (no GELU) -- forward of the gradient path
+  float* ln_rstd_out;    // [n, T0] (optional, layer-norm variant with pre_act): per-frame rstd, kept for the backward pass
   const __nv_bfloat16* ln_wb48;  // [C][48] (optional) B operand of conv0_ln_mma_kernel: filters, bias and affine terms
                                  // as bf16 hi/lo rows
   __nv_bfloat16* out;    // [n, T0, C] channels-last
@@ -145,8 +146,13 @@ std::string launch_gelu_fwd(const __nv_bfloat16* u, __nv_bfloat16* y, long long 
 std::string launch_gelu_bwd(const __nv_bfloat16* u, __nv_bfloat16* d, long long n, cudaStream_t s);
 std::string launch_add_gelu(const __nv_bfloat16* h0, const __nv_bfloat16* up, float* out, long long n, cudaStream_t s);
 std::string launch_grad_cast(const float* g, const __nv_bfloat16* u, __nv_bfloat16* out, long long n, cudaStream_t s);
-std::string launch_ln_bwd(const float* dy, const void* x, int x_fp32, long long rows, int H, const float* gamma, float eps,
-                          const float* add, float* dx, __nv_bfloat16* dx16, cudaStream_t s);
+// dy: fp32, or bf16 when dy_fp32 == 0 (then dx16 may alias dy: a warp reads its row before writing it)
+std::string launch_ln_bwd(const void* dy, const void* x, int x_fp32, long long rows, int H, const float* gamma, float eps,
+                          const float* add, float* dx, __nv_bfloat16* dx16, cudaStream_t s, int dy_fp32 = 1);
+// conv0 + LayerNorm over channels (layer-norm front ends), backward to the waveform
+std::string launch_conv0_ln_bwd(const __nv_bfloat16* du, const __nv_bfloat16* u, const float* rstd, int n, long long L, int T0, int C,
+                                int kw, int stride, const float* w, const float* gamma, const float* beta, float* g, float* dx,
+                                long long ld, cudaStream_t s);
 std::string launch_head_bwd(const float* logits, int ldl, int V, const __nv_bfloat16* w_head, int n, int T, int H,
                             const int* frames, float* dh, float* out_val, cudaStream_t s);
 std::string launch_head_vjp(const float* logits, int ldl, int V, const __nv_bfloat16* w_head, int n, int T, int H,

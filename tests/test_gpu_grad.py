@@ -36,14 +36,18 @@ def reference_grads(model, x, frames):
 
     w = model.wav2vec2
     NL = len(w.encoder.layers)
-    hooks.append(w.encoder.layer_norm.register_forward_hook(keep("layer0")))
+    stable = bool(model.config.do_stable_layer_norm)
+    # input of encoder layer 0: the LayerNorm'ed sum (post-LN encoders) / the un-normalised sum after dropout (stable-LN)
+    hooks.append((w.encoder.dropout if stable else w.encoder.layer_norm).register_forward_hook(keep("layer0")))
     for l, layer in enumerate(w.encoder.layers):
         hooks.append(layer.register_forward_hook(keep(f"layer{l + 1}")))
     hooks.append(w.feature_projection.register_forward_hook(keep("h0")))
     convs = w.feature_extractor.conv_layers
+    layer_norm_front = model.config.feat_extract_norm == "layer"
+    # "convu<l>": the pre-activation of conv layer l (after its norm, if it has one)
     hooks.append(convs[0].layer_norm.register_forward_hook(keep("convu0")))
     for l in range(1, len(convs)):
-        hooks.append(convs[l].conv.register_forward_hook(keep(f"convu{l}")))
+        hooks.append((convs[l].layer_norm if layer_norm_front else convs[l].conv).register_forward_hook(keep(f"convu{l}")))
     hooks.append(convs[-1].register_forward_hook(keep(f"conv{len(convs) - 1}")))
     xt = torch.tensor(x, requires_grad=True)
     logits = model(xt).logits
@@ -67,12 +71,20 @@ def cosine(a, b):
     return float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30))
 
 
-@pytest.mark.parametrize("attn", ["tensor_core", "cuda_core"])
-def test_gradient_stages_match_autograd_tiny(P, attn):
+def _chan_last(t, T_l):
+    """HF conv activations are [n, C, T] (LayerNorm'ed ones [n, T, C]); the path keeps [n, T, C]."""
+    a = t.numpy()
+    return a if a.shape[1] == T_l else a.transpose(0, 2, 1)
+
+
+@pytest.mark.parametrize("variant,attn", [("tiny_group", "tensor_core"), ("tiny_group", "cuda_core"),
+                                          ("tiny_layer_stable", "tensor_core")])
+def test_gradient_stages_match_autograd_tiny(P, variant, attn):
     """Every stage of the backward pass against autograd (tiny model): localises a wrong kernel to its stage.  Attention
     backward both as batched tensor-core contractions (the product path) and on the CUDA-core cross-check kernels."""
-    cfg = VARIANTS["tiny_group"]
+    cfg = VARIANTS[variant]
     model = build_model(cfg)
+    stable = cfg.do_stable_layer_norm
     rng = np.random.default_rng(0)
     x = rng.standard_normal((3, 6000)).astype(np.float32)
     T = cfg.num_frames(6000)
@@ -89,9 +101,11 @@ def test_gradient_stages_match_autograd_tiny(P, attn):
     fwd = []
     for l in range(NC):
         mine = eng.grad_peek(f"f.convu{l}", (3, lens[l], cfg.conv_dim[l]), torch.bfloat16).float().cpu().numpy()
-        fwd.append((f"convu{l}", rel(mine, g[f"f.convu{l}"].numpy().transpose(0, 2, 1))))
+        fwd.append((f"convu{l}", rel(mine, _chan_last(g[f"f.convu{l}"], lens[l]))))
     fwd.append(("h0", rel(eng.grad_peek("f.h0", (3, T, H), torch.bfloat16).float().cpu().numpy(), g["f.h0"].numpy())))
     for l in range(NL + 1):
+        if stable:
+            break          # the stable-LN forward keeps the fp32 residual stream, not a normalised bf16 copy per layer
         mine = eng.grad_peek(f"f.layer{l}", (3, T, H), torch.bfloat16).float().cpu().numpy()
         fwd.append((f"layer{l}", rel(mine, g[f"f.layer{l}"].numpy())))
     lg = eng.grad_peek("f.logits", (3, T, 32)).cpu().numpy()
@@ -103,10 +117,10 @@ def test_gradient_stages_match_autograd_tiny(P, attn):
         report.append((f"layer{l}", rel(mine, g[f"layer{l}"].numpy())))
     report.append(("h0", rel(eng.grad_peek("h0", (3, T, H)).cpu().numpy(), g["h0"].numpy())))
     mine = eng.grad_peek(f"conv{NC - 1}", (3, lens[-1], cfg.conv_dim[-1]), torch.bfloat16).float().cpu().numpy()
-    report.append((f"conv{NC - 1}", rel(mine, g[f"conv{NC - 1}"].numpy().transpose(0, 2, 1))))
+    report.append((f"conv{NC - 1}", rel(mine, _chan_last(g[f"conv{NC - 1}"], lens[-1]))))
     for l in range(NC - 2, -1, -1):
         mine = eng.grad_peek(f"convu{l}", (3, lens[l], cfg.conv_dim[l]), torch.bfloat16).float().cpu().numpy()
-        report.append((f"convu{l}", rel(mine, g[f"convu{l}"].numpy().transpose(0, 2, 1))))
+        report.append((f"convu{l}", rel(mine, _chan_last(g[f"convu{l}"], lens[l]))))
     report.append(("x", rel(grad.cpu().numpy(), gx)))
     print("gradient stages (max rel err vs autograd): " + "; ".join(f"{k} {v:.2e}" for k, v in report))
     assert max(v for _, v in fwd) < 0.03, fwd
@@ -118,11 +132,17 @@ def test_gradient_stages_match_autograd_tiny(P, attn):
 
 
 @pytest.mark.parametrize("name,n,L", [("tiny_group", 35, 9000), ("wav2vec2-base", 32, 16000), ("tiny_group", 3, 183600),
-                                      ("wav2vec2-large", 4, 16000)])
+                                      ("wav2vec2-large", 4, 16000), ("tiny_layer_stable", 34, 9000),
+                                      ("wav2vec2-large-lv60", 3, 16000)])
 def test_input_gradients_match_autograd_at_batch_32(P, name, n, L):
     """d (max logit of frame j) / d waveform for >= 32 rows with different target frames (one ragged tile for the tiny
     model: 32 + 3) against torch autograd on the transformers model."""
-    cfg = VARIANTS[name] if name in VARIANTS else MODELS[name]
+    if name == "wav2vec2-large-lv60":      # layer-norm front end with conv bias + stable-LN encoder at full width
+        import dataclasses
+        cfg = dataclasses.replace(MODELS["wav2vec2-large"], feat_extract_norm="layer", conv_bias=True,
+                                  do_stable_layer_norm=True, num_hidden_layers=6)
+    else:
+        cfg = VARIANTS[name] if name in VARIANTS else MODELS[name]
     model = build_model(cfg)
     rng = np.random.default_rng(n)
     x = rng.standard_normal((n, L)).astype(np.float32)
@@ -182,7 +202,7 @@ def test_expected_gradients_explainer_properties(P):
 
 
 def test_gradient_path_rejects_unbuilt_configurations(P):
-    cfg = VARIANTS["tiny_layer_stable"]
+    cfg = VARIANTS["tiny_conformer_rel"]
     eng = P.Engine(build_model(cfg), cfg, max_batch=2)
     with pytest.raises(RuntimeError, match="gradient path"):
         eng.grad_waveforms(torch.zeros((1, 4000), device="cuda"), [0])
