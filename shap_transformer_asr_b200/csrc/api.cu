@@ -72,6 +72,11 @@ __global__ void set_dyn_kernel(DynArgs* dst, const DynArgs v) { *dst = v; }
 // expected-gradients path: transposed dense weights of one encoder layer (dX = dY W runs as a contraction with W^T)
 struct GradW {
   bf16 *wqkvT = nullptr, *woT = nullptr, *w1T = nullptr, *w2T = nullptr;
+  // conformer: second macaron feed-forward, pointwise convs, rotary q|k and v projections, reversed depthwise taps
+  bf16 *f2w1T = nullptr, *f2w2T = nullptr, *pw1T = nullptr, *pw2T = nullptr, *wqkT = nullptr, *wvT = nullptr;
+  float* dw_flip = nullptr;
+  // relative positions, per clip length: linear_pos(pe) [2T'-1, H] and its per-head transpose [heads][64][Rp]
+  bf16 *pos_proj = nullptr, *pos_projT = nullptr;
 };
 struct GradPlan;
 
@@ -144,6 +149,8 @@ struct w2s_handle {
   bf16* conv_wT[W2S_MAX_CONV_LAYERS] = {};
   bf16* fp_wT = nullptr;
   bf16* pos_w_bwd = nullptr;          // flipped / transposed positional-conv filters (built at create)
+  float *grad_ones = nullptr, *grad_zeros = nullptr;   // [H]: identity scale / shift of the depthwise backward
+  std::vector<void*> grad_pos_allocs;                  // relative-position tables of the current grad_L
   std::map<int, std::shared_ptr<GradPlan>> grad_plans;
   long long grad_L = -1;
   int grad_tile = 32;
@@ -167,6 +174,7 @@ struct w2s_handle {
     }
     plans.clear();
     grad_plans.clear();
+    for (void* p : grad_pos_allocs) cudaFree(p);
     if (cap_stream) cudaStreamDestroy(cap_stream);
     if (dyn_dev) cudaFree(dyn_dev);
     if (clip) cudaFree(clip);

@@ -121,7 +121,8 @@ std::string launch_transpose_f32(const float* src, float* dst, int R, int C, cud
 
 // rotary: out[b, t, h, :] = x * cos(t) + rotate_half(x) * sin(t), angle[t, i] = t * base^(-2 (i mod hd/2) / hd)
 __global__ void __launch_bounds__(256) rotary_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int T, int H,
-                                                      int hd, float log2_base, __nv_bfloat16* __restrict__ out) {
+                                                      int hd, float log2_base, __nv_bfloat16* __restrict__ out,
+                                                      float sign) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * H) return;
   const long long r = i / H;
@@ -134,13 +135,14 @@ __global__ void __launch_bounds__(256) rotary_kernel(const __nv_bfloat16* __rest
   sincosf((float)t * inv_freq, &sn, &cs);
   const float xv = __bfloat162float(x[i]);
   const float other = d < half ? -__bfloat162float(x[i + half]) : __bfloat162float(x[i - half]);
-  out[i] = __float2bfloat16_rn(xv * cs + other * sn);
+  out[i] = __float2bfloat16_rn(xv * cs + other * (sign * sn));
 }
 std::string launch_rotary(const __nv_bfloat16* x, long long rows, int T, int H, int hd, int base, __nv_bfloat16* out,
-                          cudaStream_t s) {
+                          cudaStream_t s, int inverse) {
   if (rows == 0) return "";
   const long long n = rows * H;
-  rotary_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, rows, T, H, hd, log2f((float)base), out);
+  rotary_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, rows, T, H, hd, log2f((float)base), out,
+                                                                        inverse ? -1.0f : 1.0f);
   W2S_CUDA_OK(cudaGetLastError());
   return "";
 }

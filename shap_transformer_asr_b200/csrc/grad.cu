@@ -741,6 +741,146 @@ std::string launch_conv0_ln_bwd(const __nv_bfloat16* du, const __nv_bfloat16* u,
   return "";
 }
 
+// ---- conformer encoder (HF modeling_wav2vec2_conformer.py:568-630): activation, GLU, relative-position shift ----------
+// act'(u) for the encoder's activation (ACT2FN[config.hidden_act]): swish'(u) = s (1 + u (1 - s)), s = sigmoid(u)
+__device__ __forceinline__ float act_grad(float u, int act) {
+  if (act == ACT_SWISH) {
+    const float sg = 1.0f / (1.0f + __expf(-u));
+    return sg * fmaf(u, 1.0f - sg, 1.0f);
+  }
+  return gelu_grad(u);
+}
+
+// y = act(u)
+__global__ void __launch_bounds__(256) act_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ y,
+                                                       long long n2, int act) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t a = reinterpret_cast<const uint32_t*>(u)[i];
+    reinterpret_cast<uint32_t*>(y)[i] = pack_bf16x2(apply_act(bf16_lo(a), act), apply_act(bf16_hi(a), act));
+  }
+}
+std::string launch_act_fwd(const __nv_bfloat16* u, __nv_bfloat16* y, long long n, int act, cudaStream_t s) {
+  if (n % 2) return "act_fwd: element count must be even";
+  if (n == 0) return "";
+  const long long n2 = n / 2;
+  act_fwd_kernel<<<(unsigned)((n2 + 255) / 256 > 148 * 16 ? 148 * 16 : (n2 + 255) / 256), 256, 0, s>>>(u, y, n2, act);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+// d <- d * act'(u) (* chan_scale[column] when given: the folded BatchNorm scale that sits between u's producer and act)
+__global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ d,
+                                                       long long n2, int act, const float* __restrict__ chan_scale, int H) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t a = reinterpret_cast<const uint32_t*>(u)[i];
+    const uint32_t g = reinterpret_cast<const uint32_t*>(d)[i];
+    float lo = bf16_lo(g) * act_grad(bf16_lo(a), act), hi = bf16_hi(g) * act_grad(bf16_hi(a), act);
+    if (chan_scale) {
+      const int c = (int)((2 * i) % H);
+      lo *= chan_scale[c];
+      hi *= chan_scale[c + 1];
+    }
+    reinterpret_cast<uint32_t*>(d)[i] = pack_bf16x2(lo, hi);
+  }
+}
+std::string launch_act_bwd(const __nv_bfloat16* u, __nv_bfloat16* d, long long n, int act, const float* chan_scale, int H,
+                           cudaStream_t s) {
+  if (n % 2 || H % 2) return "act_bwd: element and channel counts must be even";
+  if (n == 0) return "";
+  const long long n2 = n / 2;
+  act_bwd_kernel<<<(unsigned)((n2 + 255) / 256 > 148 * 16 ? 148 * 16 : (n2 + 255) / 256), 256, 0, s>>>(u, d, n2, act, chan_scale, H);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+// GLU over interleaved (value, gate) column pairs: out[r, j] = raw[r, 2j] sigmoid(raw[r, 2j + 1])
+__global__ void __launch_bounds__(256) glu_fwd_kernel(const __nv_bfloat16* __restrict__ raw, __nv_bfloat16* __restrict__ out,
+                                                       long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t a = reinterpret_cast<const uint32_t*>(raw)[i];
+    out[i] = __float2bfloat16_rn(bf16_lo(a) / (1.0f + __expf(-bf16_hi(a))));
+  }
+}
+std::string launch_glu_fwd(const __nv_bfloat16* raw, __nv_bfloat16* out, long long n, cudaStream_t s) {
+  if (n == 0) return "";
+  glu_fwd_kernel<<<(unsigned)((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256), 256, 0, s>>>(raw, out, n);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+// d raw[r, 2j] = d out sigmoid(gate);  d raw[r, 2j + 1] = d out value sigmoid(gate) (1 - sigmoid(gate))
+__global__ void __launch_bounds__(256) glu_bwd_kernel(const __nv_bfloat16* __restrict__ raw, const __nv_bfloat16* __restrict__ dout,
+                                                       __nv_bfloat16* __restrict__ draw, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t a = reinterpret_cast<const uint32_t*>(raw)[i];
+    const float g = __bfloat162float(dout[i]);
+    const float sg = 1.0f / (1.0f + __expf(-bf16_hi(a)));
+    reinterpret_cast<uint32_t*>(draw)[i] = pack_bf16x2(g * sg, g * bf16_lo(a) * sg * (1.0f - sg));
+  }
+}
+std::string launch_glu_bwd(const __nv_bfloat16* raw, const __nv_bfloat16* dout, __nv_bfloat16* draw, long long n, cudaStream_t s) {
+  if (n == 0) return "";
+  glu_bwd_kernel<<<(unsigned)((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256), 256, 0, s>>>(raw, dout, draw, n);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+// relative positions: S[bh, i, j] += BD[bh, i, T - 1 - i + j]  (the HF rel_shift as index arithmetic, :540-553)
+__global__ void __launch_bounds__(256) rel_shift_add_kernel(float* __restrict__ S, const float* __restrict__ BD, int T, int Tp,
+                                                             int Rp) {
+  const long long bh = blockIdx.y;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)T * T; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / T), j = (int)(e - (long long)i * T);
+    S[(bh * T + i) * Tp + j] += BD[(bh * T + i) * Rp + (T - 1 - i + j)];
+  }
+}
+std::string launch_rel_shift_add(float* S, const float* BD, int BH, int T, int Tp, int Rp, cudaStream_t s) {
+  if (BH == 0) return "";
+  const long long per = (long long)T * T;
+  rel_shift_add_kernel<<<dim3((unsigned)((per + 255) / 256 > 1024 ? 1024 : (per + 255) / 256), BH), 256, 0, s>>>(S, BD, T, Tp, Rp);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+// the transpose of that gather: dBD[bh, i, r] = dS[bh, i, r - (T - 1) + i] where that key exists, else 0 (all Rp columns written)
+__global__ void __launch_bounds__(256) rel_unshift_kernel(const __nv_bfloat16* __restrict__ dS, __nv_bfloat16* __restrict__ dBD,
+                                                           int T, int Tp, int Rp) {
+  const long long bh = blockIdx.y;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)T * Rp; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / Rp), r = (int)(e - (long long)i * Rp);
+    const int j = r - (T - 1) + i;
+    dBD[(bh * T + i) * Rp + r] = (j >= 0 && j < T) ? dS[(bh * T + i) * Tp + j] : __float2bfloat16_rn(0.f);
+  }
+}
+std::string launch_rel_unshift(const __nv_bfloat16* dS, __nv_bfloat16* dBD, int BH, int T, int Tp, int Rp, cudaStream_t s) {
+  if (BH == 0) return "";
+  const long long per = (long long)T * Rp;
+  rel_unshift_kernel<<<dim3((unsigned)((per + 255) / 256 > 1024 ? 1024 : (per + 255) / 256), BH), 256, 0, s>>>(dS, dBD, T, Tp, Rp);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
+// depthwise conv backward-data taps: dst[j][c] = src[k - 1 - j][c]  (taps stored [k][H]; "same" padding, odd k)
+__global__ void flip_taps_kernel(const float* __restrict__ src, float* __restrict__ dst, int k, int H) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < k * H) {
+    const int j = i / H, c = i - j * H;
+    dst[i] = src[(k - 1 - j) * H + c];
+  }
+}
+std::string launch_flip_taps(const float* src, float* dst, int k, int H, cudaStream_t s) {
+  flip_taps_kernel<<<(k * H + 255) / 256, 256, 0, s>>>(src, dst, k, H);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+__global__ void fill_f32_kernel(float* dst, float v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = v;
+}
+std::string launch_fill_f32(float* dst, float v, int n, cudaStream_t s) {
+  fill_f32_kernel<<<(n + 255) / 256, 256, 0, s>>>(dst, v, n);
+  W2S_CUDA_OK(cudaGetLastError());
+  return "";
+}
+
 // ---- weight re-layout for the backward contractions (once, at first use) --------------------------------------
 // dst[c][r] = src[r][c]  (bf16, R x C -> C x R)
 __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R, int C) {

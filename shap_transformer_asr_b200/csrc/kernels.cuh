@@ -118,8 +118,9 @@ std::string launch_bn_fold(const float* g, const float* b, const float* mean, co
 std::string launch_depthwise(const __nv_bfloat16* in, int B, int T, int H, int k, const float* w, const float* scale,
                              const float* shift, int act, __nv_bfloat16* out, cudaStream_t s);
 std::string launch_transpose_f32(const float* src, float* dst, int R, int C, cudaStream_t s);
+// inverse = 1 applies the transposed rotation (the backward of the forward one)
 std::string launch_rotary(const __nv_bfloat16* x, long long rows, int T, int H, int hd, int base, __nv_bfloat16* out,
-                          cudaStream_t s);
+                          cudaStream_t s, int inverse = 0);
 std::string launch_relpos(int T, int H, __nv_bfloat16* out, cudaStream_t s);
 
 // ---- K9: lm_head + log-softmax + gather -----------------------------------------------------------------
@@ -169,6 +170,16 @@ std::string launch_conv_gather(const __nv_bfloat16* dcol, int n, int T_in, int T
 std::string launch_conv0_bwd(const __nv_bfloat16* du, const __nv_bfloat16* u, int n, long long L, int T0, int C, int kw, int stride,
                              const float* w, const float* gn_a, const float* gamma, const float* beta, float* m12, float* g,
                              float* dx, long long ld, cudaStream_t s);
+// conformer encoder pieces of the gradient path
+std::string launch_act_fwd(const __nv_bfloat16* u, __nv_bfloat16* y, long long n, int act, cudaStream_t s);
+std::string launch_act_bwd(const __nv_bfloat16* u, __nv_bfloat16* d, long long n, int act, const float* chan_scale, int H,
+                           cudaStream_t s);
+std::string launch_glu_fwd(const __nv_bfloat16* raw, __nv_bfloat16* out, long long n, cudaStream_t s);
+std::string launch_glu_bwd(const __nv_bfloat16* raw, const __nv_bfloat16* dout, __nv_bfloat16* draw, long long n, cudaStream_t s);
+std::string launch_rel_shift_add(float* S, const float* BD, int BH, int T, int Tp, int Rp, cudaStream_t s);
+std::string launch_rel_unshift(const __nv_bfloat16* dS, __nv_bfloat16* dBD, int BH, int T, int Tp, int Rp, cudaStream_t s);
+std::string launch_flip_taps(const float* src, float* dst, int k, int H, cudaStream_t s);
+std::string launch_fill_f32(float* dst, float v, int n, cudaStream_t s);
 std::string launch_transpose_bf16(const __nv_bfloat16* src, __nv_bfloat16* dst, int R, int C, cudaStream_t s);
 std::string launch_repack_posconv_bwd(const float* src, __nv_bfloat16* dst, int H, int G, int kw, cudaStream_t s);
 

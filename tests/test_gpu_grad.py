@@ -34,10 +34,12 @@ def reference_grads(model, x, frames):
             grabs[name] = t
         return hook
 
-    w = model.wav2vec2
+    conformer = hasattr(model, "wav2vec2_conformer")
+    w = model.wav2vec2_conformer if conformer else model.wav2vec2
     NL = len(w.encoder.layers)
-    stable = bool(model.config.do_stable_layer_norm)
-    # input of encoder layer 0: the LayerNorm'ed sum (post-LN encoders) / the un-normalised sum after dropout (stable-LN)
+    stable = conformer or bool(model.config.do_stable_layer_norm)
+    # input of encoder layer 0: the LayerNorm'ed sum (post-LN encoders) / the un-normalised stream after dropout (stable-LN
+    # encoders and the conformer, whose layers end in their own final_layer_norm)
     hooks.append((w.encoder.dropout if stable else w.encoder.layer_norm).register_forward_hook(keep("layer0")))
     for l, layer in enumerate(w.encoder.layers):
         hooks.append(layer.register_forward_hook(keep(f"layer{l + 1}")))
@@ -78,13 +80,15 @@ def _chan_last(t, T_l):
 
 
 @pytest.mark.parametrize("variant,attn", [("tiny_group", "tensor_core"), ("tiny_group", "cuda_core"),
-                                          ("tiny_layer_stable", "tensor_core")])
+                                          ("tiny_layer_stable", "tensor_core"), ("tiny_conformer_rel", "tensor_core"),
+                                          ("tiny_conformer_rotary", "tensor_core")])
 def test_gradient_stages_match_autograd_tiny(P, variant, attn):
     """Every stage of the backward pass against autograd (tiny model): localises a wrong kernel to its stage.  Attention
     backward both as batched tensor-core contractions (the product path) and on the CUDA-core cross-check kernels."""
     cfg = VARIANTS[variant]
     model = build_model(cfg)
     stable = cfg.do_stable_layer_norm
+    conformer = cfg.kind == "conformer"
     rng = np.random.default_rng(0)
     x = rng.standard_normal((3, 6000)).astype(np.float32)
     T = cfg.num_frames(6000)
@@ -102,9 +106,14 @@ def test_gradient_stages_match_autograd_tiny(P, variant, attn):
     for l in range(NC):
         mine = eng.grad_peek(f"f.convu{l}", (3, lens[l], cfg.conv_dim[l]), torch.bfloat16).float().cpu().numpy()
         fwd.append((f"convu{l}", rel(mine, _chan_last(g[f"f.convu{l}"], lens[l]))))
-    fwd.append(("h0", rel(eng.grad_peek("f.h0", (3, T, H), torch.bfloat16).float().cpu().numpy(), g["f.h0"].numpy())))
+    if conformer:          # the projection is the fp32 stream itself; every layer's output (after final_layer_norm) is saved
+        fwd.append(("h0", rel(eng.grad_peek("f.h0", (3, T, H)).cpu().numpy(), g["f.h0"].numpy())))
+        for l in range(1, NL + 1):
+            fwd.append((f"layer{l}", rel(eng.grad_peek(f"f.layer{l}", (3, T, H)).cpu().numpy(), g[f"f.layer{l}"].numpy())))
+    else:
+        fwd.append(("h0", rel(eng.grad_peek("f.h0", (3, T, H), torch.bfloat16).float().cpu().numpy(), g["f.h0"].numpy())))
     for l in range(NL + 1):
-        if stable:
+        if stable or conformer:
             break          # the stable-LN forward keeps the fp32 residual stream, not a normalised bf16 copy per layer
         mine = eng.grad_peek(f"f.layer{l}", (3, T, H), torch.bfloat16).float().cpu().numpy()
         fwd.append((f"layer{l}", rel(mine, g[f"f.layer{l}"].numpy())))
@@ -133,7 +142,8 @@ def test_gradient_stages_match_autograd_tiny(P, variant, attn):
 
 @pytest.mark.parametrize("name,n,L", [("tiny_group", 35, 9000), ("wav2vec2-base", 32, 16000), ("tiny_group", 3, 183600),
                                       ("wav2vec2-large", 4, 16000), ("tiny_layer_stable", 34, 9000),
-                                      ("wav2vec2-large-lv60", 3, 16000)])
+                                      ("wav2vec2-large-lv60", 3, 16000), ("tiny_conformer_rel", 34, 9000),
+                                      ("tiny_conformer_rotary", 33, 9000), ("wav2vec2-conformer-large", 3, 16000)])
 def test_input_gradients_match_autograd_at_batch_32(P, name, n, L):
     """d (max logit of frame j) / d waveform for >= 32 rows with different target frames (one ragged tile for the tiny
     model: 32 + 3) against torch autograd on the transformers model."""
@@ -141,6 +151,9 @@ def test_input_gradients_match_autograd_at_batch_32(P, name, n, L):
         import dataclasses
         cfg = dataclasses.replace(MODELS["wav2vec2-large"], feat_extract_norm="layer", conv_bias=True,
                                   do_stable_layer_norm=True, num_hidden_layers=6)
+    elif name == "wav2vec2-conformer-large":   # the C4 model (w2v2conformer.py:57) at full width, 6 of its 24 layers
+        import dataclasses
+        cfg = dataclasses.replace(MODELS[name], num_hidden_layers=6)
     else:
         cfg = VARIANTS[name] if name in VARIANTS else MODELS[name]
     model = build_model(cfg)
@@ -202,10 +215,16 @@ def test_expected_gradients_explainer_properties(P):
 
 
 def test_gradient_path_rejects_unbuilt_configurations(P):
+    """What the gradient path does not cover fails loudly: the conformer's CUDA-core attention cross-check, and a target
+    frame outside the clip."""
     cfg = VARIANTS["tiny_conformer_rel"]
     eng = P.Engine(build_model(cfg), cfg, max_batch=2)
+    eng.grad_debug(False, simt_attention=True)
     with pytest.raises(RuntimeError, match="gradient path"):
         eng.grad_waveforms(torch.zeros((1, 4000), device="cuda"), [0])
+    eng.grad_debug(False, simt_attention=False)
+    with pytest.raises(RuntimeError, match="target frame"):
+        eng.grad_waveforms(torch.zeros((1, 4000), device="cuda"), [10 ** 6])
     eng.close()
 
 
