@@ -824,36 +824,45 @@ std::string launch_glu_bwd(const __nv_bfloat16* raw, const __nv_bfloat16* dout, 
   return "";
 }
 
-// relative positions: S[bh, i, j] += BD[bh, i, T - 1 - i + j]  (the HF rel_shift as index arithmetic, :540-553)
-__global__ void __launch_bounds__(256) rel_shift_add_kernel(float* __restrict__ S, const float* __restrict__ BD, int T, int Tp,
+// relative positions: S[bh, i, j] += BD[bh, i, T - 1 - i + j]  (the HF rel_shift as index arithmetic, :540-553).
+// One CTA per (query row, batch x head): no index division, contiguous reads and writes.
+__global__ void __launch_bounds__(128) rel_shift_add_kernel(float* __restrict__ S, const float* __restrict__ BD, int T, int Tp,
                                                              int Rp) {
-  const long long bh = blockIdx.y;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)T * T; e += (long long)gridDim.x * blockDim.x) {
-    const int i = (int)(e / T), j = (int)(e - (long long)i * T);
-    S[(bh * T + i) * Tp + j] += BD[(bh * T + i) * Rp + (T - 1 - i + j)];
-  }
+  const long long row = (long long)blockIdx.y * T + blockIdx.x;
+  const int i = blockIdx.x;
+  float* s = S + row * Tp;
+  const float* bd = BD + row * Rp + (T - 1 - i);
+  for (int j = threadIdx.x; j < T; j += blockDim.x) s[j] += bd[j];
 }
 std::string launch_rel_shift_add(float* S, const float* BD, int BH, int T, int Tp, int Rp, cudaStream_t s) {
   if (BH == 0) return "";
-  const long long per = (long long)T * T;
-  rel_shift_add_kernel<<<dim3((unsigned)((per + 255) / 256 > 1024 ? 1024 : (per + 255) / 256), BH), 256, 0, s>>>(S, BD, T, Tp, Rp);
+  rel_shift_add_kernel<<<dim3(T, BH), 128, 0, s>>>(S, BD, T, Tp, Rp);
   W2S_CUDA_OK(cudaGetLastError());
   return "";
 }
-// the transpose of that gather: dBD[bh, i, r] = dS[bh, i, r - (T - 1) + i] where that key exists, else 0 (all Rp columns written)
-__global__ void __launch_bounds__(256) rel_unshift_kernel(const __nv_bfloat16* __restrict__ dS, __nv_bfloat16* __restrict__ dBD,
+// the transpose of that gather: dBD[bh, i, r] = dS[bh, i, r - (T - 1) + i] where that key exists, else 0 (all Rp columns
+// written, eight per thread as one 16-byte store)
+__global__ void __launch_bounds__(128) rel_unshift_kernel(const __nv_bfloat16* __restrict__ dS, __nv_bfloat16* __restrict__ dBD,
                                                            int T, int Tp, int Rp) {
-  const long long bh = blockIdx.y;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)T * Rp; e += (long long)gridDim.x * blockDim.x) {
-    const int i = (int)(e / Rp), r = (int)(e - (long long)i * Rp);
-    const int j = r - (T - 1) + i;
-    dBD[(bh * T + i) * Rp + r] = (j >= 0 && j < T) ? dS[(bh * T + i) * Tp + j] : __float2bfloat16_rn(0.f);
+  const long long row = (long long)blockIdx.y * T + blockIdx.x;
+  const int i = blockIdx.x;
+  const __nv_bfloat16* src = dS + row * Tp;
+  __nv_bfloat16* dst = dBD + row * Rp;
+  const int shift = i - (T - 1);
+  for (int r0 = threadIdx.x * 8; r0 < Rp; r0 += blockDim.x * 8) {
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int j = r0 + k + shift;
+      v[k] = (j >= 0 && j < T) ? src[j] : __float2bfloat16_rn(0.f);
+    }
+    *reinterpret_cast<uint4*>(dst + r0) = *reinterpret_cast<const uint4*>(v);
   }
 }
 std::string launch_rel_unshift(const __nv_bfloat16* dS, __nv_bfloat16* dBD, int BH, int T, int Tp, int Rp, cudaStream_t s) {
   if (BH == 0) return "";
-  const long long per = (long long)T * Rp;
-  rel_unshift_kernel<<<dim3((unsigned)((per + 255) / 256 > 1024 ? 1024 : (per + 255) / 256), BH), 256, 0, s>>>(dS, dBD, T, Tp, Rp);
+  if (Rp % 8) return "rel_unshift: padded relative-position count must be a multiple of 8";
+  rel_unshift_kernel<<<dim3(T, BH), 128, 0, s>>>(dS, dBD, T, Tp, Rp);
   W2S_CUDA_OK(cudaGetLastError());
   return "";
 }
