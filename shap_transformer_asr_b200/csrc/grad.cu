@@ -155,11 +155,87 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const void* dy, const void*
     }
   }
 }
+// Same, four consecutive elements per lane and step (16-byte loads / stores of the fp32 streams): H % 4 == 0.
+__device__ __forceinline__ float4 ln_ld4(const void* p, long long i, bool f32) {
+  if (f32) return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i);
+  const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p) + i);
+  return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+}
+template <bool X_F32, bool DY_F32>
+__global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const void* dy, const void* __restrict__ x, long long rows,
+                                                          int H, const float* __restrict__ gamma, float eps,
+                                                          const float* __restrict__ add, float* __restrict__ dx,
+                                                          __nv_bfloat16* __restrict__ dx16) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  constexpr int NV = 8;   // H <= 1024
+  const long long base = row * H;
+  float4 xv[NV], gv[NV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = (lane + 32 * i) * 4;
+    xv[i] = idx < H ? ln_ld4(x, base + idx, X_F32) : make_float4(0.f, 0.f, 0.f, 0.f);
+    sum += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {   // the gradient loads are independent of the statistics: issue them early
+    const int idx = (lane + 32 * i) * 4;
+    gv[i] = idx < H ? ln_ld4(dy, base + idx, DY_F32) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float mean = warp_sum(sum) / (float)H;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if ((lane + 32 * i) * 4 < H) {
+      const float a = xv[i].x - mean, b = xv[i].y - mean, c = xv[i].z - mean, d = xv[i].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)H + eps);
+  float sg = 0.f, sgx = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = (lane + 32 * i) * 4;
+    if (idx < H) {
+      const float4 gm = *reinterpret_cast<const float4*>(gamma + idx);
+      gv[i] = make_float4(gv[i].x * gm.x, gv[i].y * gm.y, gv[i].z * gm.z, gv[i].w * gm.w);
+      xv[i] = make_float4((xv[i].x - mean) * rstd, (xv[i].y - mean) * rstd, (xv[i].z - mean) * rstd, (xv[i].w - mean) * rstd);
+      sg += (gv[i].x + gv[i].y) + (gv[i].z + gv[i].w);
+      sgx += (gv[i].x * xv[i].x + gv[i].y * xv[i].y) + (gv[i].z * xv[i].z + gv[i].w * xv[i].w);
+    }
+  }
+  const float mg = warp_sum(sg) / (float)H, mgx = warp_sum(sgx) / (float)H;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = (lane + 32 * i) * 4;
+    if (idx < H) {
+      float4 v = make_float4(rstd * (gv[i].x - mg - xv[i].x * mgx), rstd * (gv[i].y - mg - xv[i].y * mgx),
+                             rstd * (gv[i].z - mg - xv[i].z * mgx), rstd * (gv[i].w - mg - xv[i].w * mgx));
+      if (add) {
+        const float4 a = *reinterpret_cast<const float4*>(add + base + idx);
+        v = make_float4(v.x + a.x, v.y + a.y, v.z + a.z, v.w + a.w);
+      }
+      if (dx) *reinterpret_cast<float4*>(dx + base + idx) = v;
+      if (dx16) *reinterpret_cast<uint2*>(dx16 + base + idx) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+  }
+}
+
 std::string launch_ln_bwd(const void* dy, const void* x, int x_fp32, long long rows, int H, const float* gamma, float eps,
                           const float* add, float* dx, __nv_bfloat16* dx16, cudaStream_t s, int dy_fp32) {
   if (H > 1024) return "ln_bwd: H > 1024 not supported";
   if (rows == 0) return "";
   const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (H % 4 == 0) {
+    if (x_fp32 && dy_fp32) ln_bwd_vec_kernel<true, true><<<grid, 256, 0, s>>>(dy, x, rows, H, gamma, eps, add, dx, dx16);
+    else if (x_fp32) ln_bwd_vec_kernel<true, false><<<grid, 256, 0, s>>>(dy, x, rows, H, gamma, eps, add, dx, dx16);
+    else if (dy_fp32) ln_bwd_vec_kernel<false, true><<<grid, 256, 0, s>>>(dy, x, rows, H, gamma, eps, add, dx, dx16);
+    else ln_bwd_vec_kernel<false, false><<<grid, 256, 0, s>>>(dy, x, rows, H, gamma, eps, add, dx, dx16);
+    W2S_CUDA_OK(cudaGetLastError());
+    return "";
+  }
   if (x_fp32 && dy_fp32) ln_bwd_kernel<true, true><<<grid, 256, 0, s>>>(dy, x, rows, H, gamma, eps, add, dx, dx16);
   else if (x_fp32) ln_bwd_kernel<true, false><<<grid, 256, 0, s>>>(dy, x, rows, H, gamma, eps, add, dx, dx16);
   else if (dy_fp32) ln_bwd_kernel<false, true><<<grid, 256, 0, s>>>(dy, x, rows, H, gamma, eps, add, dx, dx16);
