@@ -671,19 +671,24 @@ std::string launch_conv_gather(const __nv_bfloat16* dcol, int n, int T_in, int T
 // pass 1: per (row, channel) the two time means (one warp per 32 channels x a slab of frames, fp32 atomics-free: one CTA
 //         per (row, 64-channel group) walks all frames);  pass 2: per (row, frame) the 10 tap sums g[t][j] = sum_c w[c][j] d c0[t, c];
 // pass 3: gather d x[i] = g[i / 5][i % 5] + g[i / 5 - 1][i % 5 + 5].
+constexpr int GN_BWD_CHUNKS = 32;   // time chunks per (row, 64 channels): 8 x n x 32 CTAs instead of 8 x n
 __global__ void __launch_bounds__(256) gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ du, const __nv_bfloat16* __restrict__ u,
                                                             int T0, int C, const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, float* __restrict__ m12 /* [n, C, 2] */) {
-  // CTA = (64 channels, row); thread = (channel pair, frame lane): 32 channel pairs x 8 frame lanes
-  const int row = blockIdx.y, c0 = blockIdx.x * 64;
+                                                            const float* __restrict__ beta,
+                                                            float* __restrict__ part /* [n, GN_BWD_CHUNKS, C, 2] sums */) {
+  // CTA = (64 channels, row, time chunk); thread = (channel pair, frame lane): 32 channel pairs x 8 frame lanes
+  const int row = blockIdx.y, c0 = blockIdx.x * 64, z = blockIdx.z;
   const int cp = threadIdx.x & 31, fl = threadIdx.x >> 5;
   const int c = c0 + 2 * cp;
+  const int per = (T0 + GN_BWD_CHUNKS - 1) / GN_BWD_CHUNKS;
+  const int t_lo = z * per, t_hi = min(T0, t_lo + per);
   __shared__ float red[8][32][4];
   float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
   if (c < C) {
     const float ga = gamma[c], gb = gamma[c + 1], ba = beta[c], bb = beta[c + 1];
     const float iga = 1.0f / ga, igb = 1.0f / gb;
-    for (int t = fl; t < T0; t += 8) {
+#pragma unroll 4
+    for (int t = t_lo + fl; t < t_hi; t += 8) {
       const long long o = ((long long)row * T0 + t) * C + c;
       const uint32_t dv = *reinterpret_cast<const uint32_t*>(du + o);
       const uint32_t uv = *reinterpret_cast<const uint32_t*>(u + o);
@@ -700,40 +705,87 @@ __global__ void __launch_bounds__(256) gn_bwd_stats_kernel(const __nv_bfloat16* 
     float r[4] = {0.f, 0.f, 0.f, 0.f};
     for (int f = 0; f < 8; ++f)
       for (int q = 0; q < 4; ++q) r[q] += red[f][cp][q];
-    float* dst = m12 + ((long long)row * C + c) * 2;
-    const float invT = 1.0f / (float)T0;
-    dst[0] = r[0] * invT; dst[1] = r[2] * invT;   // channel c: (m1, m2)
-    dst[2] = r[1] * invT; dst[3] = r[3] * invT;   // channel c + 1
+    float* dst = part + (((long long)row * GN_BWD_CHUNKS + z) * C + c) * 2;
+    dst[0] = r[0]; dst[1] = r[2];   // channel c: (sum du, sum du xhat)
+    dst[2] = r[1]; dst[3] = r[3];   // channel c + 1
   }
 }
+// chunk sums -> means m1 = mean(du), m2 = mean(du xhat), in a fixed order (deterministic), folded with the forward scale
+// a_c = gamma_c rstd_c into the affine form the tap kernel applies per element:
+//   d c0 = a (du - m1 - xhat m2),  xhat = (u - beta) / gamma   =>   d c0 = A du + B u + D
+__global__ void gn_bwd_reduce_kernel(const float* __restrict__ part, int n, int C, int T0, const float* __restrict__ gn_a,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     float* __restrict__ coef /* [n, C, 3] */) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (row, channel)
+  if (i >= (long long)n * C) return;
+  const long long row = i / C;
+  const int c = (int)(i - row * C);
+  float s1 = 0.f, s2 = 0.f;
+  for (int z = 0; z < GN_BWD_CHUNKS; ++z) {
+    const float* p = part + (((long long)row * GN_BWD_CHUNKS + z) * C + c) * 2;
+    s1 += p[0];
+    s2 += p[1];
+  }
+  const float m1 = s1 / (float)T0, m2 = s2 / (float)T0;
+  const float a = gn_a[i], ig = 1.0f / gamma[c];
+  coef[i * 3 + 0] = a;
+  coef[i * 3 + 1] = -a * m2 * ig;
+  coef[i * 3 + 2] = a * (beta[c] * m2 * ig - m1);
+}
 
-// pass 2: g[row, t, j] = sum_c w[c][j] a_c (du - m1_c - xhat m2_c); one warp per frame, lanes stride the channels
+// pass 2: g[row, t, j] = sum_c w[c][j] (A_c du + B_c u + D_c).  A warp takes two adjacent frames per step and a lane a
+// channel pair (4-byte loads); the filters sit transposed in shared memory ([tap][channel]: conflict-free 8-byte reads)
+// and are read once per two frames.
 template <int KW>
 __global__ void __launch_bounds__(256) conv0_bwd_taps_kernel(const __nv_bfloat16* __restrict__ du, const __nv_bfloat16* __restrict__ u,
                                                               int T0, int C, const float* __restrict__ w /* [C][KW] */,
-                                                              const float* __restrict__ gn_a /* [n, C] */,
-                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                              const float* __restrict__ m12, float* __restrict__ g /* [n, T0, KW] */) {
+                                                              const float* __restrict__ coef /* [n, C, 3] */,
+                                                              float* __restrict__ g /* [n, T0, KW] */) {
+  extern __shared__ float s_w[];   // [KW][C]
+  for (int i = threadIdx.x; i < C * KW; i += blockDim.x) s_w[(i % KW) * C + i / KW] = w[i];
+  __syncthreads();
   const int row = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int t = blockIdx.x * 8 + warp; t < T0; t += gridDim.x * 8) {
-    float acc[KW];
+  const float* cf_row = coef + (long long)row * C * 3;
+  for (int t = 2 * (blockIdx.x * 8 + warp); t < T0; t += 2 * gridDim.x * 8) {
+    const bool two = t + 1 < T0;
+    float acc0[KW], acc1[KW];
 #pragma unroll
-    for (int j = 0; j < KW; ++j) acc[j] = 0.f;
-    for (int c = lane; c < C; c += 32) {
-      const long long o = ((long long)row * T0 + t) * C + c;
-      const float xh = (__bfloat162float(u[o]) - beta[c]) / gamma[c];
-      const float* mm = m12 + ((long long)row * C + c) * 2;
-      const float dc = gn_a[(long long)row * C + c] * (__bfloat162float(du[o]) - mm[0] - xh * mm[1]);
+    for (int j = 0; j < KW; ++j) acc0[j] = acc1[j] = 0.f;
+    const long long o = ((long long)row * T0 + t) * C;
+    for (int c = 2 * lane; c < C; c += 64) {
+      const float2 k0 = *reinterpret_cast<const float2*>(cf_row + c * 3);       // A_c   B_c
+      const float2 k1 = *reinterpret_cast<const float2*>(cf_row + c * 3 + 2);   // D_c   A_c+1
+      const float2 k2 = *reinterpret_cast<const float2*>(cf_row + c * 3 + 4);   // B_c+1 D_c+1
+      const uint32_t d0 = *reinterpret_cast<const uint32_t*>(du + o + c), u0 = *reinterpret_cast<const uint32_t*>(u + o + c);
+      const float x0 = fmaf(k0.x, bf16_lo(d0), fmaf(k0.y, bf16_lo(u0), k1.x));
+      const float y0 = fmaf(k1.y, bf16_hi(d0), fmaf(k2.x, bf16_hi(u0), k2.y));
+      float x1 = 0.f, y1 = 0.f;
+      if (two) {
+        const uint32_t d1 = *reinterpret_cast<const uint32_t*>(du + o + C + c), u1 = *reinterpret_cast<const uint32_t*>(u + o + C + c);
+        x1 = fmaf(k0.x, bf16_lo(d1), fmaf(k0.y, bf16_lo(u1), k1.x));
+        y1 = fmaf(k1.y, bf16_hi(d1), fmaf(k2.x, bf16_hi(u1), k2.y));
+      }
 #pragma unroll
-      for (int j = 0; j < KW; ++j) acc[j] = fmaf(__ldg(w + c * KW + j), dc, acc[j]);
+      for (int j = 0; j < KW; ++j) {
+        const float2 wj = *reinterpret_cast<const float2*>(s_w + j * C + c);
+        acc0[j] = fmaf(wj.x, x0, fmaf(wj.y, y0, acc0[j]));
+        acc1[j] = fmaf(wj.x, x1, fmaf(wj.y, y1, acc1[j]));
+      }
     }
 #pragma unroll
-    for (int j = 0; j < KW; ++j) acc[j] = warp_sum(acc[j]);
+    for (int j = 0; j < KW; ++j) {
+      acc0[j] = warp_sum(acc0[j]);
+      acc1[j] = warp_sum(acc1[j]);
+    }
     if (lane == 0) {
       float* dst = g + ((long long)row * T0 + t) * KW;
 #pragma unroll
-      for (int j = 0; j < KW; ++j) dst[j] = acc[j];
+      for (int j = 0; j < KW; ++j) dst[j] = acc0[j];
+      if (two) {
+#pragma unroll
+        for (int j = 0; j < KW; ++j) dst[KW + j] = acc1[j];
+      }
     }
   }
 }
@@ -757,9 +809,13 @@ std::string launch_conv0_bwd(const __nv_bfloat16* du, const __nv_bfloat16* u, in
   if (kw != 10) return "conv0 backward: only kernel width 10 is implemented";
   if (C % 64) return "conv0 backward: channel count must be a multiple of 64";
   if (n == 0) return "";
-  gn_bwd_stats_kernel<<<dim3(C / 64, n), 256, 0, s>>>(du, u, T0, C, gamma, beta, m12);
-  conv0_bwd_taps_kernel<10><<<dim3((unsigned)((T0 + 7) / 8 > 1024 ? 1024 : (T0 + 7) / 8), n), 256, 0, s>>>(du, u, T0, C, w, gn_a, gamma,
-                                                                                                          beta, m12, g);
+  // the caller's scratch buffer `m12` holds the [n, C, 3] coefficients + the [n, 32, C, 2] chunk sums
+  float* coef = m12;
+  float* part = m12 + (long long)n * C * 3;
+  gn_bwd_stats_kernel<<<dim3(C / 64, n, GN_BWD_CHUNKS), 256, 0, s>>>(du, u, T0, C, gamma, beta, part);
+  gn_bwd_reduce_kernel<<<(unsigned)(((long long)n * C + 255) / 256), 256, 0, s>>>(part, n, C, T0, gn_a, gamma, beta, coef);
+  const unsigned gx = (unsigned)((T0 + 15) / 16 > 1024 ? 1024 : (T0 + 15) / 16);
+  conv0_bwd_taps_kernel<10><<<dim3(gx, n), 256, sizeof(float) * C * 10, s>>>(du, u, T0, C, w, coef, g);
   conv0_bwd_gather_kernel<<<dim3((unsigned)((L + 255) / 256 > 1024 ? 1024 : (L + 255) / 256), n), 256, 0, s>>>(g, T0, kw, stride, L, dx, ld);
   W2S_CUDA_OK(cudaGetLastError());
   return "";

@@ -293,7 +293,7 @@ struct GradBuilder {
     W2S_TRY(alloc(&plan->D[0], dmax));
     W2S_TRY(alloc(&plan->D[1], dmax));
     W2S_TRY(alloc(&dcol, colmax));
-    W2S_TRY(alloc(&m12, (size_t)n * C0 * 2));
+    W2S_TRY(alloc(&m12, (size_t)n * C0 * (3 + 2 * 32)));   // launch_conv0_bwd scratch: coefficients + 32 time-chunk partial sums
     W2S_TRY(alloc(&gtap, (size_t)n * Tl[0] * c.conv_kernel[0]));
     W2S_TRY(alloc(&plan->frames, (size_t)n));
     plan->dA = dA;

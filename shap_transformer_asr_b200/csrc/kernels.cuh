@@ -167,6 +167,8 @@ std::string launch_head_transpose(const __nv_bfloat16* src, int ld, int off, int
                                   cudaStream_t s);
 std::string launch_conv_gather(const __nv_bfloat16* dcol, int n, int T_in, int T_out, int C, int kw, int stride,
                                const __nv_bfloat16* u_prev, __nv_bfloat16* out, cudaStream_t s);
+// conv0 + GroupNorm over time, backward to the waveform.  m12: scratch of n * C * (3 + 64) floats (per-(row, channel)
+// coefficients + 32 time-chunk partial sums); g: scratch [n, T0, kw]
 std::string launch_conv0_bwd(const __nv_bfloat16* du, const __nv_bfloat16* u, int n, long long L, int T0, int C, int kw, int stride,
                              const float* w, const float* gn_a, const float* gamma, const float* beta, float* m12, float* g,
                              float* dx, long long ld, cudaStream_t s);
