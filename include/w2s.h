@@ -130,7 +130,7 @@ int w2s_vjp_waveforms(w2s_handle* h, const float* x_dev, int64_t n, int64_t L, i
                       float* grad_dev, float* out_dev, void* stream);
 /* Test hooks of the gradient path.  `on` bit 0: keep snapshots of the gradient after every encoder layer / conv layer
  * ("layer<l>", "h0", "conv<l>", "convu<l>", forward activations "f.*"); bit 1: run attention backward on the CUDA-core
- * cross-check kernels instead of the tensor-core contractions.  w2s_grad_peek copies a snapshot out (returns bytes copied, 0 = unknown name, < 0 = buffer
+ * cross-check kernels, bit 2: as batched tensor-core contractions + row kernels, instead of the fused tcgen05 kernel.  w2s_grad_peek copies a snapshot out (returns bytes copied, 0 = unknown name, < 0 = buffer
  * too small by that many bytes). */
 int w2s_grad_debug(w2s_handle* h, int on);
 int64_t w2s_grad_peek(w2s_handle* h, const char* name, void* dst_dev, int64_t max_bytes, void* stream);

@@ -156,6 +156,7 @@ struct w2s_handle {
   int grad_tile = 32;
   bool grad_debug = false, grad_debug_built = false;
   bool grad_attn_simt = false;        // cross-check: attention backward on the CUDA-core kernels (w2s_grad_debug bit 1)
+  bool grad_attn_unfused = false;     // cross-check: attention backward as batched contractions + row kernels (bit 2)
   std::vector<int32_t> grad_frames_host;
   float *grad_out = nullptr, *grad_out_val = nullptr;
   const float* grad_gout = nullptr;
@@ -1012,6 +1013,7 @@ int w2s_create(const w2s_config* cfg, const char* const* names, const float* con
   if (e.empty()) e = attention_rel_init();
   if (e.empty()) e = posconv_init();
   if (e.empty()) e = attention_fa_init();
+  if (e.empty()) e = attention_bwd_init();
   if (e.empty()) {
     WeightTable wt;
     wt.prefix = cfg->kind == 1 ? "wav2vec2_conformer." : "wav2vec2.";
@@ -1150,10 +1152,11 @@ int w2s_vjp_waveforms(w2s_handle* h, const float* x_dev, int64_t n, int64_t L, i
 }
 
 int w2s_grad_debug(w2s_handle* h, int on) {
-  const bool snaps = (on & 1) != 0, simt = (on & 2) != 0;
-  if (simt != h->grad_attn_simt) h->grad_L = -1;   // rebuild the plans
+  const bool snaps = (on & 1) != 0, simt = (on & 2) != 0, unfused = (on & 4) != 0;
+  if (simt != h->grad_attn_simt || unfused != h->grad_attn_unfused) h->grad_L = -1;   // rebuild the plans
   h->grad_debug = snaps;
   h->grad_attn_simt = simt;
+  h->grad_attn_unfused = unfused;
   return 0;
 }
 

@@ -24,6 +24,7 @@ namespace w2s {
 
 struct AttnFaDev {
   __nv_bfloat16* ctx;
+  float* lse;   // optional [B, heads, T]: log2-domain log-sum-exp of the scaled scores (the gradient path's backward kernel)
   int B, T, H, heads, qtiles, num_items, nb;
   float scale_log2e;
 };
@@ -287,6 +288,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       const float inv = rcp_approx(L);
       const int qt = item % p.qtiles, h = (item / p.qtiles) % p.heads, b = item / (p.qtiles * p.heads);
       const int i = qt * 128 + row;
+      if (p.lse && grp == 0 && i < p.T) p.lse[((long long)b * p.heads + h) * p.T + i] = fmaf(m, p.scale_log2e, __log2f(L));
       if (i < p.T) {
         __nv_bfloat16* orow = p.ctx + ((long long)b * p.T + i) * p.H + h * 64 + grp * 32;
 #pragma unroll
@@ -423,6 +425,7 @@ std::string attention_fa_prepare(const AttnParams& p, int num_sms, AttnFaPlan** 
   if (!attention_fa_supported(p)) return "attention (tcgen05): unsupported shape";
   AttnFaPlan* pl = new AttnFaPlan();
   pl->dev.ctx = p.ctx;
+  pl->dev.lse = p.lse;
   pl->dev.B = p.B; pl->dev.T = p.T; pl->dev.H = p.H; pl->dev.heads = p.heads;
   pl->dev.qtiles = (p.T + 127) / 128;
   pl->dev.num_items = pl->dev.qtiles * p.heads * p.B;

@@ -13,6 +13,8 @@
 
 struct GradLayerBuf {
   bf16* qkv = nullptr;    // [rows, 3H]   saved q | k | v
+  bf16* ctx = nullptr;    // [rows, H]    attention output (fused backward: D_i = dO_i . O_i)
+  float* lse = nullptr;   // [n, heads, T] log-sum-exp of the scaled scores (fused backward)
   float* s1 = nullptr;    // [rows, H]    h + attention(h): input of layer_norm
   bf16* u = nullptr;      // [rows, I]    pre-activation of the feed-forward
   float* s2 = nullptr;    // [rows, H]    h1 + ffn(h1): input of final_layer_norm
@@ -23,6 +25,8 @@ struct GradLayerBuf {
 struct GradConfBuf {
   bf16 *u1 = nullptr, *u2 = nullptr;   // [rows, I]      pre-activations of the two macaron feed-forwards
   bf16* qkv = nullptr;                 // [rows, 3H|4H]  q | k | v  or  q+u | q+v | k | v
+  bf16* ctx = nullptr;                 // [rows, H]      attention output  } rotary: the fused attention backward
+  float* lse = nullptr;                // [n, heads, T]  log-sum-exp       }
   bf16* raw = nullptr;                 // [rows, 2H]     pointwise_conv1 output, (value, gate) interleaved
   bf16* z = nullptr;                   // [rows, H]      BatchNorm output, the activation's input
   float *r1 = nullptr, *r2 = nullptr, *r3 = nullptr, *r4 = nullptr, *r5 = nullptr;   // [rows, H] each
@@ -35,6 +39,7 @@ struct GradPlan {
   std::vector<PosConvPlan*> posconv;
   std::vector<AttnFaPlan*> attn_fa;
   std::vector<AttnRelPlan*> attn_rel;
+  std::vector<AttnBwdPlan*> attn_bwd;
   std::vector<void*> allocs;
   // buffers the entry point reads / snapshots
   float* logits = nullptr;
@@ -45,6 +50,7 @@ struct GradPlan {
   ~GradPlan() {
     for (auto* f : attn_fa) attention_fa_free(f);
     for (auto* a : attn_rel) attention_rel_free(a);
+    for (auto* a : attn_bwd) attention_bwd_free(a);
     for (auto* pc : posconv) posconv_free(pc);
     for (auto* g : gemms) delete g;
     for (void* p : allocs) cudaFree(p);
@@ -226,8 +232,16 @@ struct GradBuilder {
     W2S_TRY(alloc(&ctx, (size_t)rows * H));
     W2S_TRY(alloc(&ffn, (size_t)rows * I));
     W2S_TRY(alloc(&plan->logits, (size_t)rows * h->head_ldl));
+    // attention backward: one fused tcgen05 kernel (attention_bwd.cu) unless the relative-position term is present or a
+    // cross-check form was asked for (w2s_grad_debug bits 1 / 2)
+    const bool attn_fused = !rel && !h->grad_attn_simt && !h->grad_attn_unfused;
+    const size_t nlse = (size_t)n * c.num_attention_heads * T;
     std::vector<GradLayerBuf> lb(conf ? 0 : NL);
     for (int l = 0; l < NL && !conf; ++l) {
+      if (attn_fused) {
+        W2S_TRY(alloc(&lb[l].ctx, (size_t)rows * H));
+        W2S_TRY(alloc(&lb[l].lse, nlse));
+      }
       W2S_TRY(alloc(&lb[l].qkv, (size_t)rows * 3 * H));
       W2S_TRY(alloc(&lb[l].s1, (size_t)rows * H));
       W2S_TRY(alloc(&lb[l].u, (size_t)rows * I));
@@ -236,6 +250,10 @@ struct GradBuilder {
     std::vector<GradConfBuf> cb(conf ? NL : 0);
     bf16 *hrot = nullptr, *dC2 = nullptr;
     for (int l = 0; l < NL && conf; ++l) {
+      if (attn_fused) {
+        W2S_TRY(alloc(&cb[l].ctx, (size_t)rows * H));
+        W2S_TRY(alloc(&cb[l].lse, nlse));
+      }
       W2S_TRY(alloc(&cb[l].u1, (size_t)rows * I));
       W2S_TRY(alloc(&cb[l].u2, (size_t)rows * I));
       W2S_TRY(alloc(&cb[l].qkv, (size_t)rows * QW));
@@ -265,6 +283,11 @@ struct GradBuilder {
     float *aS = nullptr, *adP = nullptr;
     bf16 *aP = nullptr, *aPT = nullptr, *adS = nullptr, *adST = nullptr, *aQT = nullptr, *aKT = nullptr, *adOT = nullptr;
     const bool attn_tc = !h->grad_attn_simt;
+    float *adelta = nullptr, *adq = nullptr;
+    if (attn_fused) {
+      W2S_TRY(alloc(&adelta, nlse));
+      W2S_TRY(alloc(&adq, (size_t)rows * H));
+    }
     if (conf && !attn_tc) return "gradient path: the CUDA-core attention backward covers Wav2Vec2ForCTC only";
     const int Rp = (2 * T - 1 + 63) / 64 * 64;             // relative positions 2T'-1, padded like Tp
     float* aBD = nullptr;
@@ -273,7 +296,7 @@ struct GradBuilder {
       W2S_TRY(alloc(&aBD, (size_t)n * heads * T * Rp));
       W2S_TRY(alloc(&adBD, (size_t)n * heads * T * Rp));
     }
-    if (attn_tc) {
+    if (attn_tc && !attn_fused) {
       W2S_TRY(alloc(&aS, nsc));
       W2S_TRY(alloc(&adP, nsc));
       W2S_TRY(alloc(&aP, nsc, true));
@@ -429,6 +452,10 @@ struct GradBuilder {
           plan->attn_rel.push_back(rp);
           add(ls + "attention", [=](cudaStream_t s) { return attention_rel_launch(rp, s); });
         } else {
+          if (attn_fused) {
+            lp.ctx = B.ctx;
+            lp.lse = B.lse;
+          }
           AttnFaPlan* afl = nullptr;
           W2S_TRY(attention_fa_prepare(lp, h->num_sms, &afl));
           plan->attn_fa.push_back(afl);
@@ -436,7 +463,7 @@ struct GradBuilder {
         }
       }
       {
-        GemmProblem p = PlanBuilder::plain(ctx, rows, H, w.wo, H);
+        GemmProblem p = PlanBuilder::plain(attn_fused ? B.ctx : ctx, rows, H, w.wo, H);
         p.epi.bias = w.bo; p.epi.residual = B.r1; p.epi.res_fp32 = 1; p.epi.out = B.r2; p.epi.out_fp32 = 1;
         W2S_TRY(add_gemm(ls + "out_proj", p));
       }
@@ -486,13 +513,17 @@ struct GradBuilder {
       {
         AttnParams lp = ap;
         lp.qkv = B.qkv;
+        if (attn_fused) {
+          lp.ctx = B.ctx;
+          lp.lse = B.lse;
+        }
         AttnFaPlan* afl = nullptr;
         W2S_TRY(attention_fa_prepare(lp, h->num_sms, &afl));
         plan->attn_fa.push_back(afl);
         add(ls + "attention", [=](cudaStream_t s) { return attention_fa_launch(afl, s); });
       }
       {
-        GemmProblem p = PlanBuilder::plain(ctx, rows, H, w.wo, H);
+        GemmProblem p = PlanBuilder::plain(attn_fused ? B.ctx : ctx, rows, H, w.wo, H);
         p.epi.bias = w.bo;
         if (stable) {
           p.epi.residual = r1; p.epi.res_fp32 = 1;
@@ -549,9 +580,17 @@ struct GradBuilder {
     // ================================ backward to the waveform ===================================================
     // attention backward of one layer: (saved q | k | v, dC = d ctx) -> dQKV; shared by both encoder orders
     // (pos_proj / pos_projT: the conformer's relative-position term, S += shift((q + v) pos_proj^T); null otherwise)
-    auto add_attention_bwd = [&](const std::string& ls, const bf16* saved_qkv, const bf16* pos_proj,
-                                 const bf16* pos_projT) -> std::string {
-      if (!attn_tc) {
+    auto add_attention_bwd = [&](const std::string& ls, const bf16* saved_qkv, const bf16* pos_proj, const bf16* pos_projT,
+                                 const bf16* saved_ctx, const float* saved_lse) -> std::string {
+      if (attn_fused) {
+        AttnParams bp = ap;
+        bp.qkv = saved_qkv;
+        AttnBwdPlan* abp = nullptr;
+        W2S_TRY(attention_bwd_prepare(bp, dC, saved_lse, adelta, adq, dQKV, h->num_sms, &abp));
+        plan->attn_bwd.push_back(abp);
+        add(ls + "attention_bwd", [=](cudaStream_t s) { return attention_bwd_launch(abp, dC, saved_ctx, q_off, s); });
+        plan->steps.back().flops = 10.0 * T * (double)T * H * n;   // five T' x T' x 64 contractions per head
+      } else if (!attn_tc) {
         const bf16* q = saved_qkv;
         add(ls + "attention_bwd", [=](cudaStream_t s) { return launch_attn_bwd(q, dC, nn, T, H, heads, 0.125f, dQKV, attn_stats, s); });
       } else {
@@ -709,7 +748,7 @@ struct GradBuilder {
         GemmProblem p = PlanBuilder::plain(dS16, rows, H, gw.woT, H);
         p.epi.out = dC;
         W2S_TRY(add_gemm(ls + "out_proj_bwd", p));
-        W2S_TRY(add_attention_bwd(ls, B.qkv, rel ? gw.pos_proj : nullptr, rel ? gw.pos_projT : nullptr));
+        W2S_TRY(add_attention_bwd(ls, B.qkv, rel ? gw.pos_proj : nullptr, rel ? gw.pos_projT : nullptr, B.ctx, B.lse));
         if (rotary) {   // q | k came from the rotated input, v from the plain one
           GemmProblem qk = PlanBuilder::plain(dQKV, rows, 2 * H, gw.wqkT, H);
           qk.a_row_stride = 3 * H;
@@ -761,7 +800,7 @@ struct GradBuilder {
         p.epi.out = dC;
         W2S_TRY(add_gemm(ls + "out_proj_bwd", p));
       }
-      W2S_TRY(add_attention_bwd(ls, B.qkv, nullptr, nullptr));
+      W2S_TRY(add_attention_bwd(ls, B.qkv, nullptr, nullptr, B.ctx, B.lse));
       {
         GemmProblem p = PlanBuilder::plain(dQKV, rows, 3 * H, gw.wqkvT, H);
         p.epi.out = dT; p.epi.out_fp32 = 1;
@@ -805,7 +844,7 @@ struct GradBuilder {
         p.epi.out = dC;
         W2S_TRY(add_gemm(ls + "out_proj_bwd", p));
       }
-      W2S_TRY(add_attention_bwd(ls, B.qkv, nullptr, nullptr));
+      W2S_TRY(add_attention_bwd(ls, B.qkv, nullptr, nullptr, B.ctx, B.lse));
       {
         GemmProblem p = PlanBuilder::plain(dQKV, rows, 3 * H, gw.wqkvT, H);
         p.epi.residual = dS; p.epi.res_fp32 = 1; p.epi.out = dA; p.epi.out_fp32 = 1;

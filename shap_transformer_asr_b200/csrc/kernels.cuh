@@ -94,6 +94,7 @@ struct AttnParams {
   float scale;
   // conformer relative positions (null when unused): the biases u / v are already folded into the q+u / q+v columns
   const __nv_bfloat16* pos_proj;  // [2T-1, H] linear_pos(rel_pos_emb), row r <-> relative position T-1-r
+  float* lse;                     // optional (attention_fa only): [B, heads, T] log2-domain log-sum-exp, saved for the backward
 };
 std::string launch_attention_simt(const AttnParams& p, cudaStream_t s);
 // persistent, warp-specialised tcgen05 kernel with independent key blocks (attention_fa.cu)
@@ -103,6 +104,15 @@ bool attention_fa_supported(const AttnParams& p);
 std::string attention_fa_prepare(const AttnParams& p, int num_sms, AttnFaPlan** plan);
 std::string attention_fa_launch(const AttnFaPlan* plan, cudaStream_t s);
 void attention_fa_free(AttnFaPlan* plan);
+// fused attention backward (attention_bwd.cu): delta + one persistent tcgen05 kernel + dQ cast; needs the forward's lse
+struct AttnBwdPlan;
+std::string attention_bwd_init();
+bool attention_bwd_supported(const AttnParams& p);
+std::string attention_bwd_prepare(const AttnParams& p, const __nv_bfloat16* dctx, const float* lse, float* delta, float* dq,
+                                  __nv_bfloat16* dqkv, int num_sms, AttnBwdPlan** plan);
+std::string attention_bwd_launch(const AttnBwdPlan* plan, const __nv_bfloat16* dctx, const __nv_bfloat16* ctx, int q_off,
+                                 cudaStream_t s);
+void attention_bwd_free(AttnBwdPlan* plan);
 // conformer relative-position attention on tcgen05
 struct AttnRelPlan;
 std::string attention_rel_init();

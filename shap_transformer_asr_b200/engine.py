@@ -214,9 +214,10 @@ class Engine:
                                                None, self._stream()), "w2s_vjp_waveforms")
         return grad
 
-    def grad_debug(self, snapshots: bool = True, simt_attention: bool = False):
-        """Test hooks: keep per-stage snapshots (grad_peek); run attention backward on the CUDA-core cross-check kernels."""
-        self.lib.w2s_grad_debug(self._h, int(bool(snapshots)) | (2 if simt_attention else 0))
+    def grad_debug(self, snapshots: bool = True, simt_attention: bool = False, unfused_attention: bool = False):
+        """Test hooks: keep per-stage snapshots (grad_peek); run attention backward on the CUDA-core cross-check kernels, or
+        as batched tensor-core contractions + row kernels, instead of the fused tcgen05 kernel."""
+        self.lib.w2s_grad_debug(self._h, int(bool(snapshots)) | (2 if simt_attention else 0) | (4 if unfused_attention else 0))
 
     def grad_peek(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
         """Snapshot of an intermediate gradient of the last grad_waveforms call (tests; needs grad_debug(True))."""

@@ -79,12 +79,13 @@ def _chan_last(t, T_l):
     return a if a.shape[1] == T_l else a.transpose(0, 2, 1)
 
 
-@pytest.mark.parametrize("variant,attn", [("tiny_group", "tensor_core"), ("tiny_group", "cuda_core"),
-                                          ("tiny_layer_stable", "tensor_core"), ("tiny_conformer_rel", "tensor_core"),
-                                          ("tiny_conformer_rotary", "tensor_core")])
+@pytest.mark.parametrize("variant,attn", [("tiny_group", "fused"), ("tiny_group", "contractions"), ("tiny_group", "cuda_core"),
+                                          ("tiny_layer_stable", "fused"), ("tiny_conformer_rel", "contractions"),
+                                          ("tiny_conformer_rotary", "fused"), ("tiny_conformer_rotary", "contractions")])
 def test_gradient_stages_match_autograd_tiny(P, variant, attn):
     """Every stage of the backward pass against autograd (tiny model): localises a wrong kernel to its stage.  Attention
-    backward both as batched tensor-core contractions (the product path) and on the CUDA-core cross-check kernels."""
+    backward as the fused tcgen05 kernel (the product path), as batched tensor-core contractions + row kernels (the product
+    path of the relative-position conformer) and on the CUDA-core cross-check kernels."""
     cfg = VARIANTS[variant]
     model = build_model(cfg)
     stable = cfg.do_stable_layer_norm
@@ -95,7 +96,7 @@ def test_gradient_stages_match_autograd_tiny(P, variant, attn):
     frames = np.array([0, 5, T - 1], dtype=np.int32)
     gx, g, out, NL = reference_grads(model, x, frames)
     eng = P.Engine(model, cfg, max_batch=4)
-    eng.grad_debug(True, simt_attention=attn == "cuda_core")
+    eng.grad_debug(True, simt_attention=attn == "cuda_core", unfused_attention=attn == "contractions")
     grad, val = eng.grad_waveforms(torch.from_numpy(x).cuda(), frames)
     torch.cuda.synchronize()
     H = cfg.hidden_size
