@@ -144,7 +144,8 @@ def test_gradient_stages_match_autograd_tiny(P, variant, attn):
 @pytest.mark.parametrize("name,n,L", [("tiny_group", 35, 9000), ("wav2vec2-base", 32, 16000), ("tiny_group", 3, 183600),
                                       ("wav2vec2-large", 4, 16000), ("tiny_layer_stable", 34, 9000),
                                       ("wav2vec2-large-lv60", 3, 16000), ("tiny_conformer_rel", 34, 9000),
-                                      ("tiny_conformer_rotary", 33, 9000), ("wav2vec2-conformer-large", 3, 16000)])
+                                      ("tiny_conformer_rotary", 33, 9000), ("wav2vec2-conformer-large", 3, 16000),
+                                      ("tiny_group", 2, 330000)])      # T' = 1031: nine key blocks in the fused attention backward
 def test_input_gradients_match_autograd_at_batch_32(P, name, n, L):
     """d (max logit of frame j) / d waveform for >= 32 rows with different target frames (one ragged tile for the tiny
     model: 32 + 3) against torch autograd on the transformers model."""

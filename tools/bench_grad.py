@@ -24,12 +24,14 @@ def main():
     ap.add_argument("--rows", type=int, default=64)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--simt-attention", action="store_true", help="attention backward on the CUDA-core cross-check kernels")
+    ap.add_argument("--unfused-attention", action="store_true", help="attention backward as batched contractions + row kernels "
+                    "(the form before the fused tcgen05 kernel; still the product path of the relative-position conformer)")
     ap.add_argument("--explain-frames", type=int, default=0, help="also time ExpectedGradientsExplainer.shap_values over the "
                     "first N output frames (-1 = all T' frames: the reference's full job) with 200 samples and 5 backgrounds")
     args = ap.parse_args()
     cfg = MODELS[args.model]
     eng = Engine(build_random_init_model(cfg, seed=0), cfg, max_batch=4)
-    eng.grad_debug(False, simt_attention=args.simt_attention)
+    eng.grad_debug(False, simt_attention=args.simt_attention, unfused_attention=args.unfused_attention)
     L = args.samples
     T = eng.num_frames(L)
     x = torch.from_numpy(np.stack([synthetic_clip(L, seed=s) for s in range(4)])).cuda()
@@ -70,7 +72,7 @@ def main():
     fwd_names |= {f"conv{l}" for l in range(1, 8)} | {f"conv{l}_gelu" for l in range(0, 8)}
     fwd = sum(v["ms"] for k, v in prof.items() if k.replace("grad.", "") in fwd_names)
     print(json.dumps({"metric": "expected_gradient_passes_per_sec", "value": args.rows / (ms / 1e3), "unit": "fwd+bwd passes/s",
-                      "model": args.model, "attention_backward": "cuda_core" if args.simt_attention else "tensor_core", "num_samples": L, "frames": T, "rows_per_call": args.rows, "ms_per_call": ms,
+                      "model": args.model, "attention_backward": "cuda_core" if args.simt_attention else ("contractions" if args.unfused_attention or (cfg.kind == "conformer" and cfg.position_embeddings_type == "relative") else "fused_tcgen05"), "num_samples": L, "frames": T, "rows_per_call": args.rows, "ms_per_call": ms,
                       "reference_recorded": {"passes_per_s": 114600 / 5586.0, "source": "evaluation.ipynb:463,513 (batch 1, GPU model not recorded)"},
                       "explain": explain, "profiled_ms": tot, "forward_share": fwd / tot, "top_steps_ms": top,
                       "clip_estimate_s": {"passes": T * 200, "seconds": T * 200 / (args.rows / (ms / 1e3))}}), flush=True)
