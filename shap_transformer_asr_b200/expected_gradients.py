@@ -13,6 +13,11 @@ UNPINNED; what is pinned is the gradient, against torch autograd on the ``transf
 
 with the per-sample gradient rows evaluated by ``Engine.grad_waveforms`` in tiles.  Samples are drawn once per output
 index from a seeded ``numpy`` generator, as shap reseeds per explained output.
+
+Multi-GPU (one process per GPU, ``torch.distributed`` initialised): the passes of different output frames are
+independent, so the OUTPUT FRAMES are split into contiguous blocks over the ranks -- no collective on the data path, every
+rank accumulates only its own columns of phi, and one all-gather at the end assembles ``[D, L]`` on every rank.  Because a
+column is produced by exactly one rank in the same order as on one GPU, the result is bit-identical for any world size.
 """
 from __future__ import annotations
 
@@ -20,6 +25,8 @@ from typing import Optional
 
 import numpy as np
 import torch
+
+from . import dist as wdist
 
 
 def make_background(num_samples: int, num_background: int = 5, seed: Optional[int] = None) -> np.ndarray:
@@ -31,12 +38,14 @@ def make_background(num_samples: int, num_background: int = 5, seed: Optional[in
 class ExpectedGradientsExplainer:
     """phi[L, T'] for the ModelWrapper outputs (max logit per frame) of one clip."""
 
-    def __init__(self, engine, background: np.ndarray, nsamples: int = 200, seed: int = 0, batch: int = 64):
+    def __init__(self, engine, background: np.ndarray, nsamples: int = 200, seed: int = 0, batch: int = 64,
+                 shard_outputs: bool = True):
         self.engine = engine
         self.background = np.ascontiguousarray(background, dtype=np.float32)
         self.nsamples = int(nsamples)
         self.seed = seed
         self.batch = int(batch)
+        self.shard_outputs = bool(shard_outputs)     # split the output frames over the ranks of torch.distributed
 
     def shap_values(self, x, frames=None) -> np.ndarray:
         """x: normalised clip [L] -> attributions [1, L, D] (the reference's on-disk layout, D = T' when ``frames`` is
@@ -61,15 +70,18 @@ class ExpectedGradientsExplainer:
             alpha[d] = rng.uniform(size=S).astype(np.float32)
         rind_t = torch.from_numpy(rind.reshape(-1)).to(eng.device)
         alpha_t = torch.from_numpy(alpha.reshape(-1)).to(eng.device)
-        out_of = torch.arange(D, device=eng.device).repeat_interleave(S)       # row -> output slot
+        rank, world = wdist.rank_world() if self.shard_outputs else (0, 1)
+        d_lo, d_hi = wdist.shard_range(D, rank, world)                         # this rank's output frames
+        out_of = torch.arange(D, device=eng.device).repeat_interleave(S) - d_lo   # row -> local output slot
         row_frames = np.repeat(frames, S)
-        phi = torch.zeros((D, L), dtype=torch.float32, device=eng.device)
-        for r0 in range(0, D * S, self.batch):
-            r1 = min(r0 + self.batch, D * S)
+        phi = torch.zeros((d_hi - d_lo, L), dtype=torch.float32, device=eng.device)
+        for r0 in range(d_lo * S, d_hi * S, self.batch):
+            r1 = min(r0 + self.batch, d_hi * S)
             b = bg[rind_t[r0:r1]]
             delta = xt[None] - b
             xs = torch.addcmul(b, alpha_t[r0:r1, None], delta)
             g, _ = eng.grad_waveforms(xs, row_frames[r0:r1])
             phi.index_add_(0, out_of[r0:r1], g * delta)
         phi /= S
+        phi = wdist.all_gather_rows(phi, D, rank, world)                       # [D, L] on every rank
         return phi.t().contiguous()[None].cpu().numpy()

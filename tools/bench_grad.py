@@ -3,6 +3,8 @@
 114 600 passes in 5586 s for the 11.5 s clip, evaluation.ipynb:463,513 -> 20.5 passes/s at batch 1 on their GPU).
 
     python tools/bench_grad.py [--model wav2vec2-base] [--samples 183600] [--rows 64] [--steps 3]
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/bench_grad.py --explain-frames -1
+        (the output frames of the explained clip are split over the ranks; one all-gather at the end)
 """
 import argparse
 import json
@@ -30,7 +32,10 @@ def main():
                     "first N output frames (-1 = all T' frames: the reference's full job) with 200 samples and 5 backgrounds")
     args = ap.parse_args()
     cfg = MODELS[args.model]
-    eng = Engine(build_random_init_model(cfg, seed=0), cfg, max_batch=4)
+    from shap_transformer_asr_b200 import dist as wdist
+    rank, world = wdist.init_from_env()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    eng = Engine(build_random_init_model(cfg, seed=0), cfg, device=local, max_batch=4)
     eng.grad_debug(False, simt_attention=args.simt_attention, unfused_attention=args.unfused_attention)
     L = args.samples
     T = eng.num_frames(L)
@@ -60,17 +65,23 @@ def main():
         ex = ExpectedGradientsExplainer(eng, make_background(L, 5, seed=0), nsamples=200, seed=0, batch=args.rows)
         clip = synthetic_clip(L)
         torch.cuda.synchronize()
+        wdist.barrier()
         t0 = time.perf_counter()
         phi = ex.shap_values(clip, np.arange(nf, dtype=np.int32))
+        torch.cuda.synchronize()
+        wdist.barrier()
         dt = time.perf_counter() - t0
         explain = {"frames": nf, "samples_per_frame": 200, "passes": nf * 200, "seconds": dt, "passes_per_s": nf * 200 / dt,
                    "shap_shape": list(phi.shape), "finite": bool(np.isfinite(phi).all()),
-                   "reference_recorded_seconds_all_frames": 5586.0 if L == 183600 else None}
+                   "reference_recorded_seconds_all_frames": 5586.0 if L == 183600 else None, "n_gpus": world,
+                   "sharding": "output frames split over the ranks, one all-gather of phi [D, L]"}
     top = {k: round(v["ms"], 2) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:14]}
     fwd_names = {"conv0_stats", "conv0", "featproj_ln", "featproj", "pos_pad", "pos_conv", "pos_add", "encoder_ln", "qkv",
                  "attention", "out_proj", "ln1", "ffn1", "ffn_gelu", "ffn2", "ln2", "lm_head"}
     fwd_names |= {f"conv{l}" for l in range(1, 8)} | {f"conv{l}_gelu" for l in range(0, 8)}
     fwd = sum(v["ms"] for k, v in prof.items() if k.replace("grad.", "") in fwd_names)
+    if rank != 0:
+        return
     print(json.dumps({"metric": "expected_gradient_passes_per_sec", "value": args.rows / (ms / 1e3), "unit": "fwd+bwd passes/s",
                       "model": args.model, "attention_backward": "cuda_core" if args.simt_attention else ("contractions" if args.unfused_attention or (cfg.kind == "conformer" and cfg.position_embeddings_type == "relative") else "fused_tcgen05"), "num_samples": L, "frames": T, "rows_per_call": args.rows, "ms_per_call": ms,
                       "reference_recorded": {"passes_per_s": 114600 / 5586.0, "source": "evaluation.ipynb:463,513 (batch 1, GPU model not recorded)"},
