@@ -54,3 +54,59 @@ def test_one_mufu_gelu_matches_exact_erf_gelu():
     assert np.abs(out - ref).max() < 1.5e-6
     big = np.abs(ref) > 1e-3
     assert (np.abs(out - ref)[big] / np.abs(ref)[big]).max() < 5e-4   # bf16 rounding of the result is 4e-3
+
+
+def test_fused_attention_backward_recurrence_matches_autograd():
+    """attention_bwd_kernel (attention_bwd.cu) restated in numpy, tile by tile: key blocks j outside, query blocks i inside,
+    P = exp2(S c - LSE_i) from the forward's log-sum-exp (no row maximum in the backward), D_i = dO_i . O_i,
+    dS = P (dP - D_i) scale, dV_j += P^T dO_i, dK_j += dS^T Q_i, dQ_i += dS K_j (one partial per key block), P and dS
+    rounded to bf16 before they feed the contractions, padding keys masked to P = 0.  Against torch autograd on
+    softmax(Q K^T / sqrt d) V with an upstream gradient dO."""
+    rng = np.random.default_rng(3)
+    T, d, BLK = 300, 64, 128                    # three blocks, the last one ragged (44 valid rows / keys)
+    q, k, v, dO = (_bf16(rng.standard_normal((T, d)) * s) for s in (1.0, 1.0, 1.0, 0.5))
+    scale = 1.0 / math.sqrt(d)
+    tq, tk, tv = (torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (q, k, v))
+    out = torch.softmax(tq @ tk.T * scale, -1) @ tv
+    out.backward(torch.tensor(dO, dtype=torch.float64))
+    # what the forward kernel leaves behind: O (bf16) and the log2-domain LSE of the scaled scores
+    c = scale * math.log2(math.e)
+    S = q.astype(np.float64) @ k.astype(np.float64).T
+    lse2 = np.log2(np.exp2(S * c - (S * c).max(1, keepdims=True)).sum(1)) + (S * c).max(1)
+    O = _bf16(out.detach().numpy())
+    delta = (dO.astype(np.float64) * O).sum(1)
+    nb = (T + BLK - 1) // BLK
+    pad = nb * BLK
+
+    def padded(a):
+        z = np.zeros((pad, d), np.float32)
+        z[:T] = a
+        return z
+
+    qp, kp, vp, dop = padded(q), padded(k), padded(v), padded(dO)
+    lse_p = np.full(pad, 1e30)
+    lse_p[:T] = lse2
+    del_p = np.zeros(pad)
+    del_p[:T] = delta
+    dq = np.zeros((pad, d), np.float32)
+    dk = np.zeros((pad, d), np.float32)
+    dv = np.zeros((pad, d), np.float32)
+    for j in range(nb):
+        ks, vs = kp[j * BLK:(j + 1) * BLK], vp[j * BLK:(j + 1) * BLK]
+        nvalid = T - j * BLK
+        for i in range(nb):
+            sl = slice(i * BLK, (i + 1) * BLK)
+            s_ij = qp[sl] @ ks.T                                  # tensor cores, fp32 accumulate
+            dp_ij = dop[sl] @ vs.T
+            p = np.exp2(s_ij * np.float32(c) - lse_p[sl, None]).astype(np.float32)
+            p[:, max(nvalid, 0):] = 0.0                           # keys past the clip
+            ds = (p * (dp_ij - del_p[sl, None]) * scale).astype(np.float32)
+            pb, dsb = _bf16(p), _bf16(ds)
+            dv[j * BLK:(j + 1) * BLK] += pb.T @ dop[sl]
+            dk[j * BLK:(j + 1) * BLK] += dsb.T @ qp[sl]
+            dq[sl] += dsb @ ks
+    for mine, ref, name in ((dq[:T], tq.grad, "dQ"), (dk[:T], tk.grad, "dK"), (dv[:T], tv.grad, "dV")):
+        r = ref.numpy()
+        err = np.abs(mine - r).max() / np.abs(r).max()
+        assert err < 6e-3, (name, err)          # bf16 rounding of P / dS / O, nothing else
+    assert np.all(dq[T:] == 0) and np.all(dk[T:] == 0) and np.all(dv[T:] == 0)     # padded rows receive nothing
