@@ -133,6 +133,16 @@ int w2s_vjp_waveforms(w2s_handle* h, const float* x_dev, int64_t n, int64_t L, i
  * cross-check kernels, bit 2: as batched tensor-core contractions + row kernels, instead of the fused tcgen05 kernel.  w2s_grad_peek copies a snapshot out (returns bytes copied, 0 = unknown name, < 0 = buffer
  * too small by that many bytes). */
 int w2s_grad_debug(w2s_handle* h, int on);
+/* DeepLIFT handler rules of feasability_tests/custom_shap_handlers.py:35-80 for the backward pass of w2s_grad_waveforms.
+ * With rules != 0 every call carries PAIRED rows: rows [0, n/2) are explained inputs, row n/2 + r is the reference
+ * (background) row of row r; n even and at most 32.  Reference rows receive no output seed: their gradient rows are zero.
+ *   bit 0: SiLU activations use the rescale multiplier (act(x) - act(ref)) / (x - ref) (shap's nonlinear_1d; the ordinary
+ *          derivative where |x - ref| < 1e-6); LayerNorm / GroupNorm are linear_1d, i.e. the ordinary gradient, like every
+ *          module shap has no handler for (GELUActivation, attention);
+ *   bit 1: the reference's GLU handler as written: GLU inputs that differ from the reference by >= 1e-6 receive
+ *          grad_output * 5e-6 (a placeholder its author left in; off by default).
+ * rules = 0 restores the plain gradient. */
+int w2s_grad_rules(w2s_handle* h, int rules);
 int64_t w2s_grad_peek(w2s_handle* h, const char* name, void* dst_dev, int64_t max_bytes, void* stream);
 
 /* Standalone masker (conformer_test.ipynb:138-141 semantics with keep-bits): materialise

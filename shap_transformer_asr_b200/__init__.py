@@ -13,3 +13,4 @@ from .metrics import eta_raw, eta_raw_segments, greedy_ctc_decode, wer  # noqa: 
 from .sweep import add_noise, explain_test_set, make_test_set  # noqa: F401
 from .modelzoo import build_random_init_model  # noqa: F401
 from .expected_gradients import ExpectedGradientsExplainer, make_background  # noqa: F401
+from .deeplift import DeepLiftExplainer  # noqa: F401

@@ -66,6 +66,7 @@ SIGNATURES = {
     "w2s_vjp_waveforms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
     "w2s_grad_debug": (C.c_int, [C.c_void_p, C.c_int]),
+    "w2s_grad_rules": (C.c_int, [C.c_void_p, C.c_int]),
     "w2s_grad_peek": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "w2s_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "w2s_wls": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p,

@@ -157,6 +157,7 @@ struct w2s_handle {
   bool grad_debug = false, grad_debug_built = false;
   bool grad_attn_simt = false;        // cross-check: attention backward on the CUDA-core kernels (w2s_grad_debug bit 1)
   bool grad_attn_unfused = false;     // cross-check: attention backward as batched contractions + row kernels (bit 2)
+  int grad_rules = 0, grad_rules_built = 0;   // w2s_grad_rules: DeepLIFT handler rules on paired [explained | reference] rows
   std::vector<int32_t> grad_frames_host;
   float *grad_out = nullptr, *grad_out_val = nullptr;
   const float* grad_gout = nullptr;
@@ -1157,6 +1158,13 @@ int w2s_grad_debug(w2s_handle* h, int on) {
   h->grad_debug = snaps;
   h->grad_attn_simt = simt;
   h->grad_attn_unfused = unfused;
+  return 0;
+}
+
+int w2s_grad_rules(w2s_handle* h, int rules) {
+  if (!h) return 1;
+  if (rules & ~3) return fail(h, "grad_rules: unknown rule bits");
+  h->grad_rules = rules;
   return 0;
 }
 

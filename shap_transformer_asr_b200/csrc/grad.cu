@@ -250,7 +250,7 @@ std::string launch_ln_bwd(const void* dy, const void* x, int x_fp32, long long r
 __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ logits, int ldl, int V,
                                                         const __nv_bfloat16* __restrict__ w_head, int n, int T, int H,
                                                         const int* __restrict__ frames, float* __restrict__ dh,
-                                                        float* __restrict__ out_val) {
+                                                        float* __restrict__ out_val, int active) {
   const int b = blockIdx.x;
   const int t = frames[b];
   __shared__ int s_arg;
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
   float* dst = dh + (long long)b * T * H;
   for (long long i = threadIdx.x; i < (long long)T * H; i += blockDim.x) {
     const int tt = (int)(i / H), k = (int)(i - (long long)tt * H);
-    dst[i] = tt == t ? __bfloat162float(w_head[(long long)arg * H + k]) : 0.f;
+    dst[i] = (tt == t && b < active) ? __bfloat162float(w_head[(long long)arg * H + k]) : 0.f;   // reference rows: no seed
   }
 }
 // General vector-Jacobian seed for the same output: out[b, t] = max_v logits[b, t, v] for EVERY frame and an upstream
@@ -332,9 +332,9 @@ std::string launch_head_vjp(const float* logits, int ldl, int V, const __nv_bflo
 }
 
 std::string launch_head_bwd(const float* logits, int ldl, int V, const __nv_bfloat16* w_head, int n, int T, int H,
-                            const int* frames, float* dh, float* out_val, cudaStream_t s) {
+                            const int* frames, float* dh, float* out_val, cudaStream_t s, int active) {
   if (n == 0) return "";
-  head_bwd_kernel<<<n, 256, 0, s>>>(logits, ldl, V, w_head, n, T, H, frames, dh, out_val);
+  head_bwd_kernel<<<n, 256, 0, s>>>(logits, ldl, V, w_head, n, T, H, frames, dh, out_val, active < 0 ? n : active);
   W2S_CUDA_OK(cudaGetLastError());
   return "";
 }
@@ -900,13 +900,32 @@ std::string launch_act_fwd(const __nv_bfloat16* u, __nv_bfloat16* y, long long n
   return "";
 }
 
-// d <- d * act'(u) (* chan_scale[column] when given: the folded BatchNorm scale that sits between u's producer and act)
+// DeepLIFT "rescale" multiplier of an activation (shap's nonlinear_1d, which custom_shap_handlers.py:45-52 assigns to SiLU):
+// (act(x) - act(r)) / (x - r) between the explained row's input x and the paired reference row's r; the ordinary
+// derivative where |x - r| < 1e-6
+__device__ __forceinline__ float act_rescale(float x, float r, int act) {
+  const float dx = x - r;
+  return fabsf(dx) < 1e-6f ? act_grad(x, act) : (apply_act(x, act) - apply_act(r, act)) / dx;
+}
+// d <- d * act'(u) (* chan_scale[column] when given: the folded BatchNorm scale that sits between u's producer and act).
+// pair2 > 0: rows come as [explained | reference] halves (pair2 = bf16 PAIRS per half) and the explained half uses the
+// rescale multiplier against its reference row.
 __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ d,
-                                                       long long n2, int act, const float* __restrict__ chan_scale, int H) {
+                                                       long long n2, int act, const float* __restrict__ chan_scale, int H,
+                                                       long long pair2) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
     const uint32_t a = reinterpret_cast<const uint32_t*>(u)[i];
     const uint32_t g = reinterpret_cast<const uint32_t*>(d)[i];
-    float lo = bf16_lo(g) * act_grad(bf16_lo(a), act), hi = bf16_hi(g) * act_grad(bf16_hi(a), act);
+    float mlo, mhi;
+    if (pair2 > 0 && i < pair2) {
+      const uint32_t r = reinterpret_cast<const uint32_t*>(u)[i + pair2];
+      mlo = act_rescale(bf16_lo(a), bf16_lo(r), act);
+      mhi = act_rescale(bf16_hi(a), bf16_hi(r), act);
+    } else {
+      mlo = act_grad(bf16_lo(a), act);
+      mhi = act_grad(bf16_hi(a), act);
+    }
+    float lo = bf16_lo(g) * mlo, hi = bf16_hi(g) * mhi;
     if (chan_scale) {
       const int c = (int)((2 * i) % H);
       lo *= chan_scale[c];
@@ -916,11 +935,13 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const __nv_bfloat16* __res
   }
 }
 std::string launch_act_bwd(const __nv_bfloat16* u, __nv_bfloat16* d, long long n, int act, const float* chan_scale, int H,
-                           cudaStream_t s) {
+                           cudaStream_t s, int paired) {
   if (n % 2 || H % 2) return "act_bwd: element and channel counts must be even";
+  if (paired && n % 4) return "act_bwd: paired rows need an even row count";
   if (n == 0) return "";
   const long long n2 = n / 2;
-  act_bwd_kernel<<<(unsigned)((n2 + 255) / 256 > 148 * 16 ? 148 * 16 : (n2 + 255) / 256), 256, 0, s>>>(u, d, n2, act, chan_scale, H);
+  act_bwd_kernel<<<(unsigned)((n2 + 255) / 256 > 148 * 16 ? 148 * 16 : (n2 + 255) / 256), 256, 0, s>>>(u, d, n2, act, chan_scale, H,
+                                                                                                     paired ? n2 / 2 : 0);
   W2S_CUDA_OK(cudaGetLastError());
   return "";
 }
@@ -940,18 +961,33 @@ std::string launch_glu_fwd(const __nv_bfloat16* raw, __nv_bfloat16* out, long lo
   return "";
 }
 // d raw[r, 2j] = d out sigmoid(gate);  d raw[r, 2j + 1] = d out value sigmoid(gate) (1 - sigmoid(gate))
+// pair > 0 (elements of the explained half): the reference's GLU handler (custom_shap_handlers.py:63-80, a placeholder its
+// author left in): every GLU input channel whose explained and reference values differ by >= 1e-6 receives
+// grad_output * 5e-6, the others the ordinary gradient
 __global__ void __launch_bounds__(256) glu_bwd_kernel(const __nv_bfloat16* __restrict__ raw, const __nv_bfloat16* __restrict__ dout,
-                                                       __nv_bfloat16* __restrict__ draw, long long n) {
+                                                       __nv_bfloat16* __restrict__ draw, long long n, long long pair) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const uint32_t a = reinterpret_cast<const uint32_t*>(raw)[i];
     const float g = __bfloat162float(dout[i]);
     const float sg = 1.0f / (1.0f + __expf(-bf16_hi(a)));
-    reinterpret_cast<uint32_t*>(draw)[i] = pack_bf16x2(g * sg, g * bf16_lo(a) * sg * (1.0f - sg));
+    float dv = g * sg, dg = g * bf16_lo(a) * sg * (1.0f - sg);
+    if (pair > 0) {
+      const uint32_t r = reinterpret_cast<const uint32_t*>(raw)[i < pair ? i + pair : i - pair];
+      // the saved inputs are bf16: two values that round to the same bf16 number of magnitude m may still differ by up to
+      // m 2^-8 in the fp32 model, so "differs by < 1e-6" is only certain below m = 2.5e-4
+      auto same = [](float x, float y) { return fabsf(x - y) < 1e-6f && fabsf(x) < 2.5e-4f; };
+      if (!same(bf16_lo(a), bf16_lo(r))) dv = g * 5e-6f;
+      if (!same(bf16_hi(a), bf16_hi(r))) dg = g * 5e-6f;
+    }
+    reinterpret_cast<uint32_t*>(draw)[i] = pack_bf16x2(dv, dg);
   }
 }
-std::string launch_glu_bwd(const __nv_bfloat16* raw, const __nv_bfloat16* dout, __nv_bfloat16* draw, long long n, cudaStream_t s) {
+std::string launch_glu_bwd(const __nv_bfloat16* raw, const __nv_bfloat16* dout, __nv_bfloat16* draw, long long n, cudaStream_t s,
+                           int placeholder_paired) {
   if (n == 0) return "";
-  glu_bwd_kernel<<<(unsigned)((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256), 256, 0, s>>>(raw, dout, draw, n);
+  if (placeholder_paired && n % 2) return "glu_bwd: paired rows need an even row count";
+  glu_bwd_kernel<<<(unsigned)((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256), 256, 0, s>>>(raw, dout, draw, n,
+                                                                                                   placeholder_paired ? n / 2 : 0);
   W2S_CUDA_OK(cudaGetLastError());
   return "";
 }

@@ -197,6 +197,14 @@ struct GradBuilder {
     const int QW = (rel ? 4 : 3) * H;                       // q | k | v  or  q+u | q+v | k | v
     const int q_off = 0, k_off = QW - 2 * H, v_off = QW - H;
     const int eact = c.hidden_act == 1 ? ACT_SWISH : ACT_GELU;   // the conformer encoder's activation
+    // DeepLIFT handler rules of the reference (custom_shap_handlers.py:35-80; w2s_grad_rules): rows are [explained | reference]
+    // halves.  bit 0: SiLU modules use the rescale multiplier (shap's nonlinear_1d); LayerNorm / GroupNorm are linear_1d =
+    // the ordinary gradient, and so is every module shap does not know (GELUActivation, the attention matmuls).  bit 1: the
+    // GLU placeholder rule.  The reference rows get no seed (head_bwd), so their gradients stay zero.
+    const int rules = h->grad_rules;
+    if (rules && (n % 2)) return "grad_rules: paired rows need an even number of rows per call (and at most 32)";
+    const int rescale_act = (rules & 1) && eact == ACT_SWISH ? 1 : 0, glu_placeholder = (rules & 2) ? 1 : 0;
+    const int active_rows = rules ? n / 2 : -1;
 
     // ---- buffers ------------------------------------------------------------------------------------------------
     std::vector<bf16*> u(NC), y(NC);
@@ -691,7 +699,7 @@ struct GradBuilder {
       // per-row target frame (w2s_grad_waveforms), or an upstream gradient over all frames (w2s_vjp_waveforms)
       add("head_bwd", [=](cudaStream_t s) {
         if (hh->grad_gout) return launch_head_vjp(lg, ldl, V, hw, nn, T, H, hh->grad_gout, seed, hh->grad_out_val, s);
-        return launch_head_bwd(lg, ldl, V, hw, nn, T, H, fr, seed, hh->grad_out_val, s);
+        return launch_head_bwd(lg, ldl, V, hw, nn, T, H, fr, seed, hh->grad_out_val, s, active_rows);
       });
       if (stable || conf) {   // final encoder LayerNorm: dA = d (residual stream after the last layer)
         const float* g = h->enc_ln_g;
@@ -719,7 +727,7 @@ struct GradBuilder {
         GemmProblem p = PlanBuilder::plain(dS16, rows, H, w2T, I);      // dS16 = bf16 copy of gc
         p.epi.alpha = 0.5f; p.epi.out = dF;
         W2S_TRY(add_gemm(nm + "ffn2_bwd", p));
-        add(nm + "act_bwd", [=](cudaStream_t s) { return launch_act_bwd(usave, dF, rows * I, eact, nullptr, H, s); });
+        add(nm + "act_bwd", [=](cudaStream_t s) { return launch_act_bwd(usave, dF, rows * I, eact, nullptr, H, s, rescale_act); });
         GemmProblem q = PlanBuilder::plain(dF, rows, I, w1T, H);
         q.epi.out = dT; q.epi.out_fp32 = 1;
         W2S_TRY(add_gemm(nm + "ffn1_bwd", q));
@@ -736,9 +744,9 @@ struct GradBuilder {
         const float* sc = w.dw_scale;
         const int kd = c.conv_depthwise_kernel_size;
         const float *flip = gw.dw_flip, *ones = h->grad_ones, *zeros = h->grad_zeros;
-        add(ls + "conv_act_bwd", [=](cudaStream_t s) { return launch_act_bwd(z, dC, rows * H, eact, sc, H, s); });
+        add(ls + "conv_act_bwd", [=](cudaStream_t s) { return launch_act_bwd(z, dC, rows * H, eact, sc, H, s, rescale_act); });
         add(ls + "depthwise_bwd", [=](cudaStream_t s) { return launch_depthwise(dC, nn, T, H, kd, flip, ones, zeros, ACT_NONE, dC2, s); });
-        add(ls + "glu_bwd", [=](cudaStream_t s) { return launch_glu_bwd(raw, dC2, dQKV, rows * H, s); });
+        add(ls + "glu_bwd", [=](cudaStream_t s) { return launch_glu_bwd(raw, dC2, dQKV, rows * H, s, glu_placeholder); });
         GemmProblem q = PlanBuilder::plain(dQKV, rows, 2 * H, gw.pw1T, H);
         q.epi.out = dT; q.epi.out_fp32 = 1;
         W2S_TRY(add_gemm(ls + "pw1_bwd", q));
@@ -928,9 +936,10 @@ struct GradBuilder {
 };
 
 std::string get_grad_plan(w2s_handle* h, int n, long long L, GradPlan** out) {
-  if (h->grad_L != L || h->grad_debug_built != h->grad_debug) {
+  if (h->grad_L != L || h->grad_debug_built != h->grad_debug || h->grad_rules_built != h->grad_rules) {
     cudaDeviceSynchronize();
     h->grad_plans.clear();
+    h->grad_rules_built = h->grad_rules;
     if (h->grad_L != L || h->grad_pos_allocs.empty()) W2S_TRY(grad_prepare_positions(h, (int)num_frames(h->cfg, L, nullptr)));
     h->grad_L = L;
     h->grad_debug_built = h->grad_debug;
@@ -964,6 +973,9 @@ std::string run_grad(w2s_handle* h, const float* x, long long ld, long long L, i
     h->grad_frames_host.assign(frames_host, frames_host + n);
   }
   const int tile = h->grad_tile;
+  if (h->grad_rules && (n > tile || n % 2))
+    return "grad_rules: paired [explained | reference] rows must come as one tile (an even number of rows, at most " +
+           std::to_string(tile) + ")";
   for (int64_t k0 = 0; k0 < n; k0 += tile) {
     const int nt = (int)((n - k0) < tile ? (n - k0) : tile);
     GradPlan* pl = nullptr;

@@ -165,7 +165,7 @@ std::string launch_conv0_ln_bwd(const __nv_bfloat16* du, const __nv_bfloat16* u,
                                 int kw, int stride, const float* w, const float* gamma, const float* beta, float* g, float* dx,
                                 long long ld, cudaStream_t s);
 std::string launch_head_bwd(const float* logits, int ldl, int V, const __nv_bfloat16* w_head, int n, int T, int H,
-                            const int* frames, float* dh, float* out_val, cudaStream_t s);
+                            const int* frames, float* dh, float* out_val, cudaStream_t s, int active = -1);
 std::string launch_head_vjp(const float* logits, int ldl, int V, const __nv_bfloat16* w_head, int n, int T, int H,
                             const float* gout, float* dh, float* out_all, cudaStream_t s);
 std::string launch_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx, int B, int T, int H, int heads, float scale,
@@ -184,10 +184,12 @@ std::string launch_conv0_bwd(const __nv_bfloat16* du, const __nv_bfloat16* u, in
                              float* dx, long long ld, cudaStream_t s);
 // conformer encoder pieces of the gradient path
 std::string launch_act_fwd(const __nv_bfloat16* u, __nv_bfloat16* y, long long n, int act, cudaStream_t s);
+// paired: rows are [explained | reference] halves and the explained half uses the DeepLIFT rescale multiplier
 std::string launch_act_bwd(const __nv_bfloat16* u, __nv_bfloat16* d, long long n, int act, const float* chan_scale, int H,
-                           cudaStream_t s);
+                           cudaStream_t s, int paired = 0);
 std::string launch_glu_fwd(const __nv_bfloat16* raw, __nv_bfloat16* out, long long n, cudaStream_t s);
-std::string launch_glu_bwd(const __nv_bfloat16* raw, const __nv_bfloat16* dout, __nv_bfloat16* draw, long long n, cudaStream_t s);
+std::string launch_glu_bwd(const __nv_bfloat16* raw, const __nv_bfloat16* dout, __nv_bfloat16* draw, long long n, cudaStream_t s,
+                           int placeholder_paired = 0);
 std::string launch_rel_shift_add(float* S, const float* BD, int BH, int T, int Tp, int Rp, cudaStream_t s);
 std::string launch_rel_unshift(const __nv_bfloat16* dS, __nv_bfloat16* dBD, int BH, int T, int Tp, int Rp, cudaStream_t s);
 std::string launch_flip_taps(const float* src, float* dst, int k, int H, cudaStream_t s);

@@ -219,6 +219,13 @@ class Engine:
         as batched tensor-core contractions + row kernels, instead of the fused tcgen05 kernel."""
         self.lib.w2s_grad_debug(self._h, int(bool(snapshots)) | (2 if simt_attention else 0) | (4 if unfused_attention else 0))
 
+    GRAD_TILE_ROWS = 32       # rows per device tile of grad_waveforms (paired rows must fit one tile)
+
+    def grad_rules(self, rescale_silu: bool = False, glu_placeholder: bool = False):
+        """DeepLIFT handler rules of feasability_tests/custom_shap_handlers.py for the following grad_waveforms calls, whose
+        rows must then be [explained | reference] halves (even count, at most GRAD_TILE_ROWS); both False: plain gradient."""
+        self._check(self.lib.w2s_grad_rules(self._h, (1 if rescale_silu else 0) | (2 if glu_placeholder else 0)), "w2s_grad_rules")
+
     def grad_peek(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
         """Snapshot of an intermediate gradient of the last grad_waveforms call (tests; needs grad_debug(True))."""
         out = torch.empty(shape, dtype=dtype, device=self.device)

@@ -266,3 +266,86 @@ def test_model_wrapper_output_is_differentiable_as_in_the_reference(P):
     # without requires_grad the wrapper stays on the evaluation path (no autograd node, no saved activations)
     assert not wrap(torch.from_numpy(x).cuda()).requires_grad
     eng.close()
+
+
+def deeplift_reference_grads(model, rows, frames, rescale_silu=True, glu_placeholder=False):
+    """The handler rules of feasability_tests/custom_shap_handlers.py:35-80 as torch backward hooks on the transformers
+    model (what shap's PyTorchDeep does with them): `rows` = [explained | reference] halves; SiLU modules use the rescale
+    multiplier (nonlinear_1d), GLU the reference's placeholder, everything else the ordinary gradient (linear_1d /
+    no handler).  Returns the rule-modified input gradients of the explained half."""
+    saved, hooks = {}, []
+
+    def keep(mod, inp, out):
+        saved[mod] = (inp[0].detach(), out.detach())
+
+    def silu_rule(mod, grad_in, grad_out):
+        xin, y = saved[mod]
+        h = xin.shape[0] // 2
+        dx, dy = xin[:h] - xin[h:], y[:h] - y[h:]
+        rep = [2] + [1] * (dx.dim() - 1)
+        safe = torch.where(dx.abs() < 1e-6, torch.ones_like(dx), dx)
+        return (torch.where(dx.abs().repeat(rep) < 1e-6, grad_in[0], grad_out[0] * (dy / safe).repeat(rep)),)
+
+    def glu_rule(mod, grad_in, grad_out):
+        xin, _ = saved[mod]
+        h = xin.shape[0] // 2
+        dx = xin[:h] - xin[h:]
+        rep0 = [2] + [1] * (dx.dim() - 1)
+        rep1 = [1, 2] + [1] * (grad_out[0].dim() - 2)
+        return (torch.where(dx.abs().repeat(rep0) < 1e-6, grad_in[0], grad_out[0].repeat(rep1) * 5e-6),)
+
+    for mod in model.modules():
+        if rescale_silu and isinstance(mod, torch.nn.SiLU):
+            hooks += [mod.register_forward_hook(keep), mod.register_full_backward_hook(silu_rule)]
+        if glu_placeholder and isinstance(mod, torch.nn.GLU):
+            hooks += [mod.register_forward_hook(keep), mod.register_full_backward_hook(glu_rule)]
+    xt = torch.tensor(rows, requires_grad=True)
+    n = len(rows) // 2
+    logits = model(xt).logits
+    out = logits.max(-1).values[torch.arange(n), torch.as_tensor(frames[:n], dtype=torch.long)]   # explained half only
+    out.sum().backward()
+    for h in hooks:
+        h.remove()
+    return xt.grad.detach().numpy()[:n], out.detach().numpy()
+
+
+@pytest.mark.parametrize("variant,glu", [("tiny_conformer_rel", False), ("tiny_conformer_rotary", False),
+                                         ("tiny_conformer_rel", True), ("tiny_group", False)])
+def test_deeplift_handler_rules_match_torch_hooks(P, variant, glu):
+    """f4 of SURVEY.md 8: the reference's DeepLIFT handler rules (rescale on SiLU, linear pass-through on the norms, the GLU
+    placeholder as an option) on the device backward pass, against the same rules as torch backward hooks; then the
+    explainer built on them (mean over the background of modified-gradient x (input - reference), layout [1, L, D]).
+    For the GELU-only Wav2Vec2ForCTC the rules must change nothing."""
+    cfg = VARIANTS[variant]
+    model = build_model(cfg)
+    rng = np.random.default_rng(5)
+    L, B = 6000, 5
+    x = rng.standard_normal(L).astype(np.float32)
+    bg = P.make_background(L, B, seed=4) + 0.3 * rng.standard_normal((B, L)).astype(np.float32)   # references far from zero too
+    T = cfg.num_frames(L)
+    frames = np.array([3, T - 2], dtype=np.int32)
+    rows = np.concatenate([np.repeat(x[None], 2 * B, 0), np.tile(bg, (2, 1))]).astype(np.float32)   # 10 explained | 10 references
+    row_frames = np.concatenate([np.repeat(frames, B)] * 2).astype(np.int32)
+    ref_g, ref_out = deeplift_reference_grads(model, rows, row_frames, True, glu)
+    plain_g, _ = deeplift_reference_grads(model, rows, row_frames, False, False)
+    eng = P.Engine(model, cfg, max_batch=4)
+    eng.grad_rules(True, glu)
+    g, val = eng.grad_waveforms(torch.from_numpy(rows).cuda(), row_frames)
+    eng.grad_rules(False, False)
+    g = g.cpu().numpy()
+    assert np.all(g[2 * B:] == 0)                       # reference rows carry no seed
+    e = rel(g[:2 * B], ref_g)
+    changed = rel(ref_g, plain_g)                       # how much the rules move the gradient at all
+    print(f"{variant} glu_placeholder={glu}: rule-modified gradient max rel err {e:.3e} "
+          f"(the rules change the plain gradient by {changed:.3e} of its maximum)")
+    assert e < GRAD_TOL and cosine(g[:2 * B], ref_g) > 0.998
+    if variant == "tiny_group":
+        assert changed == 0.0                           # GELU-only model: nothing to rescale
+    else:
+        assert changed > 0.02                           # the test would not notice a missing rule otherwise
+    assert np.abs(val.cpu().numpy()[:2 * B] - ref_out).max() < 0.025 * np.abs(ref_out).max() + 1e-3
+    phi = P.DeepLiftExplainer(eng, bg, rescale_silu=True, glu_placeholder=glu).shap_values(x, frames)
+    assert phi.shape == (1, L, 2)
+    want = (ref_g.reshape(2, B, L) * (x[None, None] - bg[None])).mean(1).T
+    assert rel(phi[0], want) < 2 * GRAD_TOL and cosine(phi[0], want) > 0.995
+    eng.close()
