@@ -2,13 +2,15 @@
 // shap_calculation.py:125-162): forward pass with saved activations + backward pass to the waveform, for one batch tile.
 // Included by api.cu inside its anonymous namespace (it needs w2s_handle / Step / PlanBuilder::plain).
 //
-// Scope of this slice: Wav2Vec2ForCTC -- both front ends (feat_extract_norm = "group" / "layer") and both encoder orders
+// Scope: Wav2Vec2ForCTC -- both front ends (feat_extract_norm = "group" / "layer") and both encoder orders
 // (post-LN: facebook/wav2vec2-base-960h, the model the reference runs, and wav2vec2-large-960h; stable-LN: the
 // wav2vec2-large-lv60 family), GELU; and Wav2Vec2ConformerForCTC (macaron feed-forwards, relative-position or rotary
 // attention, GLU / depthwise / BatchNorm convolution module; swish or GELU).  Only d(output)/d(input) is
 // computed: no weight gradients.  Every dense backward contraction dX = dY W runs on the tcgen05 contraction kernels of
-// the forward pass with pre-transposed weights; attention backward and the normalisation / activation / conv-gather
-// steps are CUDA-core kernels (grad.cu).
+// the forward pass with pre-transposed weights; attention backward is one fused tcgen05 kernel (attention_bwd.cu; the
+// relative-position conformer: seven batched contractions + row kernels); the normalisation / activation / conv-gather
+// steps are CUDA-core kernels (grad.cu).  w2s_grad_rules switches the activation / GLU steps to the reference's DeepLIFT
+// handler rules on paired [explained | reference] rows.
 #pragma once
 
 struct GradLayerBuf {
