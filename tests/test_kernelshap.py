@@ -226,3 +226,46 @@ def test_expected_gradients_estimator_on_a_mock_engine():
     # completeness: sum_i phi_ij = f_j(x) - E f_j(bg) for this model, up to sampling noise
     gap = phi[0].sum(0) - (0.5 * a * (x ** 2).sum() - 0.5 * a * (bg ** 2).sum(1).mean())
     assert np.abs(gap).max() < 0.05 * np.abs(0.5 * a * (x ** 2).sum()).max()
+
+
+def test_deeplift_explainer_pairs_rows_and_averages_on_a_mock_engine():
+    """DeepLiftExplainer (the reference's shap.DeepExplainer + custom_shap_handlers.py loop) on a mock engine: every device
+    call carries [explained | reference] halves of at most GRAD_TILE_ROWS rows, the rules are switched on for the calls and
+    off afterwards, and phi = mean over the background of gradient x (x - reference) in the layout [1, L, D]."""
+    import torch
+    from shap_transformer_asr_b200.deeplift import DeepLiftExplainer
+    L, D, B = 40, 7, 5
+    a = np.linspace(0.5, 2.0, D).astype(np.float32)
+    log = []
+
+    class Mock:
+        device = torch.device("cpu")
+        GRAD_TILE_ROWS = 32
+        rules = (False, False)
+
+        def num_frames(self, n):
+            return D
+
+        def grad_rules(self, rescale_silu=False, glu_placeholder=False):
+            Mock.rules = (rescale_silu, glu_placeholder)
+
+        def grad_waveforms(self, rows, frames):
+            n = rows.shape[0]
+            assert Mock.rules == (True, False) and n % 2 == 0 and n <= 32
+            h = n // 2
+            assert np.array_equal(np.asarray(frames)[:h], np.asarray(frames)[h:])
+            log.append(n)
+            # a toy "rule-modified gradient": a_j * (x + ref) for the explained half, zero for the reference half
+            aj = torch.from_numpy(a[np.asarray(frames)[:h]]).float()
+            g = torch.zeros_like(rows)
+            g[:h] = aj[:, None] * (rows[:h] + rows[h:])
+            return g, torch.zeros(n)
+
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(L).astype(np.float32)
+    bg = rng.standard_normal((B, L)).astype(np.float32)
+    phi = DeepLiftExplainer(Mock(), bg).shap_values(x)
+    assert phi.shape == (1, L, D) and Mock.rules == (False, False)
+    want = np.stack([(a[j] * (x[None] + bg) * (x[None] - bg)).mean(0) for j in range(D)], 1)
+    assert np.allclose(phi[0], want, rtol=1e-5, atol=1e-6)
+    assert log == [30, 30, 10]          # three output frames x five pairs per call, then the last frame
