@@ -509,7 +509,10 @@ constexpr int AT_MAXV = 32;   // T <= 1024
 template <bool DS>   // false: P = softmax(S);  true: dS = P (dP - sum_j P dP), with `in16` = P and `in32` = dP
 __global__ void __launch_bounds__(256) attn_rows_t_kernel(const float* __restrict__ in32, const __nv_bfloat16* __restrict__ in16,
                                                            int T, int Tp, __nv_bfloat16* __restrict__ out,
-                                                           __nv_bfloat16* __restrict__ outT) {
+                                                           __nv_bfloat16* __restrict__ outT, const float* __restrict__ bd,
+                                                           int Rp) {
+  // bd (softmax only): the conformer's relative-position scores [bh, T, Rp]; S[i, j] += bd[i, T - 1 - i + j] (the HF
+  // rel_shift as index arithmetic, modeling_wav2vec2_conformer.py:540-553) while the row is read
   extern __shared__ __nv_bfloat16 tile[];   // [32][Tp + 2]
   const int pitch = Tp + 2;
   const long long bh = blockIdx.y;
@@ -523,10 +526,11 @@ __global__ void __launch_bounds__(256) attn_rows_t_kernel(const float* __restric
     float v[AT_MAXV];
     if constexpr (!DS) {
       float mx = -INFINITY;
+      const float* bdrow = bd ? bd + (bh * (long long)T + i) * Rp + (T - 1 - i) : nullptr;
 #pragma unroll
       for (int c = 0; c < AT_MAXV; ++c) {
         const int j = c * 32 + lane;
-        v[c] = j < T ? row32[j] : -INFINITY;
+        v[c] = j < T ? row32[j] + (bdrow ? bdrow[j] : 0.f) : -INFINITY;
         mx = fmaxf(mx, v[c]);
       }
       mx = warp_max(mx);
@@ -570,7 +574,8 @@ __global__ void __launch_bounds__(256) attn_rows_t_kernel(const float* __restric
     if (lane < nrow) outT[base + (long long)j * Tp + i0 + lane] = tile[lane * pitch + j];
 }
 
-std::string launch_attn_softmax_t(const float* S, int BH, int T, int Tp, __nv_bfloat16* P, __nv_bfloat16* PT, cudaStream_t s) {
+std::string launch_attn_softmax_t(const float* S, int BH, int T, int Tp, __nv_bfloat16* P, __nv_bfloat16* PT, cudaStream_t s,
+                                  const float* bd, int Rp) {
   if (BH == 0) return "";
   if (T > 32 * AT_MAXV) return "attention backward: more than 1024 frames are not supported yet";
   const size_t smem = (size_t)32 * (Tp + 2) * sizeof(__nv_bfloat16);
@@ -580,7 +585,7 @@ std::string launch_attn_softmax_t(const float* S, int BH, int T, int Tp, __nv_bf
     W2S_CUDA_OK(cudaFuncSetAttribute(attn_rows_t_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
     attr = true;
   }
-  attn_rows_t_kernel<false><<<dim3((T + 31) / 32, BH), 256, smem, s>>>(S, nullptr, T, Tp, P, PT);
+  attn_rows_t_kernel<false><<<dim3((T + 31) / 32, BH), 256, smem, s>>>(S, nullptr, T, Tp, P, PT, bd, Rp);
   W2S_CUDA_OK(cudaGetLastError());
   return "";
 }
@@ -589,7 +594,7 @@ std::string launch_attn_ds_t(const __nv_bfloat16* P, const float* dP, int BH, in
   if (BH == 0) return "";
   if (T > 32 * AT_MAXV) return "attention backward: more than 1024 frames are not supported yet";
   const size_t smem = (size_t)32 * (Tp + 2) * sizeof(__nv_bfloat16);
-  attn_rows_t_kernel<true><<<dim3((T + 31) / 32, BH), 256, smem, s>>>(dP, P, T, Tp, dS, dST);
+  attn_rows_t_kernel<true><<<dim3((T + 31) / 32, BH), 256, smem, s>>>(dP, P, T, Tp, dS, dST, nullptr, 0);
   W2S_CUDA_OK(cudaGetLastError());
   return "";
 }
@@ -992,22 +997,7 @@ std::string launch_glu_bwd(const __nv_bfloat16* raw, const __nv_bfloat16* dout, 
   return "";
 }
 
-// relative positions: S[bh, i, j] += BD[bh, i, T - 1 - i + j]  (the HF rel_shift as index arithmetic, :540-553).
-// One CTA per (query row, batch x head): no index division, contiguous reads and writes.
-__global__ void __launch_bounds__(128) rel_shift_add_kernel(float* __restrict__ S, const float* __restrict__ BD, int T, int Tp,
-                                                             int Rp) {
-  const long long row = (long long)blockIdx.y * T + blockIdx.x;
-  const int i = blockIdx.x;
-  float* s = S + row * Tp;
-  const float* bd = BD + row * Rp + (T - 1 - i);
-  for (int j = threadIdx.x; j < T; j += blockDim.x) s[j] += bd[j];
-}
-std::string launch_rel_shift_add(float* S, const float* BD, int BH, int T, int Tp, int Rp, cudaStream_t s) {
-  if (BH == 0) return "";
-  rel_shift_add_kernel<<<dim3(T, BH), 128, 0, s>>>(S, BD, T, Tp, Rp);
-  W2S_CUDA_OK(cudaGetLastError());
-  return "";
-}
+// relative positions: the forward gather S[bh, i, j] += BD[bh, i, T - 1 - i + j] is folded into attn_rows_t_kernel;
 // the transpose of that gather: dBD[bh, i, r] = dS[bh, i, r - (T - 1) + i] where that key exists, else 0 (all Rp columns
 // written, eight per thread as one 16-byte store)
 __global__ void __launch_bounds__(128) rel_unshift_kernel(const __nv_bfloat16* __restrict__ dS, __nv_bfloat16* __restrict__ dBD,

@@ -646,9 +646,9 @@ struct GradBuilder {
           p.epi.out = aBD; p.epi.out_fp32 = 1; p.epi.alpha = 0.125f;
           p.epi.ldg = (long long)T * Rp; p.epi.ldb = (long long)heads * T * Rp; p.epi.ldm = Rp;
           W2S_TRY(add_gemm(ls + "attn_pos_scores", p));
-          add(ls + "attn_rel_shift", [=](cudaStream_t s) { return launch_rel_shift_add(aS, aBD, nn * heads, T, Tp, Rp, s); });
         }
-        add(ls + "attn_softmax", [=](cudaStream_t s) { return launch_attn_softmax_t(aS, nn * heads, T, Tp, aP, aPT, s); });
+        const float* bd = pos_proj ? aBD : nullptr;   // the rel-shift is folded into the softmax kernel's row read
+        add(ls + "attn_softmax", [=](cudaStream_t s) { return launch_attn_softmax_t(aS, nn * heads, T, Tp, aP, aPT, s, bd, Rp); });
         {
           GemmProblem p = from_rows(dC, H);                      // dP = dO V^T
           w_rows_of(p, qkv + v_off, QW);

@@ -170,7 +170,9 @@ std::string launch_head_vjp(const float* logits, int ldl, int V, const __nv_bflo
                             const float* gout, float* dh, float* out_all, cudaStream_t s);
 std::string launch_attn_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* dctx, int B, int T, int H, int heads, float scale,
                             __nv_bfloat16* dqkv, float* stats, cudaStream_t s);
-std::string launch_attn_softmax_t(const float* S, int BH, int T, int Tp, __nv_bfloat16* P, __nv_bfloat16* PT, cudaStream_t s);
+// bd != null: relative-position scores [BH, T, Rp] added with the rel-shift index arithmetic while the row is read
+std::string launch_attn_softmax_t(const float* S, int BH, int T, int Tp, __nv_bfloat16* P, __nv_bfloat16* PT, cudaStream_t s,
+                                  const float* bd = nullptr, int Rp = 0);
 std::string launch_attn_ds_t(const __nv_bfloat16* P, const float* dP, int BH, int T, int Tp, __nv_bfloat16* dS,
                              __nv_bfloat16* dST, cudaStream_t s);
 std::string launch_head_transpose(const __nv_bfloat16* src, int ld, int off, int B, int T, int Tp, int heads, __nv_bfloat16* dst,
@@ -190,7 +192,6 @@ std::string launch_act_bwd(const __nv_bfloat16* u, __nv_bfloat16* d, long long n
 std::string launch_glu_fwd(const __nv_bfloat16* raw, __nv_bfloat16* out, long long n, cudaStream_t s);
 std::string launch_glu_bwd(const __nv_bfloat16* raw, const __nv_bfloat16* dout, __nv_bfloat16* draw, long long n, cudaStream_t s,
                            int placeholder_paired = 0);
-std::string launch_rel_shift_add(float* S, const float* BD, int BH, int T, int Tp, int Rp, cudaStream_t s);
 std::string launch_rel_unshift(const __nv_bfloat16* dS, __nv_bfloat16* dBD, int BH, int T, int Tp, int Rp, cudaStream_t s);
 std::string launch_flip_taps(const float* src, float* dst, int k, int H, cudaStream_t s);
 std::string launch_fill_f32(float* dst, float v, int n, cudaStream_t s);
