@@ -158,7 +158,12 @@ struct w2s_handle {
   bool grad_attn_simt = false;        // cross-check: attention backward on the CUDA-core kernels (w2s_grad_debug bit 1)
   bool grad_attn_unfused = false;     // cross-check: attention backward as batched contractions + row kernels (bit 2)
   int grad_rules = 0, grad_rules_built = 0;   // w2s_grad_rules: DeepLIFT handler rules on paired [explained | reference] rows
-  std::vector<int32_t> grad_frames_host;
+  // target frames of a tile travel through a ring of pinned slots (a pageable source would make every call wait for the
+  // stream); a slot is reused only after the copy that read it has completed
+  static constexpr int kFrameSlots = 8;
+  int32_t* grad_frames_pinned = nullptr;          // [kFrameSlots][grad_tile]
+  cudaEvent_t grad_frames_done[kFrameSlots] = {};
+  unsigned grad_frames_next = 0;
   float *grad_out = nullptr, *grad_out_val = nullptr;
   const float* grad_gout = nullptr;
 
@@ -177,6 +182,9 @@ struct w2s_handle {
     plans.clear();
     grad_plans.clear();
     for (void* p : grad_pos_allocs) cudaFree(p);
+    if (grad_frames_pinned) cudaFreeHost(grad_frames_pinned);
+    for (auto& e : grad_frames_done)
+      if (e) cudaEventDestroy(e);
     if (cap_stream) cudaStreamDestroy(cap_stream);
     if (dyn_dev) cudaFree(dyn_dev);
     if (clip) cudaFree(clip);

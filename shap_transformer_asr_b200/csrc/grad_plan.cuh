@@ -972,7 +972,10 @@ std::string run_grad(w2s_handle* h, const float* x, long long ld, long long L, i
     for (int64_t i = 0; i < n; ++i)
       if (frames_host[i] < 0 || frames_host[i] >= T)
         return "target frame " + std::to_string(frames_host[i]) + " outside the clip's " + std::to_string(T) + " frames";
-    h->grad_frames_host.assign(frames_host, frames_host + n);
+    if (!h->grad_frames_pinned) {
+      W2S_CUDA_OK(cudaHostAlloc(&h->grad_frames_pinned, sizeof(int32_t) * w2s_handle::kFrameSlots * h->grad_tile, cudaHostAllocDefault));
+      for (auto& e : h->grad_frames_done) W2S_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
   }
   const int tile = h->grad_tile;
   if (h->grad_rules && (n > tile || n % 2))
@@ -985,8 +988,14 @@ std::string run_grad(w2s_handle* h, const float* x, long long ld, long long L, i
     DynArgs d{};
     d.x = x + k0 * ld; d.ld = ld;
     set_dyn_kernel<<<1, 1, 0, s>>>(h->dyn_dev, d);
-    if (frames_host)
-      W2S_CUDA_OK(cudaMemcpyAsync(pl->frames, h->grad_frames_host.data() + k0, sizeof(int) * nt, cudaMemcpyHostToDevice, s));
+    if (frames_host) {
+      const unsigned slot = h->grad_frames_next++ % w2s_handle::kFrameSlots;
+      W2S_CUDA_OK(cudaEventSynchronize(h->grad_frames_done[slot]));   // the copy that last read this slot (no-op when unused)
+      int32_t* src = h->grad_frames_pinned + (size_t)slot * h->grad_tile;
+      std::memcpy(src, frames_host + k0, sizeof(int32_t) * nt);
+      W2S_CUDA_OK(cudaMemcpyAsync(pl->frames, src, sizeof(int) * nt, cudaMemcpyHostToDevice, s));
+      W2S_CUDA_OK(cudaEventRecord(h->grad_frames_done[slot], s));
+    }
     h->grad_out = grad + k0 * L;
     h->grad_gout = gout ? gout + k0 * T : nullptr;
     h->grad_out_val = out_val ? out_val + k0 * (gout ? T : 1) : nullptr;
